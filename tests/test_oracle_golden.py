@@ -1,0 +1,147 @@
+"""Pin oracle/oracle.py against vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only.  Element-wise ops must match bit for bit when run with
+the torch build that generated them; GEMM-bearing paths get a few-ulp tolerance because MKL's
+blocking (and therefore summation order) depends on the host CPU."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+T = torch.from_numpy
+
+
+def close(a, b, rtol=0.0, atol=0.0):
+    a = a.detach().numpy() if isinstance(a, torch.Tensor) else a
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+def params_from(golden, prefix):
+    return {k[len(prefix):]: T(golden[k].copy()) for k in golden.files if k.startswith(prefix)}
+
+
+@pytest.mark.parametrize("tag", ["small", "tile"])
+def test_get_rays(golden, tag):
+    H, W, focal = golden[f"rays_{tag}_HWf"]
+    ro, rd = O.get_rays(int(H), int(W), float(focal), T(golden[f"rays_{tag}_c2w"]))
+    close(ro, golden[f"rays_{tag}_o"])
+    close(rd, golden[f"rays_{tag}_d"], rtol=1e-6, atol=1e-7)
+
+
+def test_get_rays_full_frame_rows(golden):
+    _, rd = O.get_rays(100, 100, float(np.float32(138.88888549804688)), T(golden["rays_small_c2w"]))
+    close(rd[T(golden["rays_full_pick"])], golden["rays_full_d"], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("S", [8, 64])
+def test_stratified(golden, S):
+    ro, rd = T(golden["strat_ro"]), T(golden["strat_rd"])
+    z, pts = O.stratified(2.0, 6.0, S, ro, rd, None)
+    close(z, golden[f"strat_det_S{S}_z"])
+    close(pts, golden[f"strat_det_S{S}_pts"])
+    z, pts = O.stratified(2.0, 6.0, S, ro, rd, T(golden[f"strat_rand_S{S}_u"]))
+    close(z, golden[f"strat_rand_S{S}_z"])
+    close(pts, golden[f"strat_rand_S{S}_pts"])
+
+
+def test_stratified_first_last_bins_half_width(golden):
+    z = golden["strat_det_S8_z"][0]
+    zr = golden["strat_rand_S8_z"]
+    step = z[1] - z[0]
+    assert np.all(zr[:, 0] <= z[0] + step / 2 + 1e-6) and np.all(zr[:, 0] >= z[0])
+    assert np.all(zr[:, -1] >= z[-1] - step / 2 - 1e-6) and np.all(zr[:, -1] <= z[-1])
+
+
+def test_stratified_tensor_near_far(golden):
+    ro, rd = T(golden["strat_ro"]), T(golden["strat_rd"])
+    z, _ = O.stratified(T(golden["strat_tensor_near"]), T(golden["strat_tensor_far"]), 8, ro, rd, None)
+    close(z, golden["strat_tensor_z"])
+
+
+@pytest.mark.parametrize("L", [2, 6, 10])
+@pytest.mark.parametrize("inc", [True, False])
+def test_posenc(golden, L, inc):
+    e = O.posenc(T(golden["enc_x"]), L, inc)
+    assert e.shape[-1] == O.posenc_dim(L, inc)
+    close(e, golden[f"enc_L{L}_{int(inc)}"])
+
+
+def test_posenc_rejects_wrong_width():
+    with pytest.raises(AssertionError):
+        O.posenc(torch.zeros(4, 2))
+
+
+def test_mlp_repo(golden):
+    p = params_from(golden, "mlp_repo_p_")
+    assert [tuple(v.shape) for v in p.values()] == [s for _, s in O.mlp_param_shapes(63, 128, 4, 2)]
+    assert sum(v.numel() for v in p.values()) == 66308
+    c, s = O.mlp_forward(p, T(golden["mlp_repo_x"]), 4, 2)
+    close(c, golden["mlp_repo_rgb"], rtol=2e-6, atol=2e-7)
+    close(s, golden["mlp_repo_sigma"], rtol=2e-6, atol=2e-6)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_mlp_variants(golden, tag):
+    ind, hid, dep, sk = (int(v) for v in golden[f"mlp_{tag}_cfg"])
+    p = params_from(golden, f"mlp_{tag}_p_")
+    assert list(p.keys()) == [k for k, _ in O.mlp_param_shapes(ind, hid, dep, sk)]
+    c, s = O.mlp_forward(p, T(golden[f"mlp_{tag}_x"]), dep, sk)
+    close(c, golden[f"mlp_{tag}_rgb"], rtol=2e-6, atol=2e-7)
+    close(s, golden[f"mlp_{tag}_sigma"], rtol=2e-6, atol=2e-6)
+
+
+@pytest.mark.parametrize("wb", [1, 0])
+def test_composite_forward_backward(golden, wb):
+    rgb, sig, z, rd = (T(golden[k]) for k in ("vol_rgb", "vol_sigma", "vol_z", "vol_rd"))
+    c, d, a, w = O.composite(rgb, sig, z, rd, bool(wb))
+    close(c, golden[f"vol{wb}_c"], rtol=1e-6, atol=1e-7)
+    close(d, golden[f"vol{wb}_d"], rtol=1e-6, atol=1e-7)
+    close(a, golden[f"vol{wb}_a"], rtol=1e-6, atol=1e-7)
+    close(w, golden[f"vol{wb}_w"], rtol=1e-6, atol=1e-12)
+    # edge rows: sigma == 0 -> white / zero acc; opaque -> acc == 1
+    assert np.allclose(golden["vol1_a"][1], 0.0) and np.allclose(golden["vol1_c"][1], 1.0)
+    assert np.allclose(golden["vol1_a"][2], 1.0, atol=1e-6)
+    gC, gD, gA, gW = (T(golden[k]) for k in ("vol_gC", "vol_gD", "vol_gA", "vol_gW"))
+    d_rgb, d_sig = O.composite_backward(rgb.double(), sig.double(), z.double(), rd.double(),
+                                        gC.double(), gD.double(), gA.double(), gW.double(), bool(wb))
+    close(d_rgb, golden[f"vol{wb}_grgb"], rtol=1e-5, atol=1e-7)
+    # fp32 autograd of cumprod divides by q; compare where the reference's own value is well conditioned
+    ref = golden[f"vol{wb}_gsigma"]
+    np.testing.assert_allclose(d_sig.numpy(), ref, rtol=2e-4, atol=1e-5 * np.abs(ref).max())
+
+
+def test_psnr(golden):
+    close(O.mse2psnr(T(golden["psnr_in"])), golden["psnr_out"])
+
+
+def test_three_train_steps(golden):
+    """Reference loop body (train.py:108-128) replayed: loss, grads and Adam-updated parameters."""
+    p = params_from(golden, "train_p0_")
+    m = {k: torch.zeros_like(v) for k, v in p.items()}
+    v = {k: torch.zeros_like(x) for k, x in p.items()}
+    ro_all, rd_all, pix = T(golden["train_ro_all"]), T(golden["train_rd_all"]), T(golden["train_pix"])
+    for step in range(3):
+        inds = T(golden[f"train_s{step}_inds"])
+        loss, g, (comp, dep, acc) = O.loss_and_grads(p, ro_all[inds], rd_all[inds], pix[inds], 2.0, 6.0, 16,
+                                                     T(golden[f"train_s{step}_u"]), num_freqs=4)
+        close(loss, golden[f"train_s{step}_loss"], rtol=1e-5)
+        close(comp, golden[f"train_s{step}_comp"], rtol=1e-5, atol=1e-6)
+        close(dep, golden[f"train_s{step}_depth"], rtol=1e-5, atol=1e-6)
+        close(acc, golden[f"train_s{step}_acc"], rtol=1e-5, atol=1e-6)
+        for k in p:
+            ref = golden[f"train_s{step}_g_{k}"]
+            np.testing.assert_allclose(g[k].numpy(), ref, rtol=1e-4, atol=1e-6 * max(1e-30, np.abs(ref).max()) + 1e-9)
+        O.adam_step(p, g, m, v, step + 1)
+        for k in p:
+            close(p[k], golden[f"train_s{step}_p_{k}"], rtol=1e-5, atol=2e-6)
+
+
+def test_render_image(golden):
+    p = params_from(golden, "train_s2_p_")
+    img = O.render_image(p, 12, 10, float(np.float32(138.88888549804688)), T(golden["train_c2w"]),
+                         n_samples=16, chunk=50, num_freqs=4)
+    close(img, golden["render_img"], rtol=1e-5, atol=1e-6)
+
+
+def test_spiral(golden):
+    close(O.spiral_poses(T(golden["train_c2w"]), 7, 0.3), golden["spiral"], rtol=1e-6, atol=1e-7)
