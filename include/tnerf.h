@@ -1,0 +1,181 @@
+/*
+ * tnerf.h -- C ABI of the B200-native TinyNeRF ray engine (libtnerf.so, sm_100a only).
+ *
+ * The reference (avihaig/tiny-nerf-pytorch) has no FFI layer: its boundary is the Python call
+ * surface of the flat modules rays/sampling/encoding/nerf/volume.  The Python
+ * modules under tiny-nerf-pytorch_b200/ keep that surface and call THIS library through ctypes;
+ * INTEGRATION.md shows the binding a reference maintainer would add.  Each entry point cites the
+ * reference code it replaces (paths relative to the reference repository).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns and sizes
+ *     every buffer (the library allocates device memory only inside a tnerf_handle);
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it, none synchronises;
+ *   - return value: 0 ok, <0 invalid argument / unsupported shape, >0 a cudaError_t;
+ *     tnerf_last_error() gives the message of the calling thread's last failure;
+ *   - float tensors are fp32, densely packed row-major unless a stride argument says otherwise;
+ *   - no call has a CPU fallback.
+ */
+#ifndef TNERF_H_
+#define TNERF_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNERF_ABI_VERSION 1
+
+typedef struct tnerf_handle tnerf_handle;
+
+/* precision of the fused MLP path */
+enum { TNERF_PREC_F16_TC = 0,   /* fp16 operands, fp32 accumulate, tcgen05 tensor cores     */
+       TNERF_PREC_F32_SIMT = 1  /* fp32 FFMA everywhere (exact mode / on-device fp32 oracle) */ };
+
+int         tnerf_abi_version(void);
+const char* tnerf_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+long long   tnerf_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * a1  rays.get_rays                                  (src/rays.py:3-33)
+ * Rays [first_ray, first_ray+n_rays) of an HxW pinhole camera, ray k = row*W + col.
+ * c2w: 16 floats row-major (device).  rays_o/rays_d: (n_rays,3).  rays_o may be NULL (the
+ * reference returns a broadcast view of c2w[:3,3]; the Python side builds the same view).
+ */
+int tnerf_get_rays(int H, int W, float focal, const float* c2w, long long first_ray, long long n_rays,
+                   float* rays_o, float* rays_d, void* stream);
+
+/* a2  ray/pixel gather of the training loop          (src/train.py:108-112)
+ * out[i,:] = src[index[i],:] for three (n_src,3) tables at once (any of the src/dst pairs may be NULL). */
+int tnerf_gather3(const long long* index, long long n, long long n_src,
+                  const float* src_a, float* dst_a, const float* src_b, float* dst_b,
+                  const float* src_c, float* dst_c, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a3  sampling.stratified_samples                    (src/sampling.py:3-28)
+ * rays_o has row stride o_stride floats (0 = one origin broadcast to all rays, 3 = dense).
+ * near/far scalars are used unless near_ray/far_ray (n_rays) are non-NULL.
+ * jitter (n_rays,n_samples) uniform [0,1) or NULL for the non-randomised path.
+ * z_vals (n_rays,n_samples), pts (n_rays,n_samples,3); either output may be NULL.
+ */
+int tnerf_stratified(const float* rays_o, long long o_stride, const float* rays_d, long long n_rays,
+                     int n_samples, float near_, float far_, const float* near_ray, const float* far_ray,
+                     const float* jitter, float* z_vals, float* pts, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a4  encoding.PositionalEncoding.forward            (src/encoding.py:21-33)
+ * x (n_pts,3) -> out (n_pts, 6*num_freqs + 3*include_input), column 3+6k+3*{sin,cos}+axis.
+ * The backward accumulates d(out)/d(x) for callers that differentiate w.r.t. positions.
+ */
+int tnerf_posenc(const float* x, long long n_pts, int num_freqs, int include_input, float* out, void* stream);
+int tnerf_posenc_bwd(const float* x, const float* g_out, long long n_pts, int num_freqs, int include_input,
+                     float* g_x, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a5  nerf.TinyNeRF                                  (src/nerf.py:4-41)
+ * A handle describes one MLP: `depth` Linear(hidden)+ReLU layers, the input re-appended after
+ * layer skip_at-1 (behind h), heads sigma=ReLU(Linear(hidden,1)), rgb=Sigmoid(Linear(hidden,3)).
+ * Parameters are bound as 2*depth+4 fp32 device pointers in state_dict order:
+ *   layers.0.weight, layers.0.bias, ..., sigma.0.weight, sigma.0.bias, rgb.0.weight, rgb.0.bias
+ * and stay owned by the caller (torch.optim mutates them in place).
+ */
+int  tnerf_create(tnerf_handle** out, int device, int in_dim, int hidden, int depth, int skip_at);
+void tnerf_destroy(tnerf_handle* h);
+int  tnerf_bind_params(tnerf_handle* h, const float* const* params_host, int n_params);
+long long tnerf_param_count(const tnerf_handle* h);
+/* The fused entry points generate the Fourier features themselves.  By default the encoding is
+ * inferred from in_dim (6L+3 -> include_input); call this to state it explicitly. */
+int  tnerf_set_encoding(tnerf_handle* h, int num_freqs, int include_input);
+/* 1 when the tcgen05 fused kernels support this handle's (in_dim, hidden, depth, skip_at) */
+int  tnerf_fused_supported(const tnerf_handle* h);
+/* Re-derive the packed fp16 operand image used by the tensor-core kernels from the bound fp32
+ * parameters.  Call after every optimiser step (cheap: one small kernel). */
+int  tnerf_pack_weights(tnerf_handle* h, void* stream);
+
+/* Unfused fp32 forward: x (n,in_dim) -> rgb (n,3), sigma (n,1).  If `acts` is non-NULL it receives
+ * the post-ReLU hidden activations (depth, n, hidden) needed by tnerf_mlp_bwd. */
+int tnerf_mlp_fwd(tnerf_handle* h, const float* x, long long n, float* rgb, float* sigma, float* acts,
+                  void* stream);
+long long tnerf_mlp_bwd_scratch_floats(const tnerf_handle* h, long long n);
+/* Unfused fp32 backward.  grads: flat (param_count) in state_dict order, ACCUMULATED into (caller
+ * zeroes).  g_x (n,in_dim) may be NULL.  scratch: tnerf_mlp_bwd_scratch_floats(h,n) floats. */
+int tnerf_mlp_bwd(tnerf_handle* h, const float* x, long long n, const float* acts, const float* rgb,
+                  const float* sigma, const float* g_rgb, const float* g_sigma, float* grads, float* g_x,
+                  float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a6  volume.volume_render                           (src/volume.py:3-44)
+ * rgb (n,S,3), sigma (n,S), z_vals (n,S; row stride z_stride floats, 0 = one row shared by all
+ * rays), rays_d (n,3) -> comp_rgb (n,3), depth (n), acc (n), weights (n,S) or NULL.
+ */
+int tnerf_composite_fwd(const float* rgb, const float* sigma, const float* z_vals, long long z_stride,
+                        const float* rays_d, long long n_rays, int n_samples, int white_bkgd,
+                        float* comp_rgb, float* depth, float* acc, float* weights, void* stream);
+/* Backward w.r.t. rgb and sigma from upstream g_comp (n,3), g_depth (n), g_acc (n), g_weights (n,S);
+ * any upstream pointer may be NULL (= zero). */
+int tnerf_composite_bwd(const float* rgb, const float* sigma, const float* z_vals, long long z_stride,
+                        const float* rays_d, long long n_rays, int n_samples, int white_bkgd,
+                        const float* g_comp, const float* g_depth, const float* g_acc, const float* g_weights,
+                        float* g_rgb, float* g_sigma, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused hot path: a3 -> a4 -> a5 -> a6 in one kernel   (src/train.py:51-56 and :114-121)
+ * Per-sample points, encodings and activations stay on chip.
+ * ray source: (rays_o,o_stride,rays_d) as in tnerf_stratified, OR rays_d == NULL and
+ * (c2w, H, W, focal, pixel_index|first_ray) to generate rays in-kernel (a1 fused in as well).
+ */
+typedef struct tnerf_ray_source {
+    const float* rays_o;      /* may be NULL when c2w is given */
+    long long    o_stride;
+    const float* rays_d;      /* NULL -> generate from the camera below */
+    const float* c2w;         /* 16 floats */
+    int          H, W;
+    float        focal;
+    const long long* pixel_index; /* optional (n_rays) pixel ids k=row*W+col; NULL -> first_ray+i */
+    long long    first_ray;
+} tnerf_ray_source;
+
+int tnerf_render_fwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long long n_rays,
+                     float near_, float far_, int n_samples, const float* jitter, int white_bkgd,
+                     int precision, float* comp_rgb, float* depth, float* acc, float* weights,
+                     float* rays_d_out, void* stream);
+
+/* Backward of tnerf_render_fwd w.r.t. the MLP parameters with activations recomputed on chip
+ * (implicit backward of src/train.py:126).  Upstream grads as in tnerf_composite_bwd.
+ * grads (param_count) is ACCUMULATED into. */
+int tnerf_render_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long long n_rays,
+                     float near_, float far_, int n_samples, const float* jitter, int white_bkgd,
+                     int precision, const float* g_comp, const float* g_depth, const float* g_acc,
+                     const float* g_weights, float grad_scale, float* grads, void* stream);
+
+/* Whole training step body: forward, MSE against target (n,3), backward   (src/train.py:114-126)
+ * loss_denom: the divisor of the summed squared error (3*n_rays for one process, 3*global rays
+ * under ray-sharded data parallel).  Outputs: comp_rgb (n,3) or NULL, loss_sum (1 float,
+ * ACCUMULATED: sum of squared errors / loss_denom), grads (param_count) ACCUMULATED. */
+int tnerf_train_fwd_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, const float* target,
+                        long long n_rays, float near_, float far_, int n_samples, const float* jitter,
+                        int white_bkgd, int precision, float loss_denom, float* comp_rgb, float* loss_sum,
+                        float* grads, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a7  loss + PSNR                                    (src/train.py:122-123, src/utils.py:14-15)
+ * out[0] = mean((pred-target)^2) over n floats, out[1] = -10*log10(max(out[0],1e-10)). */
+int tnerf_mse_psnr(const float* pred, const float* target, long long n, float* out2, void* stream);
+
+/* a9  optimiser                                      (src/train.py:80,125-128)
+ * torch.optim.Adam semantics on a flat parameter vector, fused with the GradScaler unscale:
+ * g = grads*inv_scale; if found_inf (device int, may be NULL) is non-zero the step is skipped. */
+int tnerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                    int step, float lr, float beta1, float beta2, float eps, float inv_scale,
+                    const int* found_inf, void* stream);
+/* sets *found_inf (device int) to 1 if any grad is non-finite (device-side GradScaler check) */
+int tnerf_check_finite(const float* grads, long long n, int* found_inf, void* stream);
+
+/* test hook: D(128xN) = A(128xK) * B(NxK)^T through the same tcgen05 descriptors the fused
+ * kernels use.  mode 0: A from shared memory, 1: A from tensor memory, 2: B MN-major. */
+int tnerf_umma_selftest(const float* a, const float* b, int n, int k, int mode, float* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNERF_H_ */

@@ -1,0 +1,206 @@
+"""ctypes binding of libtnerf.so (C ABI in include/tnerf.h) plus the small amount of host logic the
+flat modules share: pointer/stream plumbing, the per-model handle, flat parameter storage.
+
+There is deliberately no CPU path: a non-CUDA tensor reaching these helpers raises, and a missing
+shared library raises at import of any op that needs it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import weakref
+from typing import List, Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtnerf.so")
+
+PREC_F16_TC = 0
+PREC_F32_SIMT = 1
+
+_p = C.c_void_p
+_ll = C.c_longlong
+_i = C.c_int
+_f = C.c_float
+
+
+class RaySource(C.Structure):
+    """mirror of tnerf_ray_source (include/tnerf.h)"""
+    _fields_ = [("rays_o", _p), ("o_stride", _ll), ("rays_d", _p), ("c2w", _p), ("H", _i), ("W", _i),
+                ("focal", _f), ("pixel_index", _p), ("first_ray", _ll)]
+
+
+_SIGS = {
+    "tnerf_abi_version": (_i, []),
+    "tnerf_last_error": (C.c_char_p, []),
+    "tnerf_launch_count": (_ll, []),
+    "tnerf_get_rays": (_i, [_i, _i, _f, _p, _ll, _ll, _p, _p, _p]),
+    "tnerf_gather3": (_i, [_p, _ll, _ll, _p, _p, _p, _p, _p, _p, _p]),
+    "tnerf_stratified": (_i, [_p, _ll, _p, _ll, _i, _f, _f, _p, _p, _p, _p, _p, _p]),
+    "tnerf_posenc": (_i, [_p, _ll, _i, _i, _p, _p]),
+    "tnerf_posenc_bwd": (_i, [_p, _p, _ll, _i, _i, _p, _p]),
+    "tnerf_create": (_i, [C.POINTER(_p), _i, _i, _i, _i, _i]),
+    "tnerf_destroy": (None, [_p]),
+    "tnerf_bind_params": (_i, [_p, C.POINTER(_p), _i]),
+    "tnerf_param_count": (_ll, [_p]),
+    "tnerf_set_encoding": (_i, [_p, _i, _i]),
+    "tnerf_fused_supported": (_i, [_p]),
+    "tnerf_pack_weights": (_i, [_p, _p]),
+    "tnerf_mlp_fwd": (_i, [_p, _p, _ll, _p, _p, _p, _p]),
+    "tnerf_mlp_bwd_scratch_floats": (_ll, [_p, _ll]),
+    "tnerf_mlp_bwd": (_i, [_p, _p, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "tnerf_composite_fwd": (_i, [_p, _p, _p, _ll, _p, _ll, _i, _i, _p, _p, _p, _p, _p]),
+    "tnerf_composite_bwd": (_i, [_p, _p, _p, _ll, _p, _ll, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "tnerf_render_fwd": (_i, [_p, C.POINTER(RaySource), _ll, _f, _f, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "tnerf_render_bwd": (_i, [_p, C.POINTER(RaySource), _ll, _f, _f, _i, _p, _i, _i, _p, _p, _p, _p, _f, _p, _p]),
+    "tnerf_train_fwd_bwd": (_i, [_p, C.POINTER(RaySource), _p, _ll, _f, _f, _i, _p, _i, _i, _f, _p, _p, _p, _p]),
+    "tnerf_mse_psnr": (_i, [_p, _p, _ll, _p, _p]),
+    "tnerf_adam_step": (_i, [_p, _p, _p, _p, _ll, _i, _f, _f, _f, _f, _f, _p, _p]),
+    "tnerf_check_finite": (_i, [_p, _ll, _p, _p]),
+    "tnerf_umma_selftest": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library; raises loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C tiny-nerf-pytorch_b200/csrc`). There is no fallback path.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.tnerf_abi_version() != 1:
+            raise RuntimeError("libtnerf.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def exported_symbols() -> List[str]:
+    return sorted(_SIGS)
+
+
+def check(rc: int, what: str = "tnerf") -> None:
+    if rc != 0:
+        msg = lib().tnerf_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def need_cuda(*tensors) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("tiny-nerf-pytorch_b200 runs on CUDA (sm_100a) only: got a "
+                               f"{t.device} tensor; the CPU path is the reference implementation")
+        dev = dev or t.device
+    return dev
+
+
+def f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """fp32 + contiguous (no copy when already so)"""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def ptr(t: Optional[torch.Tensor]):
+    return None if t is None else _p(t.data_ptr())
+
+
+def stream(dev=None):
+    return _p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def launch_count() -> int:
+    return int(lib().tnerf_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------
+class ModelHandle:
+    """tnerf_handle bound to one TinyNeRF module on one device.  Re-binds pointers when parameters
+    move (``.to``) and re-packs the fp16 operand image when any parameter's version counter changes
+    (the optimiser updates parameters in place)."""
+
+    def __init__(self, module, device: torch.device):
+        self.module = weakref.ref(module)
+        self.device = device
+        h = _p()
+        check(lib().tnerf_create(C.byref(h), device.index or 0, module.in_dim, module.hidden, module.depth,
+                                 module.skip_at), "tnerf_create")
+        self.h = h
+        self._bound = None
+        self._packed_versions = None
+        self.param_count = int(lib().tnerf_param_count(h))
+        self.fused_ok = bool(lib().tnerf_fused_supported(h))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().tnerf_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def params(self) -> List[torch.Tensor]:
+        m = self.module()
+        ps = []
+        for lin in m.layers:
+            ps += [lin.weight, lin.bias]
+        ps += [m.sigma[0].weight, m.sigma[0].bias, m.rgb[0].weight, m.rgb[0].bias]
+        return ps
+
+    def bind(self) -> List[torch.Tensor]:
+        ps = self.params()
+        for p in ps:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("TinyNeRF parameters must be contiguous fp32")
+            need_cuda(p)
+        key = tuple(p.data_ptr() for p in ps)
+        if key != self._bound:
+            arr = (_p * len(ps))(*[_p(k) for k in key])
+            check(lib().tnerf_bind_params(self.h, arr, len(ps)), "tnerf_bind_params")
+            self._bound = key
+            self._packed_versions = None
+        return ps
+
+    def set_encoding(self, num_freqs: int, include_input: bool) -> None:
+        check(lib().tnerf_set_encoding(self.h, int(num_freqs), int(bool(include_input))), "tnerf_set_encoding")
+        self.fused_ok = bool(lib().tnerf_fused_supported(self.h))
+
+    def ensure_packed(self, force: bool = False) -> None:
+        ps = self.bind()
+        ver = tuple(p._version for p in ps)
+        if force or ver != self._packed_versions:
+            check(lib().tnerf_pack_weights(self.h, stream(self.device)), "tnerf_pack_weights")
+            self._packed_versions = ver
+
+
+def handle_for(module, device: torch.device) -> ModelHandle:
+    cache = module.__dict__.setdefault("_tnerf_handles", {})
+    key = (device.type, device.index or 0)
+    h = cache.get(key)
+    if h is None:
+        h = ModelHandle(module, device)
+        cache[key] = h
+    return h
+
+
+def flat_grad_views(module, flat: torch.Tensor) -> List[torch.Tensor]:
+    """Views of a flat (param_count,) gradient vector shaped like the parameters, state_dict order."""
+    out, off = [], 0
+    for p in handle_for(module, flat.device).params():
+        n = p.numel()
+        out.append(flat[off:off + n].view_as(p))
+        off += n
+    return out

@@ -1,0 +1,310 @@
+// C ABI of libtnerf.so (declared in include/tnerf.h).  Argument checking, the handle, and the fp32
+// composition of the fused entry points out of the stand-alone kernels (TNERF_PREC_F32_SIMT).
+#include "../../include/tnerf.h"
+#include "tnerf_internal.cuh"
+
+#include <cstdio>
+#include <cstring>
+
+namespace tnerf {
+
+std::atomic<long long> g_launches{0};
+static thread_local std::string t_error;
+void set_error(const std::string& msg) { t_error = msg; }
+int count_launch() {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error(std::string("kernel launch failed: ") + cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+int Workspace::reserve(size_t need) {
+    if (need <= bytes) return 0;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; bytes = 0;
+    size_t want = need + need / 4;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) { set_error("workspace cudaMalloc failed"); return (int)e; }
+    bytes = want;
+    return 0;
+}
+void Workspace::release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
+
+static int bad(const char* msg) { set_error(msg); return -1; }
+static RaySource to_device_source(const tnerf_ray_source* r) {
+    RaySource s;
+    s.rays_o = r->rays_o; s.o_stride = r->o_stride; s.rays_d = r->rays_d; s.c2w = r->c2w; s.H = r->H; s.W = r->W;
+    s.focal = r->focal; s.pixel_index = r->pixel_index; s.first_ray = r->first_ray;
+    return s;
+}
+static int check_source(const tnerf_ray_source* r) {
+    if (!r) return bad("ray source is NULL");
+    if (r->rays_d) { if (!r->rays_o) return bad("rays_o is NULL"); return 0; }
+    if (!r->c2w || r->H <= 0 || r->W <= 0 || !(r->focal > 0.f)) return bad("camera ray source needs c2w, H, W, focal");
+    return 0;
+}
+
+// materialise rays of a source into dense (n,3) buffers (used by the fp32 composition only)
+__global__ void expand_rays_kernel(RaySource rs, long long first, long long n, float* __restrict__ ro, float* __restrict__ rd) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float o[3], d[3];
+    load_ray(rs, first + i, o, d);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { ro[3 * i + c] = o[c]; rd[3 * i + c] = d[c]; }
+}
+
+// fp32 exact-mode pipeline over chunks of rays; mode 0 = render, 1 = backward from upstream grads, 2 = MSE train step
+struct F32Job {
+    int mode;
+    const float *target, *gC, *gD, *gA, *gW;
+    float loss_denom;
+    float *comp, *depth, *acc, *weights, *rays_d_out, *loss_sum, *grads;
+};
+
+static int run_f32(tnerf_handle* h, const RaySource& rs, long long n, float nr, float fr, int S, const float* jitter, int white,
+                   const F32Job& job, cudaStream_t s) {
+    if (S > 256 && job.mode != 0) return bad("fp32 backward path supports n_samples <= 256");
+    const int H = h->hidden, D = h->in_dim, depth = h->depth;
+    const int L = h->num_freqs, inc = (h->in_dim == 6 * L + 3);
+    if (L < 0 || (h->in_dim != 6 * L + 3 && h->in_dim != 6 * L)) return bad("handle in_dim is not 6L or 6L+3: set the encoding with tnerf_set_encoding");
+    long long chunk = 4096;
+    while (chunk > 64 && chunk * S > (1 << 19)) chunk >>= 1;
+    const long long m = chunk * S;
+    // floats: ro 3c, rd 3c, z m, pts 3m, enc D m, acts depth*H*m, rgb 3m, sigma m, comp/depth/acc 5c, gC 3c, g_rgb 3m, g_sigma m, scratch
+    const bool bw = job.mode != 0;
+    size_t fl = 6 * chunk + m + 3 * m + (size_t)D * m + (size_t)(bw ? depth : 2) * H * m + 4 * m + 8 * chunk;
+    if (bw) fl += 3 * chunk + 4 * m + (size_t)mlp_bwd_scratch_floats(h, m);
+    int e = h->ws.reserve(fl * sizeof(float));
+    if (e) return e;
+    float* w = reinterpret_cast<float*>(h->ws.ptr);
+    float* ro = w; w += 3 * chunk;
+    float* rd = w; w += 3 * chunk;
+    float* z = w; w += m;
+    float* pts = w; w += 3 * m;
+    float* enc = w; w += (size_t)D * m;
+    float* acts = w; w += (size_t)(bw ? depth : 2) * H * m;
+    float* rgb = w; w += 3 * m;
+    float* sig = w; w += m;
+    float* c_comp = w; w += 3 * chunk;
+    float* c_depth = w; w += chunk;
+    float* c_acc = w; w += chunk;
+    w += 3 * chunk;
+    float *gC = nullptr, *g_rgb = nullptr, *g_sig = nullptr, *scratch = nullptr;
+    if (bw) { gC = w; w += 3 * chunk; g_rgb = w; w += 3 * m; g_sig = w; w += m; scratch = w; }
+
+    for (long long a = 0; a < n; a += chunk) {
+        const long long c = (n - a < chunk) ? n - a : chunk;
+        expand_rays_kernel<<<(unsigned)((c + 255) / 256), 256, 0, s>>>(rs, a, c, ro, rd);
+        if ((e = count_launch())) return e;
+        if ((e = launch_stratified(ro, 3, rd, c, S, nr, fr, nullptr, nullptr, jitter ? jitter + a * S : nullptr, z, pts, s))) return e;
+        if ((e = launch_posenc(pts, c * S, L, inc, enc, s))) return e;
+        if ((e = mlp_forward_f32(h, enc, c * S, rgb, sig, bw ? acts : nullptr, acts, s))) return e;
+        float* o_comp = job.comp ? job.comp + 3 * a : c_comp;
+        if ((e = launch_composite_fwd(rgb, sig, z, S, rd, c, S, white, o_comp, job.depth ? job.depth + a : c_depth,
+                                      job.acc ? job.acc + a : c_acc, job.weights ? job.weights + a * S : nullptr, s))) return e;
+        if (job.rays_d_out) cudaMemcpyAsync(job.rays_d_out + 3 * a, rd, 3 * c * sizeof(float), cudaMemcpyDeviceToDevice, s);
+        if (!bw) continue;
+        const float* up_c = job.gC ? job.gC + 3 * a : nullptr;
+        if (job.mode == 2) {
+            if ((e = launch_mse_grad(o_comp, job.target + 3 * a, 3 * c, 1.f / job.loss_denom, gC, job.loss_sum, s))) return e;
+            up_c = gC;
+        }
+        if ((e = launch_composite_bwd(rgb, sig, z, S, rd, c, S, white, up_c, job.gD ? job.gD + a : nullptr, job.gA ? job.gA + a : nullptr,
+                                      job.gW ? job.gW + a * S : nullptr, g_rgb, g_sig, s))) return e;
+        if ((e = mlp_backward_f32(h, enc, c * S, acts, rgb, sig, g_rgb, g_sig, job.grads, nullptr, scratch, s))) return e;
+    }
+    return 0;
+}
+
+}  // namespace tnerf
+
+using namespace tnerf;
+
+extern "C" {
+
+int tnerf_abi_version(void) { return TNERF_ABI_VERSION; }
+const char* tnerf_last_error(void) { return t_error.c_str(); }
+long long tnerf_launch_count(void) { return g_launches.load(); }
+
+int tnerf_get_rays(int H, int W, float focal, const float* c2w, long long first_ray, long long n_rays, float* rays_o,
+                   float* rays_d, void* stream) {
+    if (H <= 0 || W <= 0 || !(focal > 0.f) || !c2w || !rays_d || first_ray < 0 || n_rays < 0 || first_ray + n_rays > (long long)H * W)
+        return bad("tnerf_get_rays: invalid argument");
+    return launch_get_rays(H, W, focal, c2w, first_ray, n_rays, rays_o, rays_d, (cudaStream_t)stream);
+}
+
+int tnerf_gather3(const long long* index, long long n, long long n_src, const float* sa, float* da, const float* sb, float* db,
+                  const float* sc, float* dc, void* stream) {
+    if (!index || n < 0 || (sa && !da) || (sb && !db) || (sc && !dc)) return bad("tnerf_gather3: invalid argument");
+    return launch_gather3(index, n, n_src, sa, da, sb, db, sc, dc, (cudaStream_t)stream);
+}
+
+int tnerf_stratified(const float* rays_o, long long o_stride, const float* rays_d, long long n_rays, int n_samples, float near_,
+                     float far_, const float* near_ray, const float* far_ray, const float* jitter, float* z_vals, float* pts,
+                     void* stream) {
+    if (n_rays < 0 || n_samples < 1 || (pts && (!rays_o || !rays_d))) return bad("tnerf_stratified: invalid argument");
+    return launch_stratified(rays_o, o_stride, rays_d, n_rays, n_samples, near_, far_, near_ray, far_ray, jitter, z_vals, pts,
+                             (cudaStream_t)stream);
+}
+
+int tnerf_posenc(const float* x, long long n_pts, int num_freqs, int include_input, float* out, void* stream) {
+    if (!x || !out || n_pts < 0 || num_freqs < 0 || num_freqs > 30) return bad("tnerf_posenc: invalid argument");
+    return launch_posenc(x, n_pts, num_freqs, include_input, out, (cudaStream_t)stream);
+}
+int tnerf_posenc_bwd(const float* x, const float* g_out, long long n_pts, int num_freqs, int include_input, float* g_x, void* stream) {
+    if (!x || !g_out || !g_x || n_pts < 0 || num_freqs < 0 || num_freqs > 30) return bad("tnerf_posenc_bwd: invalid argument");
+    return launch_posenc_bwd(x, g_out, n_pts, num_freqs, include_input, g_x, (cudaStream_t)stream);
+}
+
+int tnerf_create(tnerf_handle** out, int device, int in_dim, int hidden, int depth, int skip_at) {
+    if (!out || in_dim < 1 || hidden < 1 || depth < 1 || depth > kMaxDepth) return bad("tnerf_create: invalid shape (1 <= depth <= 8)");
+    if (skip_at == depth) return bad("tnerf_create: skip_at == depth leaves the heads with hidden+in_dim inputs (the reference errors too)");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { set_error("cudaSetDevice failed"); return (int)e; }
+    tnerf_handle* h = new tnerf_handle();
+    h->device = device; h->in_dim = in_dim; h->hidden = hidden; h->depth = depth; h->skip_at = skip_at;
+    h->n_params = 2 * depth + 4;
+    long long off = 0;
+    int last = in_dim;
+    for (int i = 0; i < depth; ++i) {
+        h->layer_in.push_back(last);
+        h->offsets.push_back(off); off += (long long)hidden * last;
+        h->offsets.push_back(off); off += hidden;
+        last = (i == skip_at - 1) ? hidden + in_dim : hidden;
+    }
+    h->offsets.push_back(off); off += hidden;       // sigma.0.weight
+    h->offsets.push_back(off); off += 1;            // sigma.0.bias
+    h->offsets.push_back(off); off += 3LL * hidden; // rgb.0.weight
+    h->offsets.push_back(off); off += 3;            // rgb.0.bias
+    h->param_count = off;
+    h->num_freqs = (in_dim >= 3 && (in_dim - 3) % 6 == 0) ? (in_dim - 3) / 6 : (in_dim % 6 == 0 ? in_dim / 6 : -1);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    h->fused_ok = fused_shape_supported(h);
+    *out = h;
+    return 0;
+}
+void tnerf_destroy(tnerf_handle* h) {
+    if (!h) return;
+    h->ws.release();
+    if (h->packed) cudaFree(h->packed);
+    if (h->slabs) cudaFree(h->slabs);
+    delete h;
+}
+int tnerf_set_encoding(tnerf_handle* h, int num_freqs, int include_input) {
+    if (!h || num_freqs < 0 || h->in_dim != 6 * num_freqs + (include_input ? 3 : 0)) return bad("tnerf_set_encoding: in_dim mismatch");
+    h->num_freqs = num_freqs;
+    h->fused_ok = fused_shape_supported(h);
+    return 0;
+}
+int tnerf_bind_params(tnerf_handle* h, const float* const* params_host, int n_params) {
+    if (!h || !params_host || n_params != h->n_params) return bad("tnerf_bind_params: expected 2*depth+4 pointers");
+    h->params.assign(params_host, params_host + n_params);
+    for (auto p : h->params) if (!p) return bad("tnerf_bind_params: NULL parameter");
+    return 0;
+}
+long long tnerf_param_count(const tnerf_handle* h) { return h ? h->param_count : -1; }
+int tnerf_fused_supported(const tnerf_handle* h) { return h && h->fused_ok; }
+int tnerf_pack_weights(tnerf_handle* h, void* stream) {
+    if (!h) return bad("NULL handle");
+    return fused_pack_weights(h, (cudaStream_t)stream);
+}
+
+int tnerf_mlp_fwd(tnerf_handle* h, const float* x, long long n, float* rgb, float* sigma, float* acts, void* stream) {
+    if (!h || h->params.empty() || !x || !rgb || !sigma || n < 0) return bad("tnerf_mlp_fwd: invalid argument / params not bound");
+    float* tmp = nullptr;
+    if (!acts) {
+        int e = h->ws.reserve((size_t)2 * n * h->hidden * sizeof(float));
+        if (e) return e;
+        tmp = reinterpret_cast<float*>(h->ws.ptr);
+    }
+    return mlp_forward_f32(h, x, n, rgb, sigma, acts, tmp, (cudaStream_t)stream);
+}
+long long tnerf_mlp_bwd_scratch_floats(const tnerf_handle* h, long long n) { return h ? mlp_bwd_scratch_floats(h, n) : -1; }
+int tnerf_mlp_bwd(tnerf_handle* h, const float* x, long long n, const float* acts, const float* rgb, const float* sigma,
+                  const float* g_rgb, const float* g_sigma, float* grads, float* g_x, float* scratch, void* stream) {
+    if (!h || h->params.empty() || !x || !acts || !rgb || !sigma || !grads || !scratch || n < 0) return bad("tnerf_mlp_bwd: invalid argument");
+    return mlp_backward_f32(h, x, n, acts, rgb, sigma, g_rgb, g_sigma, grads, g_x, scratch, (cudaStream_t)stream);
+}
+
+int tnerf_composite_fwd(const float* rgb, const float* sigma, const float* z_vals, long long z_stride, const float* rays_d,
+                        long long n_rays, int n_samples, int white_bkgd, float* comp_rgb, float* depth, float* acc, float* weights,
+                        void* stream) {
+    if (!rgb || !sigma || !z_vals || !rays_d || !comp_rgb || n_rays < 0 || n_samples < 1) return bad("tnerf_composite_fwd: invalid argument");
+    return launch_composite_fwd(rgb, sigma, z_vals, z_stride, rays_d, n_rays, n_samples, white_bkgd, comp_rgb, depth, acc, weights,
+                                (cudaStream_t)stream);
+}
+int tnerf_composite_bwd(const float* rgb, const float* sigma, const float* z_vals, long long z_stride, const float* rays_d,
+                        long long n_rays, int n_samples, int white_bkgd, const float* g_comp, const float* g_depth,
+                        const float* g_acc, const float* g_weights, float* g_rgb, float* g_sigma, void* stream) {
+    if (!rgb || !sigma || !z_vals || !rays_d || n_rays < 0 || n_samples < 1 || n_samples > 256)
+        return bad("tnerf_composite_bwd: invalid argument (n_samples <= 256)");
+    return launch_composite_bwd(rgb, sigma, z_vals, z_stride, rays_d, n_rays, n_samples, white_bkgd, g_comp, g_depth, g_acc, g_weights,
+                                g_rgb, g_sigma, (cudaStream_t)stream);
+}
+
+int tnerf_render_fwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long long n_rays, float near_, float far_, int n_samples,
+                     const float* jitter, int white_bkgd, int precision, float* comp_rgb, float* depth, float* acc, float* weights,
+                     float* rays_d_out, void* stream) {
+    if (!h || h->params.empty() || !comp_rgb || n_rays < 0 || n_samples < 1) return bad("tnerf_render_fwd: invalid argument / params not bound");
+    if (int e = check_source(rays_host)) return e;
+    const RaySource rs = to_device_source(rays_host);
+    if (precision == TNERF_PREC_F16_TC)
+        return fused_render_fwd(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, comp_rgb, depth, acc, weights, rays_d_out,
+                                (cudaStream_t)stream);
+    F32Job job{};
+    job.mode = 0; job.comp = comp_rgb; job.depth = depth; job.acc = acc; job.weights = weights; job.rays_d_out = rays_d_out;
+    return run_f32(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, job, (cudaStream_t)stream);
+}
+
+int tnerf_render_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long long n_rays, float near_, float far_, int n_samples,
+                     const float* jitter, int white_bkgd, int precision, const float* g_comp, const float* g_depth, const float* g_acc,
+                     const float* g_weights, float grad_scale, float* grads, void* stream) {
+    if (!h || h->params.empty() || !grads || n_rays < 0 || n_samples < 1) return bad("tnerf_render_bwd: invalid argument");
+    if (int e = check_source(rays_host)) return e;
+    const RaySource rs = to_device_source(rays_host);
+    if (precision == TNERF_PREC_F16_TC)
+        return fused_train(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, nullptr, 1.f, g_comp, g_depth, g_acc, g_weights,
+                           grad_scale, nullptr, nullptr, grads, (cudaStream_t)stream);
+    F32Job job{};
+    job.mode = 1; job.gC = g_comp; job.gD = g_depth; job.gA = g_acc; job.gW = g_weights; job.grads = grads;
+    return run_f32(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, job, (cudaStream_t)stream);
+}
+
+int tnerf_train_fwd_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, const float* target, long long n_rays, float near_,
+                        float far_, int n_samples, const float* jitter, int white_bkgd, int precision, float loss_denom,
+                        float* comp_rgb, float* loss_sum, float* grads, void* stream) {
+    if (!h || h->params.empty() || !target || !grads || !loss_sum || n_rays < 0 || n_samples < 1 || !(loss_denom > 0.f))
+        return bad("tnerf_train_fwd_bwd: invalid argument");
+    if (int e = check_source(rays_host)) return e;
+    const RaySource rs = to_device_source(rays_host);
+    if (precision == TNERF_PREC_F16_TC)
+        return fused_train(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, target, loss_denom, nullptr, nullptr, nullptr,
+                           nullptr, 0.f, comp_rgb, loss_sum, grads, (cudaStream_t)stream);
+    F32Job job{};
+    job.mode = 2; job.target = target; job.loss_denom = loss_denom; job.comp = comp_rgb; job.loss_sum = loss_sum; job.grads = grads;
+    return run_f32(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, job, (cudaStream_t)stream);
+}
+
+int tnerf_mse_psnr(const float* pred, const float* target, long long n, float* out2, void* stream) {
+    if (!pred || !target || !out2 || n < 0) return bad("tnerf_mse_psnr: invalid argument");
+    return launch_mse_psnr(pred, target, n, out2, (cudaStream_t)stream);
+}
+int tnerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, int step, float lr, float beta1,
+                    float beta2, float eps, float inv_scale, const int* found_inf, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || step < 1) return bad("tnerf_adam_step: invalid argument");
+    return launch_adam(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, inv_scale, found_inf, (cudaStream_t)stream);
+}
+int tnerf_check_finite(const float* grads, long long n, int* found_inf, void* stream) {
+    if (!grads || !found_inf || n < 0) return bad("tnerf_check_finite: invalid argument");
+    return launch_check_finite(grads, n, found_inf, (cudaStream_t)stream);
+}
+int tnerf_umma_selftest(const float* a, const float* b, int n, int k, int mode, float* d, void* stream) {
+    if (!a || !b || !d) return bad("tnerf_umma_selftest: invalid argument");
+    return umma_selftest(a, b, n, k, mode, d, (cudaStream_t)stream);
+}
+
+}  // extern "C"

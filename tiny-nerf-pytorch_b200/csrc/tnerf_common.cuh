@@ -1,0 +1,82 @@
+// Shared device-side math of the TinyNeRF ray engine (sm_100a).
+// Each helper cites the reference lines whose arithmetic it reproduces
+// (paths relative to the reference repository avihaig/tiny-nerf-pytorch).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace tnerf {
+
+constexpr int kMaxDepth = 8;
+constexpr float kEpsT = 1e-10f;     // src/volume.py:30
+constexpr float kLastDelta = 1e10f; // src/volume.py:20
+
+struct RaySource {          // device-side mirror of tnerf_ray_source
+    const float* rays_o;
+    long long o_stride;
+    const float* rays_d;
+    const float* c2w;
+    int H, W;
+    float focal;
+    const long long* pixel_index;
+    long long first_ray;
+};
+
+// t_i of torch.linspace(0,1,S) in fp32, bit for bit (src/sampling.py:16):
+// step = fl(1/(S-1)); first half step*i, second half 1 - step*(S-1-i) with a single rounding.
+__device__ __forceinline__ float linspace01(int i, int S) {
+    if (S <= 1) return 0.f;
+    const float step = __fdiv_rn(1.f, (float)(S - 1));
+    return (i < S / 2) ? __fmul_rn(step, (float)i) : __fmaf_rn(-step, (float)(S - 1 - i), 1.f);
+}
+
+// z_i = near*(1-t) + far*t with separate roundings (src/sampling.py:17)
+__device__ __forceinline__ float depth_bin(int i, int S, float near_, float far_) {
+    const float t = linspace01(i, S);
+    return __fadd_rn(__fmul_rn(near_, __fsub_rn(1.f, t)), __fmul_rn(far_, t));
+}
+
+// jittered depth: bins bounded by mid-points, first/last bin clamped (src/sampling.py:21-25)
+__device__ __forceinline__ float depth_sample(int i, int S, float near_, float far_, float u, bool jittered) {
+    const float zc = depth_bin(i, S, near_, far_);
+    if (!jittered) return zc;
+    const float lo = (i == 0) ? zc : __fmul_rn(0.5f, __fadd_rn(depth_bin(i - 1, S, near_, far_), zc));
+    const float hi = (i == S - 1) ? zc : __fmul_rn(0.5f, __fadd_rn(zc, depth_bin(i + 1, S, near_, far_)));
+    return __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), u));
+}
+
+// camera-space pixel direction rotated to world and normalised (src/rays.py:21-31)
+__device__ __forceinline__ void pixel_ray(long long k, int H, int W, float focal, const float* __restrict__ c2w,
+                                          float& dx, float& dy, float& dz) {
+    const int col = (int)(k % W), row = (int)(k / W);
+    const float cx = __fdiv_rn((float)col - (float)W * 0.5f, focal);
+    const float cy = -__fdiv_rn((float)row - (float)H * 0.5f, focal);
+    const float cz = -1.f;
+    float wx = fmaf(cz, c2w[2], fmaf(cy, c2w[1], cx * c2w[0]));
+    float wy = fmaf(cz, c2w[6], fmaf(cy, c2w[5], cx * c2w[4]));
+    float wz = fmaf(cz, c2w[10], fmaf(cy, c2w[9], cx * c2w[8]));
+    const float n = fmaxf(sqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx))), 1e-12f);
+    dx = __fdiv_rn(wx, n); dy = __fdiv_rn(wy, n); dz = __fdiv_rn(wz, n);
+}
+
+// origin + direction of ray i of a RaySource
+__device__ __forceinline__ void load_ray(const RaySource& rs, long long i, float o[3], float d[3]) {
+    if (rs.rays_d) {
+        d[0] = rs.rays_d[3 * i]; d[1] = rs.rays_d[3 * i + 1]; d[2] = rs.rays_d[3 * i + 2];
+        const float* po = rs.rays_o + rs.o_stride * i;
+        o[0] = po[0]; o[1] = po[1]; o[2] = po[2];
+    } else {
+        const long long k = rs.pixel_index ? rs.pixel_index[i] : rs.first_ray + i;
+        pixel_ray(k, rs.H, rs.W, rs.focal, rs.c2w, d[0], d[1], d[2]);
+        o[0] = rs.c2w[3]; o[1] = rs.c2w[7]; o[2] = rs.c2w[11];
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace tnerf

@@ -1,0 +1,567 @@
+// Tensor-core fused hot path (sm_100a): per 128-sample tile
+//   rays -> stratified depths -> Fourier features (registers) -> MLP as tcgen05 GEMMs (activations in
+//   tensor memory, weights resident in shared memory, fp32 accumulators in tensor memory) ->
+//   sigma/rgb heads -> alpha-compositing scan.
+// Replaces the reference sequence src/train.py:51-56 (render) without materialising points, encodings
+// or activations in HBM.  See DESIGN.md sections 3-5 for layouts and the roofline of each kernel.
+#include "tnerf_internal.cuh"
+#include "tnerf_ptx.cuh"
+
+namespace tnerf {
+using namespace ptx;
+
+// ================================================================================================
+// Operand images.  Every fp16 operand matrix X(r, k) (r = M or N index, k = reduction index) is stored
+// in the SWIZZLE_NONE canonical form  idx(r,k) = ((k/8)*R + r)*8 + k%8  (R rows): 8x8 core matrices
+// of 128 contiguous bytes, K-major view: LBO = R*16 B, SBO = 128 B.  The same bytes read as the
+// transposed operand (r' = k, k' = r) are the MN-major canonical form with LBO = 128 B, SBO = R*16 B,
+// which is what the backward kernel uses for dgrad/wgrad without a second copy.
+__host__ __device__ inline long long img_idx(int r, int k, int R) { return ((long long)(k >> 3) * R + r) * 8 + (k & 7); }
+
+enum { SEG_ACT = 0, SEG_X = 1, SEG_ONES = 2 };
+
+struct LayerPlan {
+    uint32_t b_off;      // byte offset of this layer's B image inside the packed image
+    uint32_t idesc;
+    uint16_t N;
+    uint8_t nseg;
+    uint8_t seg_kind[3];
+    uint8_t seg_steps[3];   // K=16 steps per segment
+};
+
+struct FusedPlan {
+    int depth, D, Kx, L, include_input, H;
+    int bias_in_x;          // x layers carry their bias in the pad column D of the encoding
+    uint32_t image_bytes;
+    LayerPlan layer[kMaxDepth + 1];   // hidden layers, then the head
+};
+
+struct FwdParams {
+    RaySource rs;
+    long long n_rays, n_units;
+    int S, G, R, white;
+    float near_, far_;
+    const float* jitter;
+    float *comp, *depth, *acc, *weights, *rays_d_out;
+    const __half* image;
+    FusedPlan plan;
+};
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: fp32 parameters -> fp16 operand image.  One thread per image element.
+struct PackArgs {
+    const float* W[kMaxDepth + 2];
+    const float* b[kMaxDepth + 2];
+    FusedPlan plan;
+    int fan[kMaxDepth + 1];
+    int skip_layer;      // index of the layer that consumes [h, x], or -1
+};
+
+__global__ void pack_weights_kernel(PackArgs a, __half* __restrict__ img) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long total = a.plan.image_bytes / 2;
+    if (e >= total) return;
+    const int nl = a.plan.depth + 1;
+    int l = 0;
+    while (l + 1 < nl && (long long)a.plan.layer[l + 1].b_off / 2 <= e) ++l;
+    const LayerPlan& lp = a.plan.layer[l];
+    const long long loc = e - lp.b_off / 2;
+    const int N = lp.N;
+    const int k = (int)((loc / 8) / N) * 8 + (int)(loc % 8);
+    const int n = (int)((loc / 8) % N);
+    // walk the K segments of this layer to find what forward-K index k means
+    int kk = k;
+    float v = 0.f;
+    const bool head = (l == a.plan.depth);
+    for (int sgi = 0; sgi < lp.nseg; ++sgi) {
+        const int len = lp.seg_steps[sgi] * 16;
+        if (kk < len) {
+            const int kind = lp.seg_kind[sgi];
+            if (head) {
+                // rows: 0 = sigma, 1..3 = rgb, rest zero
+                if (n < 4) {
+                    const float* W = (n == 0) ? a.W[a.plan.depth] : a.W[a.plan.depth + 1] + (long long)(n - 1) * a.plan.H;
+                    const float bb = (n == 0) ? a.b[a.plan.depth][0] : a.b[a.plan.depth + 1][n - 1];
+                    if (kind == SEG_ACT) v = W[kk];
+                    else if (kind == SEG_ONES) {
+                        const float hi = __half2float(__float2half_rn(bb));
+                        v = (kk == 0) ? hi : (kk == 1 ? bb - hi : 0.f);
+                    }
+                }
+            } else {
+                const float* W = a.W[l] + (long long)n * a.fan[l];
+                const float bb = a.b[l][n];
+                if (kind == SEG_ACT) v = W[kk];
+                else if (kind == SEG_X) {
+                    const int xo = (l == 0) ? 0 : a.plan.H;
+                    if (kk < a.plan.D) v = W[xo + kk];
+                    else if (kk == a.plan.Kx - 1 && a.plan.bias_in_x) v = bb;   // constant-1 column of the encoding
+                } else {
+                    const float hi = __half2float(__float2half_rn(bb));
+                    v = (kk == 0) ? hi : (kk == 1 ? bb - hi : 0.f);
+                }
+            }
+            break;
+        }
+        kk -= len;
+    }
+    img[e] = __float2half_rn(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fourier features of one point into 64 fp16 slots (packed pairs), column order of
+// src/encoding.py:27-33 ([x, sin f0, cos f0, sin f1, ...], 3 axes each).  sin/cos of the base
+// frequency use a 2-term Cody-Waite reduction (|x| < ~50) + minimax polynomials; higher octaves use
+// the double-angle recurrence s' = 2sc, c' = (c-s)(c+s): max abs error 5e-5 at 2^9, below fp16 rounding.
+__device__ __forceinline__ void sincos_small(float x, float& s, float& c) {
+    const float n = rintf(x * 0.6366197723675814f);
+    float r = fmaf(-n, 1.5707963705062866f, x);
+    r = fmaf(-n, -4.371138828673793e-08f, r);
+    const float r2 = r * r;
+    const float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f) * r2, r, r);
+    const float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f) * r2, r2,
+                          fmaf(-0.5f, r2, 1.f));
+    const int q = (int)n & 3;
+    const float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cc : cc;
+}
+
+template <int KX, bool INC>
+__device__ __forceinline__ void encode_point(const float p[3], int L, uint32_t (&pk)[KX / 2]) {
+    float f[KX];
+#pragma unroll
+    for (int i = 0; i < KX; ++i) f[i] = 0.f;
+    constexpr int base = INC ? 3 : 0;
+    if (INC) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) f[a] = p[a];
+    }
+    float s[3], c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) sincos_small(p[a], s[a], c[a]);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        const bool on = k < L;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (base + 6 * k + 3 + a < KX - 1) {
+                f[base + 6 * k + a] = on ? s[a] : 0.f;
+                f[base + 6 * k + 3 + a] = on ? c[a] : 0.f;
+            }
+            const float s2 = s[a] + s[a];
+            const float cn = (c[a] - s[a]) * (c[a] + s[a]);
+            s[a] = s2 * c[a];
+            c[a] = cn;
+        }
+    }
+    f[KX - 1] = 1.f;   // constant-1 pad column: carries the bias of the x-consuming layers
+#pragma unroll
+    for (int i = 0; i < KX / 2; ++i) pk[i] = pack_h2(f[2 * i], f[2 * i + 1]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused forward kernel.  288 threads: warps 0-3 = warpgroup A, warps 4-7 = warpgroup B (each owns one
+// 128-row tile at a time: thread <-> sample row <-> TMEM lane), warp 8 = MMA issuer + weight loader.
+constexpr int FWD_THREADS = 288;
+constexpr int TM_ACC = 0, TM_ACT = 128, TM_X = 192, TM_HEAD = 224, TM_ONES = 240, TM_WG_STRIDE = 256;
+constexpr int MAX_G = 8;
+
+struct FwdSmem {   // trailing part of dynamic smem (after the weight image)
+    float4 stage[2][MAX_G * 128];   // per warpgroup: (sigma, r, g, b) per sample of the current unit
+    float stage_z[2][MAX_G * 128];
+    uint64_t bar_w, bar_a[2], bar_acc[2];
+    uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ void composite_unit(const FwdParams& p, const float4* st, const float* sz, long long ray0, int warp_q,
+                                               int lane) {
+    const int S = p.S;
+    for (int rr = warp_q; rr < p.R; rr += 4) {
+        const long long ray = ray0 + rr;
+        if (ray >= p.n_rays) break;
+        float o[3], d[3];
+        load_ray(p.rs, ray, o, d);
+        const float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        const float4* s4 = st + rr * S;
+        const float* zz = sz + rr * S;
+        float T_carry = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, dsum = 0.f, asum = 0.f;
+        for (int base = 0; base < S; base += 32) {
+            const int i = base + lane;
+            const bool ok = i < S;
+            float zi = 0.f, alpha = 0.f, q = 1.f;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) {
+                v = s4[i];
+                zi = zz[i];
+                const float gap = ((i == S - 1) ? kLastDelta : (zz[i + 1] - zi)) * dn;
+                alpha = 1.f - expf(-v.x * gap);
+                q = 1.f - alpha + kEpsT;
+            }
+            float incl = q;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const float up = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl *= up;
+            }
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 1.f;
+            const float w = alpha * (T_carry * excl);
+            if (ok) {
+                if (p.weights) p.weights[ray * S + i] = w;
+                cr += w * v.y; cg += w * v.z; cb += w * v.w;
+                dsum += w * zi; asum += w;
+            }
+            T_carry *= __shfl_sync(0xffffffffu, incl, 31);
+        }
+        cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); dsum = warp_sum(dsum); asum = warp_sum(asum);
+        if (lane == 0) {
+            const float bg = p.white ? 1.f - asum : 0.f;
+            p.comp[3 * ray] = cr + bg; p.comp[3 * ray + 1] = cg + bg; p.comp[3 * ray + 2] = cb + bg;
+            if (p.depth) p.depth[ray] = dsum;
+            if (p.acc) p.acc[ray] = asum;
+            if (p.rays_d_out) { p.rays_d_out[3 * ray] = d[0]; p.rays_d_out[3 * ray + 1] = d[1]; p.rays_d_out[3 * ray + 2] = d[2]; }
+        }
+    }
+}
+
+template <int KX>
+__global__ void __launch_bounds__(FWD_THREADS, 1) fused_fwd_kernel(const __grid_constant__ FwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem + ((p.plan.image_bytes + 1023u) & ~1023u));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_w = smem_u32(&sm.bar_w);
+
+    if (warp == 8 && lane == 0) {
+        mbar_init(bar_w, 1);
+        for (int w = 0; w < 2; ++w) { mbar_init(smem_u32(&sm.bar_a[w]), 128); mbar_init(smem_u32(&sm.bar_acc[w]), 1); }
+        fence_barrier_init();
+    }
+    if (warp == 0) { tmem_alloc(smem_u32(&sm.tmem_slot), 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_slot;
+
+    // units are dealt round-robin: (cta, warpgroup) pair j takes units j, j + 2*grid, ...
+    const long long stride = 2LL * gridDim.x;
+
+    if (warp == 8) {
+        // ------------------------------ MMA issuer ------------------------------
+        if (lane == 0) {
+            mbar_expect_tx(bar_w, p.plan.image_bytes);
+            uint32_t off = 0;
+            while (off < p.plan.image_bytes) {
+                const uint32_t n = min(32768u, p.plan.image_bytes - off);
+                bulk_g2s(smem_u32(smem) + off, reinterpret_cast<const uint8_t*>(p.image) + off, n, bar_w);
+                off += n;
+            }
+            mbar_wait(bar_w, 0);
+            uint32_t phase[2] = {0, 0};
+            const uint32_t wbase = smem_u32(smem);
+            long long u0 = 2LL * blockIdx.x;
+            for (;; u0 += stride) {
+                const bool has0 = u0 < p.n_units, has1 = u0 + 1 < p.n_units;
+                if (!has0 && !has1) break;
+                for (int g = 0; g < p.G; ++g) {
+                    for (int step = 0; step <= p.plan.depth; ++step) {
+                        const LayerPlan& lp = p.plan.layer[step];
+                        for (int w = 0; w < 2; ++w) {
+                            if (!(w ? has1 : has0)) continue;
+                            mbar_wait(smem_u32(&sm.bar_a[w]), phase[w]);
+                            phase[w] ^= 1;
+                            tc_fence_after();
+                            const uint32_t tw = tmem + w * TM_WG_STRIDE;
+                            const uint32_t d_t = tw + (step == p.plan.depth ? TM_HEAD : TM_ACC);
+                            uint32_t kstep = 0;
+                            for (int sgi = 0; sgi < lp.nseg; ++sgi) {
+                                const uint32_t a0 = tw + (lp.seg_kind[sgi] == SEG_ACT ? TM_ACT : lp.seg_kind[sgi] == SEG_X ? TM_X : TM_ONES);
+                                for (int j = 0; j < lp.seg_steps[sgi]; ++j, ++kstep) {
+                                    const uint64_t bd = make_desc(wbase + lp.b_off + kstep * (uint32_t)lp.N * 32u, (uint32_t)lp.N * 16u, 128u);
+                                    mma_ts(d_t, a0 + j * 8, bd, lp.idesc, kstep > 0);
+                                }
+                            }
+                            tc_commit(smem_u32(&sm.bar_acc[w]));
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------ sample / epilogue warpgroups ------------------------------
+        const int wg = warp >> 2, q = warp & 3, row = q * 32 + lane;
+        const uint32_t tw = tmem + wg * TM_WG_STRIDE + ((uint32_t)(q * 32) << 16);
+        const uint32_t bar_a = smem_u32(&sm.bar_a[wg]), bar_acc = smem_u32(&sm.bar_acc[wg]);
+        float4* st = sm.stage[wg];
+        float* sz = sm.stage_z[wg];
+        {   // constant-one chunk used to add biases inside the GEMM: A[:,0] = A[:,1] = 1
+            uint32_t ones[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ones[i] = 0u;
+            ones[0] = 0x3C003C00u;
+            tmem_st8(tw + TM_ONES, ones);
+        }
+        uint32_t phase = 0;
+        const bool jit = p.jitter != nullptr;
+        for (long long u = 2LL * blockIdx.x + wg; u < p.n_units; u += stride) {
+            const long long ray0 = u * p.R;
+            for (int g = 0; g < p.G; ++g) {
+                const int urow = g * 128 + row;            // row inside the unit
+                const long long ray = ray0 + urow / p.S;
+                const int si = urow % p.S;
+                const bool valid = ray < p.n_rays;
+                float pt[3] = {0.f, 0.f, 0.f};
+                float z = 0.f;
+                if (valid) {
+                    float o[3], d[3];
+                    load_ray(p.rs, ray, o, d);
+                    z = depth_sample(si, p.S, p.near_, p.far_, jit ? p.jitter[ray * p.S + si] : 0.f, jit);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) pt[c] = __fadd_rn(o[c], __fmul_rn(d[c], z));
+                }
+                sz[urow] = z;
+                {
+                    uint32_t pk[KX / 2];
+                    if (p.plan.include_input) encode_point<KX, true>(pt, p.plan.L, pk);
+                    else encode_point<KX, false>(pt, p.plan.L, pk);
+#pragma unroll
+                    for (int c = 0; c < KX / 32; ++c) {
+                        uint32_t chunk[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) chunk[i] = pk[c * 16 + i];
+                        tmem_st16(tw + TM_X + c * 16, chunk);
+                    }
+                    if (KX % 32) {
+                        uint32_t chunk[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) chunk[i] = pk[(KX / 32) * 16 + i];
+                        tmem_st8(tw + TM_X + (KX / 32) * 16, chunk);
+                    }
+                }
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(bar_a);
+                for (int l = 0; l < p.plan.depth; ++l) {
+                    mbar_wait(bar_acc, phase);
+                    phase ^= 1;
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t v[32];
+                        tmem_ld32(tw + TM_ACC + c * 32, v);
+                        tc_wait_ld();
+                        uint32_t h[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) h[i] = pack_relu_h2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                        tmem_st16(tw + TM_ACT + c * 16, h);
+                    }
+                    tc_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(bar_a);
+                }
+                mbar_wait(bar_acc, phase);
+                phase ^= 1;
+                tc_fence_after();
+                {
+                    uint32_t v[4];
+                    tmem_ld4(tw + TM_HEAD, v);
+                    tc_wait_ld();
+                    float4 o4;
+                    o4.x = fmaxf(__uint_as_float(v[0]), 0.f);
+                    o4.y = 1.f / (1.f + __expf(-__uint_as_float(v[1])));
+                    o4.z = 1.f / (1.f + __expf(-__uint_as_float(v[2])));
+                    o4.w = 1.f / (1.f + __expf(-__uint_as_float(v[3])));
+                    st[urow] = o4;
+                }
+            }
+            bar_sync(1 + wg, 128);
+            composite_unit(p, st, sz, ray0, q, lane);
+            bar_sync(1 + wg, 128);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ================================================================================================
+// UMMA self-test: D(128 x N) = A(128 x K) B(N x K)^T through the descriptor conventions above.
+//   mode & 3: 0 = A,B K-major from smem; 1 = A from tensor memory; 2 = B MN-major; 3 = A MN-major
+//   mode & 16: swap LBO/SBO (convention probe); mode & 32: swap fp16 halves in the TMEM A packing
+__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, int N, int K,
+                                                              int mode, float* __restrict__ d) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __half* As = reinterpret_cast<__half*>(smem);
+    __half* Bs = reinterpret_cast<__half*>(smem + 128 * K * 2);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int m = mode & 3;
+    if (t == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    if (warp == 0) { tmem_alloc(smem_u32(&slot), 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    // stage operands
+    for (int e = t; e < 128 * K; e += 128) {
+        int mm, kk;
+        if (m == 3) { kk = e / 128; mm = e % 128; } else { mm = e / K; kk = e % K; }
+        const float v = a[e];
+        if (m == 3) As[img_idx(kk, mm, K)] = __float2half_rn(v);       // MN-major: rows = k, "k" = m
+        else As[img_idx(mm, kk, 128)] = __float2half_rn(v);
+    }
+    for (int e = t; e < N * K; e += 128) {
+        int nn, kk;
+        if (m == 2) { kk = e / N; nn = e % N; } else { nn = e / K; kk = e % K; }
+        const float v = b[e];
+        if (m == 2) Bs[img_idx(kk, nn, K)] = __float2half_rn(v);
+        else Bs[img_idx(nn, kk, N)] = __float2half_rn(v);
+    }
+    if (m == 1) {
+        const uint32_t tw = tmem + 256 + ((uint32_t)(warp * 32) << 16);
+        for (int c0 = 0; c0 < K / 2; c0 += 8) {
+            uint32_t r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float lo = a[(warp * 32 + lane) * K + 2 * (c0 + i)], hi = a[(warp * 32 + lane) * K + 2 * (c0 + i) + 1];
+                r[i] = (mode & 32) ? pack_h2(hi, lo) : pack_h2(lo, hi);
+            }
+            tmem_st8(tw + c0, r);
+        }
+        tc_wait_st();
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (t == 0) {
+        const uint32_t idesc = make_idesc_f16(128, N, m == 3, m == 2);
+        const uint32_t sa = smem_u32(As), sb = smem_u32(Bs);
+        for (int j = 0; j < K / 16; ++j) {
+            uint32_t a_lbo, a_sbo, a_adv, b_lbo, b_sbo, b_adv;
+            if (m == 3) { a_lbo = 128; a_sbo = K * 16; a_adv = 256; } else { a_lbo = 128 * 16; a_sbo = 128; a_adv = 128 * 32; }
+            if (m == 2) { b_lbo = 128; b_sbo = K * 16; b_adv = 256; } else { b_lbo = N * 16; b_sbo = 128; b_adv = N * 32; }
+            if (mode & 16) { uint32_t x = a_lbo; a_lbo = a_sbo; a_sbo = x; x = b_lbo; b_lbo = b_sbo; b_sbo = x; }
+            const uint64_t bd = make_desc(sb + j * b_adv, b_lbo, b_sbo);
+            if (m == 1) mma_ts(tmem, tmem + 256 + j * 8, bd, idesc, j > 0);
+            else mma_ss(tmem, make_desc(sa + j * a_adv, a_lbo, a_sbo), bd, idesc, j > 0);
+        }
+        tc_commit(smem_u32(&bar));
+    }
+    mbar_wait(smem_u32(&bar), 0);
+    tc_fence_after();
+    const uint32_t tw = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tw + c0, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) d[(warp * 32 + lane) * N + c0 + i] = __uint_as_float(v[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+int umma_selftest(const float* a, const float* b, int n, int k, int mode, float* d, cudaStream_t s) {
+    if (n < 16 || n > 256 || n % 16 || k < 16 || k > 128 || k % 16) { set_error("umma_selftest: need 16<=N<=256 (x16), 16<=K<=128 (x16)"); return -1; }
+    const size_t smem = (size_t)(128 + n) * k * 2;
+    cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    umma_selftest_kernel<<<1, 128, smem, s>>>(a, b, n, k, mode, d);
+    return count_launch();
+}
+
+// ================================================================================================
+// host side
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static bool build_plan(const tnerf_handle* h, FusedPlan& pl) {
+    if (h->hidden != 128 || h->depth < 1 || h->depth > kMaxDepth) return false;
+    int L, inc;
+    if (h->num_freqs >= 0 && h->in_dim == 6 * h->num_freqs + 3) { L = h->num_freqs; inc = 1; }
+    else if (h->num_freqs >= 0 && h->in_dim == 6 * h->num_freqs) { L = h->num_freqs; inc = 0; }
+    else return false;
+    if (L < 0 || L > 10) return false;
+    pl = FusedPlan{};
+    pl.depth = h->depth; pl.D = h->in_dim; pl.L = L; pl.include_input = inc; pl.H = 128;
+    pl.Kx = round_up(h->in_dim + 1, 16);
+    if (pl.Kx > 64) return false;
+    pl.bias_in_x = 1;    // Kx always leaves at least one pad column for the constant 1
+    uint32_t off = 0;
+    const int skip_layer = (h->skip_at >= 1 && h->skip_at <= h->depth - 1) ? h->skip_at : -1;
+    for (int l = 0; l <= h->depth; ++l) {
+        LayerPlan& lp = pl.layer[l];
+        lp.b_off = off;
+        const bool head = (l == h->depth);
+        lp.N = head ? 16 : 128;
+        lp.idesc = make_idesc_f16(128, lp.N, 0, 0);
+        int ns = 0, ksteps = 0;
+        if (l == 0) { lp.seg_kind[ns] = SEG_X; lp.seg_steps[ns++] = pl.Kx / 16; }
+        else {
+            lp.seg_kind[ns] = SEG_ACT; lp.seg_steps[ns++] = 8;
+            if (l == skip_layer) { lp.seg_kind[ns] = SEG_X; lp.seg_steps[ns++] = pl.Kx / 16; }
+            else { lp.seg_kind[ns] = SEG_ONES; lp.seg_steps[ns++] = 1; }
+        }
+        lp.nseg = ns;
+        for (int i = 0; i < ns; ++i) ksteps += lp.seg_steps[i];
+        off += (uint32_t)ksteps * 16u * lp.N * 2u;
+    }
+    pl.image_bytes = off;
+    return true;
+}
+
+bool fused_shape_supported(const tnerf_handle* h) { FusedPlan pl; return build_plan(h, pl); }
+
+int fused_pack_weights(tnerf_handle* h, cudaStream_t s) {
+    FusedPlan pl;
+    if (!build_plan(h, pl)) { set_error("fused path: unsupported MLP shape (need hidden=128, in_dim=6L(+3)<=63, depth<=8)"); return -2; }
+    if (h->params.empty()) { set_error("pack_weights: parameters not bound"); return -3; }
+    if (h->packed_bytes < pl.image_bytes) {
+        if (h->packed) cudaFree(h->packed);
+        cudaError_t e = cudaMalloc(&h->packed, pl.image_bytes);
+        if (e != cudaSuccess) { set_error("cudaMalloc(packed image) failed"); return (int)e; }
+        h->packed_bytes = pl.image_bytes;
+    }
+    PackArgs a{};
+    a.plan = pl;
+    for (int l = 0; l < h->depth; ++l) { a.W[l] = h->params[2 * l]; a.b[l] = h->params[2 * l + 1]; a.fan[l] = h->layer_in[l]; }
+    a.W[h->depth] = h->params[2 * h->depth]; a.b[h->depth] = h->params[2 * h->depth + 1];
+    a.W[h->depth + 1] = h->params[2 * h->depth + 2]; a.b[h->depth + 1] = h->params[2 * h->depth + 3];
+    const long long total = pl.image_bytes / 2;
+    pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, reinterpret_cast<__half*>(h->packed));
+    return count_launch();
+}
+
+static long long gcd_ll(long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; }
+
+int fused_render_fwd(tnerf_handle* h, const RaySource& rs, long long n, float nr, float fr, int S, const float* jitter, int white,
+                     float* comp, float* depth, float* acc, float* weights, float* rays_d_out, cudaStream_t s) {
+    if (n <= 0) return 0;
+    FwdParams p{};
+    if (!build_plan(h, p.plan)) { set_error("fused path: unsupported MLP shape"); return -2; }
+    if (!h->packed) { set_error("fused path: tnerf_pack_weights has not been called"); return -3; }
+    const long long g = gcd_ll(S, 128);
+    p.G = (int)(S / g); p.R = (int)(128 / g);
+    if (S < 1 || p.G > MAX_G) { set_error("fused path: n_samples must satisfy n_samples/gcd(n_samples,128) <= 8"); return -4; }
+    p.rs = rs; p.n_rays = n; p.n_units = (n + p.R - 1) / p.R; p.S = S; p.white = white; p.near_ = nr; p.far_ = fr;
+    p.jitter = jitter; p.comp = comp; p.depth = depth; p.acc = acc; p.weights = weights; p.rays_d_out = rays_d_out;
+    p.image = reinterpret_cast<const __half*>(h->packed);
+    const size_t smem = ((p.plan.image_bytes + 1023u) & ~1023u) + sizeof(FwdSmem);
+    long long grid = (p.n_units + 1) / 2;
+    if (grid > h->sm_count) grid = h->sm_count;
+    auto kern = p.plan.Kx == 64 ? fused_fwd_kernel<64> : p.plan.Kx == 48 ? fused_fwd_kernel<48> : p.plan.Kx == 32 ? fused_fwd_kernel<32> : fused_fwd_kernel<16>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("fused fwd: shared memory request rejected"); return (int)e; }
+    kern<<<(unsigned)grid, FWD_THREADS, smem, s>>>(p);
+    return count_launch();
+}
+
+int fused_train(tnerf_handle*, const RaySource&, long long, float, float, int, const float*, int, const float*, float, const float*,
+                const float*, const float*, const float*, float, float*, float*, float*, cudaStream_t) {
+    set_error("fused tensor-core backward not built in this revision");
+    return -9;
+}
+
+}  // namespace tnerf

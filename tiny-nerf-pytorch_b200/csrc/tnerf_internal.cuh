@@ -1,0 +1,83 @@
+// Internal declarations shared by the translation units of libtnerf.so.
+#pragma once
+#include <atomic>
+#include <string>
+#include <vector>
+#include "tnerf_common.cuh"
+
+namespace tnerf {
+
+enum { GEMM_ACCUM = 1, GEMM_RELU = 2, GEMM_SIGMOID = 4, GEMM_ATOMIC = 8 };
+
+struct GemmArgs {
+    const float* A = nullptr; long long lda = 0;
+    const float* B = nullptr; long long ldb = 0;
+    float* C = nullptr;       long long ldc = 0;
+    long long M = 0; int N = 0; long long K = 0;
+    const float* bias = nullptr;
+    const float* mask = nullptr; long long ldm = 0;
+    int flags = 0;
+    long long k_chunk = 0;
+};
+
+extern std::atomic<long long> g_launches;
+void set_error(const std::string& msg);
+// records a launch, returns the pending cudaError_t (0 if none)
+int count_launch();
+
+struct Workspace {   // grow-only device scratch owned by a handle
+    void* ptr = nullptr; size_t bytes = 0;
+    int reserve(size_t need);
+    void release();
+};
+
+}  // namespace tnerf
+
+struct tnerf_handle {
+    int device = 0, in_dim = 0, hidden = 0, depth = 0, skip_at = 0;
+    int n_params = 0;
+    long long param_count = 0;
+    std::vector<const float*> params;     // 2*depth+4 device pointers, state_dict order
+    std::vector<long long> offsets;       // offset of each param in the flat gradient vector
+    std::vector<int> layer_in;            // fan-in of each hidden layer
+    tnerf::Workspace ws;                  // fp32 path scratch
+    // tensor-core path
+    void* packed = nullptr; size_t packed_bytes = 0;   // fp16 operand image (device)
+    void* slabs = nullptr;  size_t slab_bytes = 0;     // per-CTA partial weight gradients
+    int sm_count = 0;
+    bool fused_ok = false;
+    int num_freqs = 0;                    // (in_dim-3)/6 when in_dim = 3+6L
+};
+
+namespace tnerf {
+int launch_get_rays(int H, int W, float focal, const float* c2w, long long first, long long n, float* ro, float* rd, cudaStream_t s);
+int launch_gather3(const long long* idx, long long n, long long n_src, const float* sa, float* da, const float* sb, float* db, const float* sc, float* dc, cudaStream_t s);
+int launch_stratified(const float* ro, long long os, const float* rd, long long n, int S, float nr, float fr, const float* nray, const float* fray, const float* jit, float* z, float* pts, cudaStream_t s);
+int launch_posenc(const float* x, long long n, int L, int inc, float* out, cudaStream_t s);
+int launch_posenc_bwd(const float* x, const float* g, long long n, int L, int inc, float* gx, cudaStream_t s);
+int launch_gemm(const GemmArgs& g, bool a_kc, bool b_kc, cudaStream_t s);
+int launch_colsum(const float* a, long long rows, int cols, long long lda, float* out, cudaStream_t s);
+int launch_head_grad(const float* rgb, const float* sigma, const float* g_rgb, const float* g_sigma, long long n, float* dzs, float* dzr, cudaStream_t s);
+int launch_composite_fwd(const float* rgb, const float* sigma, const float* z, long long zs, const float* rd, long long n, int S, int white, float* comp, float* depth, float* acc, float* w, cudaStream_t s);
+int launch_composite_bwd(const float* rgb, const float* sigma, const float* z, long long zs, const float* rd, long long n, int S, int white, const float* gC, const float* gD, const float* gA, const float* gW, float* g_rgb, float* g_sigma, cudaStream_t s);
+int launch_mse_psnr(const float* a, const float* b, long long n, float* out2, cudaStream_t s);
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float b1, float b2, float eps, float inv_scale, const int* found_inf, cudaStream_t s);
+int launch_check_finite(const float* g, long long n, int* flag, cudaStream_t s);
+int launch_mse_grad(const float* c, const float* t, long long n3, float inv_denom, float* gC, float* loss, cudaStream_t s);
+
+// fp32 MLP (tnerf_mlp.cu)
+int mlp_forward_f32(tnerf_handle* h, const float* x, long long n, float* rgb, float* sigma, float* acts, float* tmp, cudaStream_t s);
+int mlp_backward_f32(tnerf_handle* h, const float* x, long long n, const float* acts, const float* rgb, const float* sigma,
+                     const float* g_rgb, const float* g_sigma, float* grads, float* g_x, float* scratch, cudaStream_t s);
+long long mlp_bwd_scratch_floats(const tnerf_handle* h, long long n);
+
+// tensor-core fused path (tnerf_fused.cu)
+bool fused_shape_supported(const tnerf_handle* h);
+int fused_pack_weights(tnerf_handle* h, cudaStream_t s);
+int fused_render_fwd(tnerf_handle* h, const RaySource& rs, long long n, float nr, float fr, int S, const float* jitter, int white,
+                     float* comp, float* depth, float* acc, float* weights, float* rays_d_out, cudaStream_t s);
+int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, float fr, int S, const float* jitter, int white,
+                const float* target, float loss_denom, const float* gC, const float* gD, const float* gA, const float* gW,
+                float grad_scale, float* comp, float* loss_sum, float* grads, cudaStream_t s);
+int umma_selftest(const float* a, const float* b, int n, int k, int mode, float* d, cudaStream_t s);
+}  // namespace tnerf

@@ -1,0 +1,481 @@
+// Stand-alone (unfused) fp32 kernels behind the reference's per-op Python surface:
+// get_rays, ray gather, stratified_samples, PositionalEncoding, TinyNeRF (tiled FFMA GEMMs),
+// volume_render forward/backward, MSE/PSNR, Adam.  All are HBM- or FFMA-bound elementwise / scan /
+// SGEMM kernels; the tensor-core fused path lives in tnerf_fused.cu.
+#include "tnerf_internal.cuh"
+
+namespace tnerf {
+
+// ------------------------------------------------------------------------------------------------
+// a1 get_rays (src/rays.py:3-33): one thread per ray, 24 B written per ray.
+__global__ void get_rays_kernel(int H, int W, float focal, const float* __restrict__ c2w, long long first,
+                                long long n, float* __restrict__ ro, float* __restrict__ rd) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float dx, dy, dz;
+    pixel_ray(first + i, H, W, focal, c2w, dx, dy, dz);
+    rd[3 * i] = dx; rd[3 * i + 1] = dy; rd[3 * i + 2] = dz;
+    if (ro) { ro[3 * i] = c2w[3]; ro[3 * i + 1] = c2w[7]; ro[3 * i + 2] = c2w[11]; }
+}
+
+// a2 gather (src/train.py:110-112)
+__global__ void gather3_kernel(const long long* __restrict__ idx, long long n, long long n_src,
+                               const float* __restrict__ sa, float* __restrict__ da,
+                               const float* __restrict__ sb, float* __restrict__ db,
+                               const float* __restrict__ sc, float* __restrict__ dc) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= 3 * n) return;
+    const long long i = t / 3; const int c = (int)(t % 3);
+    long long s = idx[i];
+    if (s < 0) s += n_src;
+    if (sa) da[t] = sa[3 * s + c];
+    if (sb) db[t] = sb[3 * s + c];
+    if (sc) dc[t] = sc[3 * s + c];
+}
+
+// a3 stratified_samples (src/sampling.py:14-28): one thread per (ray, sample)
+__global__ void stratified_kernel(const float* __restrict__ ro, long long o_stride, const float* __restrict__ rd,
+                                  long long n, int S, float near_, float far_, const float* __restrict__ near_ray,
+                                  const float* __restrict__ far_ray, const float* __restrict__ jitter,
+                                  float* __restrict__ z_out, float* __restrict__ pts) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n * S) return;
+    const long long r = t / S; const int i = (int)(t % S);
+    const float nr = near_ray ? near_ray[r] : near_, fr = far_ray ? far_ray[r] : far_;
+    const float z = depth_sample(i, S, nr, fr, jitter ? jitter[t] : 0.f, jitter != nullptr);
+    if (z_out) z_out[t] = z;
+    if (pts) {
+        const float* o = ro + r * o_stride;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) pts[3 * t + c] = __fadd_rn(o[c], __fmul_rn(rd[3 * r + c], z));
+    }
+}
+
+// a4 PositionalEncoding (src/encoding.py:26-33): one thread per OUTPUT element -> coalesced stores.
+__global__ void posenc_kernel(const float* __restrict__ x, long long n, int L, int inc, float* __restrict__ out) {
+    const int D = 6 * L + (inc ? 3 : 0);
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n * D) return;
+    const long long p = t / D; int c = (int)(t % D);
+    float v;
+    if (inc && c < 3) {
+        v = x[3 * p + c];
+    } else {
+        if (inc) c -= 3;
+        const int k = c / 6, r = c % 6, axis = r % 3;
+        const float arg = x[3 * p + axis] * (float)(1 << k);   // exact power-of-two scaling
+        v = (r < 3) ? sinf(arg) : cosf(arg);
+    }
+    out[t] = v;
+}
+
+__global__ void posenc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, long long n, int L,
+                                  int inc, float* __restrict__ gx) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= 3 * n) return;
+    const long long p = t / 3; const int axis = (int)(t % 3);
+    const int D = 6 * L + (inc ? 3 : 0), base = inc ? 3 : 0;
+    const float xv = x[t];
+    const float* gp = g + p * D;
+    float acc = inc ? gp[axis] : 0.f;
+    for (int k = 0; k < L; ++k) {
+        const float f = (float)(1 << k);
+        float s, c;
+        sincosf(xv * f, &s, &c);
+        acc += f * (gp[base + 6 * k + axis] * c - gp[base + 6 * k + 3 + axis] * s);
+    }
+    gx[t] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a5 tiled FFMA GEMM  C(i,j) = sum_kk A(i,kk) * B(j,kk)   (src/nerf.py:34-41 and its autograd backward)
+//   A_KC: A(i,kk) = A[i*lda + kk]  else A[kk*lda + i];   B_KC likewise.
+//   forward  : A = activations (KC), B = weight [out,in] (KC)
+//   dgrad    : A = dY (KC),          B = weight as (j=in, kk=out): B[kk*ldb + j]  (not KC)
+//   wgrad    : A = dY as (i=out, kk=sample): A[kk*lda + i], B = X as (j=in, kk=sample) (neither KC), split-K
+constexpr int BM = 128, BN = 128, BK = 8, PAD = 4;
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
+    __shared__ __align__(16) float As[BK][BM + PAD];
+    __shared__ __align__(16) float Bs[BK][BN + PAD];
+    const int t = threadIdx.x, tx = t % 16, ty = t / 16;
+    const long long i0 = (long long)blockIdx.x * BM;
+    const int j0 = blockIdx.y * BN;
+    const long long k_begin = (long long)blockIdx.z * g.k_chunk;
+    const long long k_end = (k_begin + g.k_chunk < g.K) ? k_begin + g.k_chunk : g.K;
+    float acc[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+
+    for (long long k0 = k_begin; k0 < k_end; k0 += BK) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int idx = t + e * 256;
+            {
+                int il, kl;
+                if (A_KC) { il = idx / BK; kl = idx % BK; } else { il = idx % BM; kl = idx / BM; }
+                const long long i = i0 + il, kk = k0 + kl;
+                float v = 0.f;
+                if (i < g.M && kk < k_end) v = A_KC ? g.A[i * g.lda + kk] : g.A[kk * g.lda + i];
+                As[kl][il] = v;
+            }
+            {
+                int jl, kl;
+                if (B_KC) { jl = idx / BK; kl = idx % BK; } else { jl = idx % BN; kl = idx / BN; }
+                const long long kk = k0 + kl; const int j = j0 + jl;
+                float v = 0.f;
+                if (j < g.N && kk < k_end) v = B_KC ? g.B[(long long)j * g.ldb + kk] : g.B[kk * g.ldb + j];
+                Bs[kl][jl] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kl = 0; kl < BK; ++kl) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kl][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[kl][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kl][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kl][64 + tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const long long i = i0 + (r < 4 ? ty * 4 + r : 64 + ty * 4 + r - 4);
+        if (i >= g.M) continue;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int j = j0 + (c < 4 ? tx * 4 + c : 64 + tx * 4 + c - 4);
+            if (j >= g.N) continue;
+            float v = acc[r][c];
+            float* dst = g.C + i * g.ldc + j;
+            if (g.flags & GEMM_ATOMIC) { atomicAdd(dst, v); continue; }
+            if (g.flags & GEMM_ACCUM) v += *dst;
+            if (g.bias) v += g.bias[j];
+            if (g.flags & GEMM_RELU) v = fmaxf(v, 0.f);
+            if (g.flags & GEMM_SIGMOID) v = 1.f / (1.f + expf(-v));
+            if (g.mask) v = (g.mask[i * g.ldm + j] > 0.f) ? v : 0.f;
+            *dst = v;
+        }
+    }
+}
+
+// column sums of a (rows, cols) matrix accumulated into out[cols] (bias gradients)
+__global__ void colsum_kernel(const float* __restrict__ a, long long rows, int cols, long long lda,
+                              float* __restrict__ out) {
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= cols) return;
+    const long long r0 = (long long)blockIdx.x * 1024;
+    const long long r1 = r0 + 1024 < rows ? r0 + 1024 : rows;
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += a[r * lda + j];
+    atomicAdd(out + j, s);
+}
+
+// head pre-activation gradients (src/nerf.py:26-27 backward): ReLU mask on sigma, sigmoid' on rgb
+__global__ void head_grad_kernel(const float* __restrict__ rgb, const float* __restrict__ sigma,
+                                 const float* __restrict__ g_rgb, const float* __restrict__ g_sigma, long long n,
+                                 float* __restrict__ dz_sigma, float* __restrict__ dz_rgb) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    dz_sigma[t] = (g_sigma && sigma[t] > 0.f) ? g_sigma[t] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float v = rgb[3 * t + c];
+        dz_rgb[3 * t + c] = g_rgb ? g_rgb[3 * t + c] * v * (1.f - v) : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a6 volume_render (src/volume.py:18-44): one warp per ray, lanes over samples, 32-sample chunks with
+// a carried transmittance.  ~ (20 S + 12) B read and 20 (+4S) B written per ray -> HBM-bound.
+__global__ void composite_fwd_kernel(const float* __restrict__ rgb, const float* __restrict__ sigma,
+                                     const float* __restrict__ z, long long z_stride, const float* __restrict__ rd,
+                                     long long n, int S, int white, float* __restrict__ comp, float* __restrict__ depth,
+                                     float* __restrict__ acc_out, float* __restrict__ weights) {
+    const long long ray = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (ray >= n) return;
+    const float* zr = z + ray * z_stride;
+    const float dn = sqrtf(rd[3 * ray] * rd[3 * ray] + rd[3 * ray + 1] * rd[3 * ray + 1] + rd[3 * ray + 2] * rd[3 * ray + 2]);
+    float T_carry = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, dsum = 0.f, asum = 0.f;
+    for (int base = 0; base < S; base += 32) {
+        const int i = base + lane;
+        const bool ok = i < S;
+        float zi = 0.f, alpha = 0.f, q = 1.f;
+        if (ok) {
+            zi = zr[i];
+            const float gap = ((i == S - 1) ? kLastDelta : (zr[i + 1] - zi)) * dn;
+            alpha = 1.f - expf(-sigma[ray * S + i] * gap);
+            q = 1.f - alpha + kEpsT;
+        }
+        float incl = q;  // inclusive product scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl *= up;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.f;
+        const float w = alpha * (T_carry * excl);
+        if (ok) {
+            if (weights) weights[ray * S + i] = w;
+            const float* c = rgb + (ray * S + i) * 3;
+            cr += w * c[0]; cg += w * c[1]; cb += w * c[2];
+            dsum += w * zi; asum += w;
+        }
+        T_carry *= __shfl_sync(0xffffffffu, incl, 31);
+    }
+    cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); dsum = warp_sum(dsum); asum = warp_sum(asum);
+    if (lane == 0) {
+        const float bg = white ? 1.f - asum : 0.f;
+        comp[3 * ray] = cr + bg; comp[3 * ray + 1] = cg + bg; comp[3 * ray + 2] = cb + bg;
+        if (depth) depth[ray] = dsum;
+        if (acc_out) acc_out[ray] = asum;
+    }
+}
+
+// backward: g_i = gC.c_i - [white] sum(gC) + gD z_i + gA + gW_i;
+// dL/dalpha_i = T_i (g_i - R_i), R_{i-1} = g_i alpha_i + q_i R_i, R_{S-1} = 0; dL/dsigma = dL/dalpha * gap * exp(-sigma gap).
+// The recurrence is an affine map per sample; chunks of 32 are scanned with shuffles from the far end.
+__global__ void composite_bwd_kernel(const float* __restrict__ rgb, const float* __restrict__ sigma,
+                                     const float* __restrict__ z, long long z_stride, const float* __restrict__ rd,
+                                     long long n, int S, int white, const float* __restrict__ gC,
+                                     const float* __restrict__ gD, const float* __restrict__ gA,
+                                     const float* __restrict__ gW, float* __restrict__ g_rgb, float* __restrict__ g_sigma) {
+    const long long ray = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (ray >= n) return;
+    const float* zr = z + ray * z_stride;
+    const float dn = sqrtf(rd[3 * ray] * rd[3 * ray] + rd[3 * ray + 1] * rd[3 * ray + 1] + rd[3 * ray + 2] * rd[3 * ray + 2]);
+    const float c0 = gC ? gC[3 * ray] : 0.f, c1 = gC ? gC[3 * ray + 1] : 0.f, c2 = gC ? gC[3 * ray + 2] : 0.f;
+    const float gd = gD ? gD[ray] : 0.f, ga = gA ? gA[ray] : 0.f;
+    const float gconst = ga - (white ? (c0 + c1 + c2) : 0.f);
+    const int nchunk = (S + 31) / 32;
+    // pass 1: transmittance entering each chunk
+    float T_in = 1.f;
+    float T_chunk[8];  // S <= 256 on this path (host checks)
+    for (int ch = 0; ch < nchunk; ++ch) {
+        T_chunk[ch] = T_in;
+        const int i = ch * 32 + lane;
+        float q = 1.f;
+        if (i < S) {
+            const float gap = ((i == S - 1) ? kLastDelta : (zr[i + 1] - zr[i])) * dn;
+            q = 1.f - (1.f - expf(-sigma[ray * S + i] * gap)) + kEpsT;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q *= __shfl_xor_sync(0xffffffffu, q, o);
+        T_in *= q;
+    }
+    // pass 2: chunks from the far end, carrying R
+    float R_carry = 0.f;
+    for (int ch = nchunk - 1; ch >= 0; --ch) {
+        const int i = ch * 32 + lane;
+        const bool ok = i < S;
+        float zi = 0.f, e = 1.f, gap = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+        if (ok) {
+            zi = zr[i];
+            gap = ((i == S - 1) ? kLastDelta : (zr[i + 1] - zi)) * dn;
+            e = expf(-sigma[ray * S + i] * gap);
+            const float* c = rgb + (ray * S + i) * 3;
+            cr = c[0]; cg = c[1]; cb = c[2];
+        }
+        const float alpha = 1.f - e, q = ok ? (1.f - alpha + kEpsT) : 1.f;
+        const float g = ok ? (c0 * cr + c1 * cg + c2 * cb + gd * zi + gconst + (gW ? gW[ray * S + i] : 0.f)) : 0.f;
+        // exclusive transmittance inside the chunk
+        float incl = q;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl *= up;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.f;
+        const float T = T_chunk[ch] * excl;
+        // suffix composition of f_i(R) = a_i + q_i R : (Aa, Qq) <- f_i o f_{i+o}
+        float Aa = ok ? g * alpha : 0.f, Qq = q;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float An = __shfl_down_sync(0xffffffffu, Aa, o);
+            const float Qn = __shfl_down_sync(0xffffffffu, Qq, o);
+            if (lane + o < 32) { Aa = fmaf(Qq, An, Aa); Qq *= Qn; }
+        }
+        // F_i(R_carry) = R_{i-1}; R_i is lane i+1's value (lane 31 takes the carry itself)
+        const float Rprev = fmaf(Qq, R_carry, Aa);
+        float Ri = __shfl_down_sync(0xffffffffu, Rprev, 1);
+        if (lane == 31) Ri = R_carry;
+        if (ok) {
+            const float w = alpha * T;
+            if (g_rgb) { float* o3 = g_rgb + (ray * S + i) * 3; o3[0] = w * c0; o3[1] = w * c1; o3[2] = w * c2; }
+            if (g_sigma) g_sigma[ray * S + i] = T * (g - Ri) * gap * e;
+        }
+        R_carry = __shfl_sync(0xffffffffu, Rprev, 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a7 loss / PSNR (src/train.py:122-123, src/utils.py:14-15)
+__global__ void sqerr_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float scale,
+                                 float* __restrict__ out) {
+    float s = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float d = a[i] - b[i];
+        s = fmaf(d, d, s);
+    }
+    s = warp_sum(s);
+    __shared__ float part[32];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = (threadIdx.x < (blockDim.x >> 5)) ? part[threadIdx.x] : 0.f;
+        s = warp_sum(s);
+        if (threadIdx.x == 0) atomicAdd(out, s * scale);
+    }
+}
+__global__ void psnr_kernel(float* out2) { out2[1] = -10.f * log10f(fmaxf(out2[0], 1e-10f)); }
+
+// a9 Adam (torch.optim.Adam single-tensor math, src/train.py:80) fused with GradScaler unscale / skip
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr_over_bc1, float inv_sqrt_bc2, float b1,
+                            float b2, float eps, float inv_scale, const int* __restrict__ found_inf) {
+    if (found_inf && *found_inf) return;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i] * inv_scale;
+    const float mi = fmaf(1.f - b1, gi - m[i], m[i]);              // lerp_(grad, 1-beta1)
+    const float vi = fmaf(v[i], b2, (1.f - b2) * gi * gi);          // mul_(beta2).addcmul_(g,g,1-beta2)
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] = p[i] - lr_over_bc1 * (mi / denom);
+}
+__global__ void check_finite_kernel(const float* __restrict__ g, long long n, int* __restrict__ flag) {
+    bool bad = false;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        bad |= !isfinite(g[i]);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+// squared-error gradient of the fused fp32 train path: gC = 2 (C - t) / denom, loss += sum (C-t)^2 / denom
+__global__ void mse_grad_kernel(const float* __restrict__ c, const float* __restrict__ t, long long n3, float inv_denom,
+                                float* __restrict__ gC, float* __restrict__ loss) {
+    float s = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n3; i += (long long)gridDim.x * blockDim.x) {
+        const float d = c[i] - t[i];
+        gC[i] = 2.f * d * inv_denom;
+        s = fmaf(d, d, s);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(loss, s * inv_denom);
+}
+
+// ================================================================================================
+// host-side launchers
+static inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
+
+int launch_get_rays(int H, int W, float focal, const float* c2w, long long first, long long n, float* ro, float* rd,
+                    cudaStream_t s) {
+    if (n <= 0) return 0;
+    get_rays_kernel<<<blocks_for(n, 256), 256, 0, s>>>(H, W, focal, c2w, first, n, ro, rd);
+    return count_launch();
+}
+int launch_gather3(const long long* idx, long long n, long long n_src, const float* sa, float* da, const float* sb,
+                   float* db, const float* sc, float* dc, cudaStream_t s) {
+    if (n <= 0) return 0;
+    gather3_kernel<<<blocks_for(3 * n, 256), 256, 0, s>>>(idx, n, n_src, sa, da, sb, db, sc, dc);
+    return count_launch();
+}
+int launch_stratified(const float* ro, long long os, const float* rd, long long n, int S, float nr, float fr,
+                      const float* nray, const float* fray, const float* jit, float* z, float* pts, cudaStream_t s) {
+    if (n <= 0) return 0;
+    stratified_kernel<<<blocks_for(n * S, 256), 256, 0, s>>>(ro, os, rd, n, S, nr, fr, nray, fray, jit, z, pts);
+    return count_launch();
+}
+int launch_posenc(const float* x, long long n, int L, int inc, float* out, cudaStream_t s) {
+    if (n <= 0) return 0;
+    const long long tot = n * (6 * L + (inc ? 3 : 0));
+    posenc_kernel<<<blocks_for(tot, 256), 256, 0, s>>>(x, n, L, inc, out);
+    return count_launch();
+}
+int launch_posenc_bwd(const float* x, const float* g, long long n, int L, int inc, float* gx, cudaStream_t s) {
+    if (n <= 0) return 0;
+    posenc_bwd_kernel<<<blocks_for(3 * n, 256), 256, 0, s>>>(x, g, n, L, inc, gx);
+    return count_launch();
+}
+int launch_gemm(const GemmArgs& g, bool a_kc, bool b_kc, cudaStream_t s) {
+    if (g.M <= 0 || g.N <= 0) return 0;
+    GemmArgs a = g;
+    if (a.k_chunk <= 0) a.k_chunk = a.K > 0 ? a.K : 1;
+    dim3 grid(blocks_for(a.M, BM), blocks_for(a.N, BN), (unsigned)((a.K + a.k_chunk - 1) / a.k_chunk));
+    if (grid.z == 0) grid.z = 1;
+    if (a_kc && b_kc) sgemm_kernel<true, true><<<grid, 256, 0, s>>>(a);
+    else if (a_kc && !b_kc) sgemm_kernel<true, false><<<grid, 256, 0, s>>>(a);
+    else if (!a_kc && !b_kc) sgemm_kernel<false, false><<<grid, 256, 0, s>>>(a);
+    else sgemm_kernel<false, true><<<grid, 256, 0, s>>>(a);
+    return count_launch();
+}
+int launch_colsum(const float* a, long long rows, int cols, long long lda, float* out, cudaStream_t s) {
+    if (rows <= 0 || cols <= 0) return 0;
+    dim3 grid(blocks_for(rows, 1024), blocks_for(cols, 128));
+    colsum_kernel<<<grid, 128, 0, s>>>(a, rows, cols, lda, out);
+    return count_launch();
+}
+int launch_head_grad(const float* rgb, const float* sigma, const float* g_rgb, const float* g_sigma, long long n,
+                     float* dzs, float* dzr, cudaStream_t s) {
+    if (n <= 0) return 0;
+    head_grad_kernel<<<blocks_for(n, 256), 256, 0, s>>>(rgb, sigma, g_rgb, g_sigma, n, dzs, dzr);
+    return count_launch();
+}
+int launch_composite_fwd(const float* rgb, const float* sigma, const float* z, long long zs, const float* rd, long long n,
+                         int S, int white, float* comp, float* depth, float* acc, float* w, cudaStream_t s) {
+    if (n <= 0) return 0;
+    composite_fwd_kernel<<<blocks_for(n * 32, 256), 256, 0, s>>>(rgb, sigma, z, zs, rd, n, S, white, comp, depth, acc, w);
+    return count_launch();
+}
+int launch_composite_bwd(const float* rgb, const float* sigma, const float* z, long long zs, const float* rd, long long n,
+                         int S, int white, const float* gC, const float* gD, const float* gA, const float* gW,
+                         float* g_rgb, float* g_sigma, cudaStream_t s) {
+    if (n <= 0) return 0;
+    composite_bwd_kernel<<<blocks_for(n * 32, 256), 256, 0, s>>>(rgb, sigma, z, zs, rd, n, S, white, gC, gD, gA, gW, g_rgb, g_sigma);
+    return count_launch();
+}
+int launch_mse_psnr(const float* a, const float* b, long long n, float* out2, cudaStream_t s) {
+    cudaMemsetAsync(out2, 0, 2 * sizeof(float), s);
+    if (n > 0) {
+        unsigned nb = blocks_for(n, 256 * 8); if (nb > 1184) nb = 1184; if (nb == 0) nb = 1;
+        sqerr_sum_kernel<<<nb, 256, 0, s>>>(a, b, n, 1.f / (float)n, out2);
+        count_launch();
+    }
+    psnr_kernel<<<1, 1, 0, s>>>(out2);
+    return count_launch();
+}
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float b1, float b2,
+                float eps, float inv_scale, const int* found_inf, cudaStream_t s) {
+    if (n <= 0) return 0;
+    const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+    adam_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, g, m, v, n, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), b1, b2,
+                                                    eps, inv_scale, found_inf);
+    return count_launch();
+}
+int launch_check_finite(const float* g, long long n, int* flag, cudaStream_t s) {
+    cudaMemsetAsync(flag, 0, sizeof(int), s);
+    if (n <= 0) return 0;
+    unsigned nb = blocks_for(n, 256 * 4); if (nb > 592) nb = 592;
+    check_finite_kernel<<<nb, 256, 0, s>>>(g, n, flag);
+    return count_launch();
+}
+int launch_mse_grad(const float* c, const float* t, long long n3, float inv_denom, float* gC, float* loss, cudaStream_t s) {
+    if (n3 <= 0) return 0;
+    unsigned nb = blocks_for(n3, 256 * 4); if (nb > 592) nb = 592;
+    mse_grad_kernel<<<nb, 256, 0, s>>>(c, t, n3, inv_denom, gC, loss);
+    return count_launch();
+}
+
+}  // namespace tnerf

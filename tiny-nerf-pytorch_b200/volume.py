@@ -1,0 +1,98 @@
+"""volume.volume_render -- drop-in for the reference's src/volume.py:3-44."""
+import torch
+
+import _engine as E
+import _lazy
+import engine
+
+
+class _Composite(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, rgb, sigma, z_vals, rays_d, white):
+        dev = E.need_cuda(rgb, sigma, z_vals, rays_d)
+        n, S = int(z_vals.shape[0]), int(z_vals.shape[1])
+        rgb_c, sig_c, rd = E.f32c(rgb), E.f32c(sigma).reshape(n, S), E.f32c(rays_d)
+        if z_vals.stride(0) == 0 and z_vals.stride(1) == 1 and z_vals.dtype == torch.float32:
+            z, zs = z_vals, 0           # the expanded deterministic row of stratified_samples
+        else:
+            z, zs = E.f32c(z_vals), S
+        comp = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        depth = torch.empty((n, 1), dtype=torch.float32, device=dev)
+        acc = torch.empty((n, 1), dtype=torch.float32, device=dev)
+        w = torch.empty((n, S), dtype=torch.float32, device=dev)
+        E.check(E.lib().tnerf_composite_fwd(E.ptr(rgb_c), E.ptr(sig_c), E.ptr(z), zs, E.ptr(rd), n, S, int(white), E.ptr(comp),
+                                            E.ptr(depth), E.ptr(acc), E.ptr(w), E.stream(dev)), "tnerf_composite_fwd")
+        ctx.save_for_backward(rgb_c, sig_c, z, rd)
+        ctx.cfg = (n, S, zs, white, tuple(sigma.shape))
+        return comp, depth, acc, w
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gC, gD, gA, gW):
+        rgb_c, sig_c, z, rd = ctx.saved_tensors
+        n, S, zs, white, sig_shape = ctx.cfg
+        if S > 256:
+            raise RuntimeError("volume_render backward supports n_samples <= 256")
+        dev = rgb_c.device
+        g_rgb = torch.empty_like(rgb_c)
+        g_sig = torch.empty_like(sig_c)
+        gC, gD, gA, gW = (E.f32c(g) if g is not None else None for g in (gC, gD, gA, gW))
+        E.check(E.lib().tnerf_composite_bwd(E.ptr(rgb_c), E.ptr(sig_c), E.ptr(z), zs, E.ptr(rd), n, S, int(white), E.ptr(gC),
+                                            E.ptr(gD), E.ptr(gA), E.ptr(gW), E.ptr(g_rgb), E.ptr(g_sig), E.stream(dev)),
+                "tnerf_composite_bwd")
+        return g_rgb, g_sig.reshape(sig_shape), None, None, None
+
+
+class _LazyWeights:
+    """value provider for the deferred `weights` output of a fused render"""
+
+    def __init__(self, args):
+        self.args, self.cache = args, {}
+        self.spec, self.encoder, self.model = None, None, None
+
+    def value(self, kind):
+        if "w" not in self.cache:
+            self.cache["w"] = engine.render_weights(*self.args)
+        return self.cache["w"]
+
+
+def _try_fused(rgb, sigma, z_vals, rays_d, white_bkgd):
+    if not (isinstance(rgb, _lazy.Deferred) and isinstance(sigma, _lazy.Deferred)):
+        return None
+    node = rgb._node
+    if sigma._node is not node or rgb._kind != "rgb" or sigma._kind != "sigma" or node.cache:
+        return None
+    s = node.spec
+    if tuple(rgb.shape) != (s.n, s.S, 3) or tuple(sigma.shape) not in ((s.n, s.S, 1), (s.n, s.S)):
+        return None
+    if s.near_t is not None or s.far_t is not None:
+        return None
+    if isinstance(z_vals, _lazy.Deferred) or isinstance(rays_d, _lazy.Deferred):
+        return None
+    if not _lazy.same_tensor(z_vals, s.z_vals) or rays_d.data_ptr() != s.rd.data_ptr() or tuple(rays_d.shape) != (s.n, 3):
+        return None
+    model, enc = node.model, node.encoder
+    prec, bprec = engine.default_precision(), engine.default_bwd_precision()
+    E.handle_for(model, s.rd.device).set_encoding(enc.num_freqs, enc.include_input)
+    if prec == E.PREC_F16_TC and not engine.fused_supported(model, enc, s.S, s.rd.device):
+        prec = bprec = E.PREC_F32_SIMT
+    comp, depth, acc = engine._FusedRender.apply(model, s.ro, s.o_stride, s.rd, s.n, s.S, s.near, s.far, s.jitter,
+                                                 bool(white_bkgd), prec, bprec, *model._params())
+    wnode = _LazyWeights((model, s.ro, s.o_stride, s.rd, s.n, s.S, s.near, s.far, s.jitter, bool(white_bkgd), prec))
+    weights = _lazy.Deferred((s.n, s.S), s.rd.device, wnode, "w")
+    return comp, depth, acc, weights
+
+
+def volume_render(rgb, sigma, z_vals, rays_d, white_bkgd=True):
+    """Alpha-composite per-sample colour/density along each ray.
+
+    rgb (N,S,3), sigma (N,S,1), z_vals (N,S), rays_d (N,3) -> (comp_rgb (N,3), depth (N,1), acc (N,1),
+    weights (N,S)).  delta_last = 1e10, T = exclusive cumprod(1 - alpha + 1e-10), white background adds
+    1 - acc -- the reference's arithmetic, as one scan kernel (or fused with the MLP when rgb/sigma are
+    still deferred)."""
+    fused = _try_fused(rgb, sigma, z_vals, rays_d, white_bkgd)
+    if fused is not None:
+        return fused
+    rgb, sigma, z_vals, rays_d = (_lazy._real(t) for t in (rgb, sigma, z_vals, rays_d))
+    return _Composite.apply(rgb, sigma, z_vals, rays_d, bool(white_bkgd))
