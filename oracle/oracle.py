@@ -133,7 +133,7 @@ def init_params(in_dim: int, hidden: int = 128, depth: int = 4, skip_at: int = 2
     return out
 
 
-def mlp_forward(p: Params, x: Tensor, depth: int = 4, skip_at: int = 2) -> Tuple[Tensor, Tensor]:
+def mlp_forward(p: Params, x: Tensor, depth: int = 4, skip_at: int = 2, return_pre: bool = False):
     """h = relu(W_i h + b_i); after layer skip_at-1 the input is appended BEHIND h
     (src/nerf.py:35-38); rgb = sigmoid(W_c h + b_c), sigma = relu(W_s h + b_s) (:26-27,39-41)."""
     h = x
@@ -142,8 +142,21 @@ def mlp_forward(p: Params, x: Tensor, depth: int = 4, skip_at: int = 2) -> Tuple
         if i == skip_at - 1:
             h = torch.cat([h, x], dim=1)
     rgb = torch.sigmoid(torch.addmm(p["rgb.0.bias"], h, p["rgb.0.weight"].t()))
-    sigma = torch.addmm(p["sigma.0.bias"], h, p["sigma.0.weight"].t()).clamp_min(0)
+    pre = torch.addmm(p["sigma.0.bias"], h, p["sigma.0.weight"].t())
+    sigma = pre.clamp_min(0)
+    if return_pre:
+        return rgb, sigma, pre
     return rgb, sigma
+
+
+def last_sample_sigma_pre(p: Params, rays_o: Tensor, rays_d: Tensor, near, far, n_samples: int, u=None,
+                          num_freqs: int = 10, include_input: bool = True, depth: int = 4, skip_at: int = 2) -> Tensor:
+    """Pre-activation density of each ray's LAST sample.  Because delta_last = 1e10 (src/volume.py:20),
+    a ray's acc/rgb/depth are discontinuous in this value at 0: parity tests use it to
+    set aside rays whose last sample sits on the discontinuity."""
+    z, pts = stratified(near, far, n_samples, rays_o, rays_d, u)
+    feat = posenc(pts[:, -1, :], num_freqs, include_input)
+    return mlp_forward(p, feat, depth, skip_at, return_pre=True)[2].reshape(-1)
 
 
 # --------------------------------------------------------------------------------------

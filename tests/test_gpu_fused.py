@@ -51,7 +51,8 @@ def test_umma_selftest(dev, mode, NK):
     a = torch.randn((K, 128) if mode == 3 else (128, K), generator=g)
     b = torch.randn((K, N) if mode == 2 else (N, K), generator=g)
     d = torch.full((128, N), float("nan"), device=dev)
-    E.check(E.lib().tnerf_umma_selftest(E.ptr(a.to(dev)), E.ptr(b.to(dev)), N, K, mode, E.ptr(d), E.stream(dev)))
+    a_d, b_d = a.to(dev), b.to(dev)           # named: must outlive the asynchronous launch
+    E.check(E.lib().tnerf_umma_selftest(E.ptr(a_d), E.ptr(b_d), N, K, mode, E.ptr(d), E.stream(dev)))
     A = a.half().float().t() if mode == 3 else a.half().float()
     B = b.half().float().t() if mode == 2 else b.half().float()
     ref = A @ B.t()
@@ -85,9 +86,14 @@ def test_fused_render_vs_oracle(dev, prec, case):
                                               t_rand=None if u is None else u.to(dev), precision=prec)
     oc, od, oa, _ = O.render_rays(p, ro, rd, 2.0, 6.0, S, u, num_freqs=L, include_input=inc, depth=case["cfg"][2], skip_at=case["cfg"][3])
     tol = 2e-5 if prec == "f32" else 2e-3
-    errs = [(comp.cpu() - oc).abs().max().item(), (depth.cpu() - od).abs().max().item(), (acc.cpu() - oa).abs().max().item()]
-    # the sigma_last/1e10 discontinuity can flip a ray: allow, but report, rays whose last-sample density changes sign
-    assert errs[0] < tol and errs[2] < tol and errs[1] < tol * 6.0, errs
+    # The sigma_last / 1e10 discontinuity: a ray whose LAST sample has a density
+    # pre-activation within rounding of 0 flips between alpha_last = 0 and 1.  Such rays are set aside
+    # (and counted); every other ray must meet the bar.
+    pre = O.last_sample_sigma_pre(p, ro, rd, 2.0, 6.0, S, u, num_freqs=L, include_input=inc, depth=case["cfg"][2], skip_at=case["cfg"][3])
+    keep = pre.abs() > (1e-5 if prec == "f32" else 4e-3)
+    assert keep.float().mean() > 0.97, f"{(~keep).sum().item()} of {n} rays on the discontinuity"
+    errs = [(comp.cpu() - oc)[keep].abs().max().item(), (depth.cpu() - od)[keep].abs().max().item(), (acc.cpu() - oa)[keep].abs().max().item()]
+    assert errs[0] < tol and errs[2] < tol and errs[1] < tol * 6.0, errs    # depth is a sum of w*z with z up to 6
     assert acc.min() >= 0 and comp.shape == (n, 3) and depth.shape == (n, 1)
 
 
@@ -105,7 +111,9 @@ def test_fused_render_black_background_and_broadcast_origin(dev, prec):
     oro, ord_ = O.get_rays(20, 30, 40.0, pose)
     oc, od, oa, _ = O.render_rays(p, oro, ord_, 2.0, 6.0, 64, None, white_bkgd=False)
     tol = 2e-5 if prec == "f32" else 2e-3
-    assert (comp.cpu() - oc).abs().max() < tol and (acc.cpu() - oa).abs().max() < tol
+    keep = O.last_sample_sigma_pre(p, oro, ord_, 2.0, 6.0, 64, None).abs() > (1e-5 if prec == "f32" else 4e-3)
+    assert keep.float().mean() > 0.97
+    assert (comp.cpu() - oc)[keep].abs().max() < tol and (acc.cpu() - oa)[keep].abs().max() < tol
 
 
 # ------------------------------------------------------------------------------------------ gradients
@@ -159,12 +167,13 @@ def test_reference_call_sequence_is_fused(dev):
     scaler = torch.amp.GradScaler("cuda")
     scaler.scale(loss).backward()
     l_ref, g_ref, (oc, _, _) = O.loss_and_grads(p, ro, rd, target, 2.0, 6.0, S, u)
-    assert (comp_rgb.detach().cpu() - oc).abs().max() < 2e-3
+    keep = O.last_sample_sigma_pre(p, ro, rd, 2.0, 6.0, S, u).abs() > 4e-3
+    assert keep.float().mean() > 0.97 and (comp_rgb.detach().cpu() - oc)[keep].abs().max() < 2e-3
     for k, v in model.named_parameters():
         assert rel_l2(v.grad.cpu() / scaler.get_scale(), g_ref[k]) < 1e-2, k
     assert w.shape == (n, S)
     ow = O.render_rays(p, ro, rd, 2.0, 6.0, S, u)[3]
-    assert ((w + 0).cpu() - ow).abs().max() < 2e-3
+    assert ((w + 0).cpu() - ow)[keep].abs().max() < 2e-3
 
 
 def test_deferred_falls_back_when_chain_is_broken(dev):

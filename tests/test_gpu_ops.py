@@ -33,7 +33,7 @@ def test_get_rays_golden(golden, dev, tag):
     from rays import get_rays
     H, W, focal = golden[f"rays_{tag}_HWf"]
     ro, rd = get_rays(int(H), int(W), float(focal), T(golden[f"rays_{tag}_c2w"]).to(dev))
-    assert ro.shape == rd.shape == (int(H) * int(W), 3) and ro.stride() == (0, 1) and rd.dtype == torch.float32
+    assert ro.shape == rd.shape == (int(H) * int(W), 3) and ro.stride(0) == 0 and rd.dtype == torch.float32
     norm_close(ro, golden[f"rays_{tag}_o"], 0.0)
     norm_close(rd, golden[f"rays_{tag}_d"], 1e-6)
 
@@ -279,7 +279,8 @@ def test_psnr_and_mse_kernel(golden, dev):
     g = torch.Generator().manual_seed(0)
     a, b = torch.rand(4096, 3, generator=g), torch.rand(4096, 3, generator=g)
     out = torch.empty(2, device=dev)
-    E.check(E.lib().tnerf_mse_psnr(E.ptr(a.to(dev)), E.ptr(b.to(dev)), a.numel(), E.ptr(out), E.stream(dev)))
+    a_d, b_d = a.to(dev), b.to(dev)
+    E.check(E.lib().tnerf_mse_psnr(E.ptr(a_d), E.ptr(b_d), a.numel(), E.ptr(out), E.stream(dev)))
     m = O.mse(a, b)
     assert abs(out[0].item() - m.item()) < 1e-6 and abs(out[1].item() - O.mse2psnr(m).item()) < 1e-4
 
@@ -297,15 +298,17 @@ def test_adam_kernel_matches_torch_optim(dev):
         grad = torch.randn(n, generator=g) * (10.0 ** (step - 4))
         p_ref.grad = grad.clone()
         opt.step()
-        E.check(E.lib().tnerf_check_finite(E.ptr(grad.to(dev)), n, E.ptr(flag), E.stream(dev)))
-        E.check(E.lib().tnerf_adam_step(E.ptr(p), E.ptr((grad * 8).to(dev)), E.ptr(m), E.ptr(v), n, step, 5e-4, 0.9, 0.999, 1e-8,
+        g_d, g8_d = grad.to(dev), (grad * 8).to(dev)
+        E.check(E.lib().tnerf_check_finite(E.ptr(g_d), n, E.ptr(flag), E.stream(dev)))
+        E.check(E.lib().tnerf_adam_step(E.ptr(p), E.ptr(g8_d), E.ptr(m), E.ptr(v), n, step, 5e-4, 0.9, 0.999, 1e-8,
                                         1.0 / 8, E.ptr(flag), E.stream(dev)))
         assert flag.item() == 0
         assert (p.cpu() - p_ref.detach()).abs().max() < 2e-7
     bad = torch.randn(n, generator=g); bad[123] = float("inf")
     before = p.clone()
-    E.check(E.lib().tnerf_check_finite(E.ptr(bad.to(dev)), n, E.ptr(flag), E.stream(dev)))
-    E.check(E.lib().tnerf_adam_step(E.ptr(p), E.ptr(bad.to(dev)), E.ptr(m), E.ptr(v), n, 6, 5e-4, 0.9, 0.999, 1e-8, 1.0, E.ptr(flag), E.stream(dev)))
+    bad_d = bad.to(dev)
+    E.check(E.lib().tnerf_check_finite(E.ptr(bad_d), n, E.ptr(flag), E.stream(dev)))
+    E.check(E.lib().tnerf_adam_step(E.ptr(p), E.ptr(bad_d), E.ptr(m), E.ptr(v), n, 6, 5e-4, 0.9, 0.999, 1e-8, 1.0, E.ptr(flag), E.stream(dev)))
     assert flag.item() == 1 and torch.equal(p, before)          # GradScaler semantics: skipped step
 
 

@@ -139,6 +139,7 @@ int tnerf_get_rays(int H, int W, float focal, const float* c2w, long long first_
 
 int tnerf_gather3(const long long* index, long long n, long long n_src, const float* sa, float* da, const float* sb, float* db,
                   const float* sc, float* dc, void* stream) {
+    if (n == 0) return 0;
     if (!index || n < 0 || (sa && !da) || (sb && !db) || (sc && !dc)) return bad("tnerf_gather3: invalid argument");
     return launch_gather3(index, n, n_src, sa, da, sb, db, sc, dc, (cudaStream_t)stream);
 }
@@ -146,16 +147,19 @@ int tnerf_gather3(const long long* index, long long n, long long n_src, const fl
 int tnerf_stratified(const float* rays_o, long long o_stride, const float* rays_d, long long n_rays, int n_samples, float near_,
                      float far_, const float* near_ray, const float* far_ray, const float* jitter, float* z_vals, float* pts,
                      void* stream) {
+    if (n_rays == 0) return 0;
     if (n_rays < 0 || n_samples < 1 || (pts && (!rays_o || !rays_d))) return bad("tnerf_stratified: invalid argument");
     return launch_stratified(rays_o, o_stride, rays_d, n_rays, n_samples, near_, far_, near_ray, far_ray, jitter, z_vals, pts,
                              (cudaStream_t)stream);
 }
 
 int tnerf_posenc(const float* x, long long n_pts, int num_freqs, int include_input, float* out, void* stream) {
+    if (n_pts == 0) return 0;
     if (!x || !out || n_pts < 0 || num_freqs < 0 || num_freqs > 30) return bad("tnerf_posenc: invalid argument");
     return launch_posenc(x, n_pts, num_freqs, include_input, out, (cudaStream_t)stream);
 }
 int tnerf_posenc_bwd(const float* x, const float* g_out, long long n_pts, int num_freqs, int include_input, float* g_x, void* stream) {
+    if (n_pts == 0) return 0;
     if (!x || !g_out || !g_x || n_pts < 0 || num_freqs < 0 || num_freqs > 30) return bad("tnerf_posenc_bwd: invalid argument");
     return launch_posenc_bwd(x, g_out, n_pts, num_freqs, include_input, g_x, (cudaStream_t)stream);
 }
@@ -214,6 +218,7 @@ int tnerf_pack_weights(tnerf_handle* h, void* stream) {
 }
 
 int tnerf_mlp_fwd(tnerf_handle* h, const float* x, long long n, float* rgb, float* sigma, float* acts, void* stream) {
+    if (n == 0) return 0;
     if (!h || h->params.empty() || !x || !rgb || !sigma || n < 0) return bad("tnerf_mlp_fwd: invalid argument / params not bound");
     float* tmp = nullptr;
     if (!acts) {
@@ -226,6 +231,7 @@ int tnerf_mlp_fwd(tnerf_handle* h, const float* x, long long n, float* rgb, floa
 long long tnerf_mlp_bwd_scratch_floats(const tnerf_handle* h, long long n) { return h ? mlp_bwd_scratch_floats(h, n) : -1; }
 int tnerf_mlp_bwd(tnerf_handle* h, const float* x, long long n, const float* acts, const float* rgb, const float* sigma,
                   const float* g_rgb, const float* g_sigma, float* grads, float* g_x, float* scratch, void* stream) {
+    if (n == 0) return 0;
     if (!h || h->params.empty() || !x || !acts || !rgb || !sigma || !grads || !scratch || n < 0) return bad("tnerf_mlp_bwd: invalid argument");
     return mlp_backward_f32(h, x, n, acts, rgb, sigma, g_rgb, g_sigma, grads, g_x, scratch, (cudaStream_t)stream);
 }
@@ -233,6 +239,7 @@ int tnerf_mlp_bwd(tnerf_handle* h, const float* x, long long n, const float* act
 int tnerf_composite_fwd(const float* rgb, const float* sigma, const float* z_vals, long long z_stride, const float* rays_d,
                         long long n_rays, int n_samples, int white_bkgd, float* comp_rgb, float* depth, float* acc, float* weights,
                         void* stream) {
+    if (n_rays == 0) return 0;
     if (!rgb || !sigma || !z_vals || !rays_d || !comp_rgb || n_rays < 0 || n_samples < 1) return bad("tnerf_composite_fwd: invalid argument");
     return launch_composite_fwd(rgb, sigma, z_vals, z_stride, rays_d, n_rays, n_samples, white_bkgd, comp_rgb, depth, acc, weights,
                                 (cudaStream_t)stream);
@@ -240,6 +247,7 @@ int tnerf_composite_fwd(const float* rgb, const float* sigma, const float* z_val
 int tnerf_composite_bwd(const float* rgb, const float* sigma, const float* z_vals, long long z_stride, const float* rays_d,
                         long long n_rays, int n_samples, int white_bkgd, const float* g_comp, const float* g_depth,
                         const float* g_acc, const float* g_weights, float* g_rgb, float* g_sigma, void* stream) {
+    if (n_rays == 0) return 0;
     if (!rgb || !sigma || !z_vals || !rays_d || n_rays < 0 || n_samples < 1 || n_samples > 256)
         return bad("tnerf_composite_bwd: invalid argument (n_samples <= 256)");
     return launch_composite_bwd(rgb, sigma, z_vals, z_stride, rays_d, n_rays, n_samples, white_bkgd, g_comp, g_depth, g_acc, g_weights,
@@ -249,6 +257,7 @@ int tnerf_composite_bwd(const float* rgb, const float* sigma, const float* z_val
 int tnerf_render_fwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long long n_rays, float near_, float far_, int n_samples,
                      const float* jitter, int white_bkgd, int precision, float* comp_rgb, float* depth, float* acc, float* weights,
                      float* rays_d_out, void* stream) {
+    if (n_rays == 0) return 0;
     if (!h || h->params.empty() || !comp_rgb || n_rays < 0 || n_samples < 1) return bad("tnerf_render_fwd: invalid argument / params not bound");
     if (int e = check_source(rays_host)) return e;
     const RaySource rs = to_device_source(rays_host);
@@ -263,6 +272,7 @@ int tnerf_render_fwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long lo
 int tnerf_render_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long long n_rays, float near_, float far_, int n_samples,
                      const float* jitter, int white_bkgd, int precision, const float* g_comp, const float* g_depth, const float* g_acc,
                      const float* g_weights, float grad_scale, float* grads, void* stream) {
+    if (n_rays == 0) return 0;
     if (!h || h->params.empty() || !grads || n_rays < 0 || n_samples < 1) return bad("tnerf_render_bwd: invalid argument");
     if (int e = check_source(rays_host)) return e;
     const RaySource rs = to_device_source(rays_host);
@@ -277,6 +287,7 @@ int tnerf_render_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long lo
 int tnerf_train_fwd_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, const float* target, long long n_rays, float near_,
                         float far_, int n_samples, const float* jitter, int white_bkgd, int precision, float loss_denom,
                         float* comp_rgb, float* loss_sum, float* grads, void* stream) {
+    if (n_rays == 0) return 0;
     if (!h || h->params.empty() || !target || !grads || !loss_sum || n_rays < 0 || n_samples < 1 || !(loss_denom > 0.f))
         return bad("tnerf_train_fwd_bwd: invalid argument");
     if (int e = check_source(rays_host)) return e;

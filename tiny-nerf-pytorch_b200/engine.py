@@ -32,9 +32,11 @@ def ray_source(rays_o=None, o_stride=3, rays_d=None, c2w=None, H=0, W=0, focal=0
     return rs
 
 
-def _origin_arg(rays_o):
-    if rays_o.dim() == 2 and rays_o.stride(0) == 0 and rays_o.stride(1) == 1 and rays_o.dtype == torch.float32:
-        return rays_o, 0
+def origin_arg(rays_o):
+    """(tensor, row stride) for the C ABI: a broadcast origin (get_rays' expand view, stride 0 over rays)
+    is passed as its single row, anything else as a dense (N,3) fp32 tensor."""
+    if rays_o.dim() == 2 and rays_o.shape[0] > 0 and rays_o.stride(0) == 0:
+        return E.f32c(rays_o[0]), 0
     return E.f32c(rays_o), 3
 
 
@@ -97,7 +99,7 @@ def render_rays(model, encoder, rays_o, rays_d, near: float, far: float, n_sampl
     h.set_encoding(encoder.num_freqs, encoder.include_input)
     if prec == E.PREC_F16_TC and not fused_supported(model, encoder, n_samples, dev):
         prec = bprec = E.PREC_F32_SIMT
-    ro, o_stride = _origin_arg(rays_o)
+    ro, o_stride = origin_arg(rays_o)
     rd = E.f32c(rays_d)
     jit = E.f32c(t_rand) if t_rand is not None else None
     return _FusedRender.apply(model, ro, o_stride, rd, int(rd.shape[0]), int(n_samples), float(near), float(far), jit,

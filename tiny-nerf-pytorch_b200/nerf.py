@@ -18,7 +18,7 @@ class _MLP(torch.autograd.Function):
         n = xc.shape[0]
         rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
         sigma = torch.empty((n, 1), dtype=torch.float32, device=dev)
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        need_grad = any(ctx.needs_input_grad)     # (grad mode is always off inside Function.forward)
         acts = torch.empty((module.depth, n, module.hidden), dtype=torch.float32, device=dev) if need_grad else None
         E.check(E.lib().tnerf_mlp_fwd(h.h, E.ptr(xc), n, E.ptr(rgb), E.ptr(sigma), E.ptr(acts), E.stream(dev)), "tnerf_mlp_fwd")
         if need_grad:
@@ -36,8 +36,9 @@ class _MLP(torch.autograd.Function):
         grads = torch.zeros(h.param_count, dtype=torch.float32, device=dev)
         gx = torch.empty_like(xc) if ctx.x_grad else None
         scratch = torch.empty(int(E.lib().tnerf_mlp_bwd_scratch_floats(h.h, n)), dtype=torch.float32, device=dev)
-        E.check(E.lib().tnerf_mlp_bwd(h.h, E.ptr(xc), n, E.ptr(acts), E.ptr(rgb), E.ptr(sigma), E.ptr(E.f32c(g_rgb)),
-                                      E.ptr(E.f32c(g_sigma)), E.ptr(grads), E.ptr(gx), E.ptr(scratch), E.stream(dev)),
+        g_rgb, g_sigma = E.f32c(g_rgb), E.f32c(g_sigma)     # keep alive until the launch is enqueued
+        E.check(E.lib().tnerf_mlp_bwd(h.h, E.ptr(xc), n, E.ptr(acts), E.ptr(rgb), E.ptr(sigma), E.ptr(g_rgb),
+                                      E.ptr(g_sigma), E.ptr(grads), E.ptr(gx), E.ptr(scratch), E.stream(dev)),
                 "tnerf_mlp_bwd")
         views = E.flat_grad_views(module, grads)
         return (None, gx) + tuple(v if p.requires_grad else None for v, p in zip(views, ps))

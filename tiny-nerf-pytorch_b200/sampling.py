@@ -3,6 +3,7 @@ import torch
 
 import _engine as E
 import _lazy
+import engine
 
 
 def _as_per_ray(v, n, device):
@@ -29,10 +30,7 @@ def stratified_samples(near, far, n_samples, rays_o, rays_d, randomized=True, t_
     dev = E.need_cuda(rays_o, rays_d)
     n, S = int(rays_o.shape[0]), int(n_samples)
     rd = E.f32c(rays_d)
-    if rays_o.dim() == 2 and rays_o.stride(0) == 0 and rays_o.stride(1) == 1 and rays_o.dtype == torch.float32:
-        ro, o_stride = rays_o, 0          # broadcast origin straight from get_rays
-    else:
-        ro, o_stride = E.f32c(rays_o), 3
+    ro, o_stride = engine.origin_arg(rays_o)
     nr, nr_t = _as_per_ray(near, n, dev)
     fr, fr_t = _as_per_ray(far, n, dev)
     jitter = None

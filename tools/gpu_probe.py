@@ -21,7 +21,8 @@ def selftest(N, K, mode):
     a = torch.randn((K, 128) if m == 3 else (128, K), generator=g)
     b = torch.randn((K, N) if m == 2 else (N, K), generator=g)
     d = torch.full((128, N), float("nan"), device=dev)
-    E.check(E.lib().tnerf_umma_selftest(E.ptr(a.to(dev)), E.ptr(b.to(dev)), N, K, mode, E.ptr(d), E.stream(dev)))
+    a_d, b_d = a.to(dev), b.to(dev)
+    E.check(E.lib().tnerf_umma_selftest(E.ptr(a_d), E.ptr(b_d), N, K, mode, E.ptr(d), E.stream(dev)))
     torch.cuda.synchronize()
     ah, bh = a.half().float(), b.half().float()
     A = ah.t() if m == 3 else ah
@@ -32,7 +33,7 @@ def selftest(N, K, mode):
 
 def main():
     print(torch.cuda.get_device_name(0), torch.version.cuda)
-    for mode in (0, 16, 1, 1 | 32, 1 | 16, 2, 2 | 16, 3, 3 | 16):
+    for mode in (0, 1, 2, 3):
         for (N, K) in ((128, 64), (16, 32), (64, 128)):
             try:
                 err, mag = selftest(N, K, mode)
