@@ -118,3 +118,120 @@ def render_weights(model, ro, o_stride, rd, n, S, near, far, jitter, white, prec
     E.check(E.lib().tnerf_render_fwd(h.h, C.byref(rs), n, near, far, S, E.ptr(jitter), int(white), prec, E.ptr(comp), None, None,
                                      E.ptr(w), None, E.stream(dev)), "tnerf_render_fwd")
     return w
+
+
+class Trainer:
+    """The training-step host path (src/train.py:106-128) on the fused kernels: one
+    tnerf_train_fwd_bwd launch (rays generated in-kernel from pose + pixel ids, MSE inside), an
+    optional NCCL all-reduce of the flat gradient (+loss) for ray-sharded data parallel, one fused Adam
+    launch and one weight re-pack launch.  No host synchronisation anywhere in ``step``.
+
+    Parameters stay ordinary ``nn.Parameter``s: they are re-pointed at views of one flat fp32 buffer so
+    the optimiser is a single kernel; ``state_dict()`` / ``load_state_dict()`` speak torch.optim.Adam's
+    format, so checkpoints interchange with the reference (src/train.py:85-92,142-156)."""
+
+    def __init__(self, model, encoder, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, near=2.0, far=6.0, n_samples=64,
+                 white_bkgd=True, precision: Optional[str] = None, process_group=None):
+        self.model, self.encoder = model, encoder
+        ps = model._params()
+        dev = E.need_cuda(*ps)
+        self.device = dev
+        self.h = E.handle_for(model, dev)
+        self.h.set_encoding(encoder.num_freqs, encoder.include_input)
+        self.P = sum(p.numel() for p in ps)
+        self.flat = torch.empty(self.P, dtype=torch.float32, device=dev)
+        off = 0
+        for p in ps:
+            n = p.numel()
+            self.flat[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off:off + n].view_as(p)
+            off += n
+        self.gbuf = torch.zeros(self.P + 1, dtype=torch.float32, device=dev)   # [gradient | loss]
+        self.loss_view = self.gbuf[self.P:]
+        self.exp_avg = torch.zeros(self.P, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.P, dtype=torch.float32, device=dev)
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.near, self.far, self.S, self.white = float(near), float(far), int(n_samples), bool(white_bkgd)
+        self.prec = _PREC[precision.lower()] if precision else default_bwd_precision()
+        if self.prec == E.PREC_F16_TC and not fused_supported(model, encoder, self.S, dev):
+            self.prec = E.PREC_F32_SIMT
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.steps = 0
+        self.h.bind()
+        if self.prec == E.PREC_F16_TC:
+            self.h.ensure_packed(force=True)
+
+    # ---- one optimisation step ------------------------------------------------------------------
+    def _finish(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.gbuf, group=self.pg)
+        self.steps += 1
+        st = E.stream(self.device)
+        E.check(E.lib().tnerf_adam_step(E.ptr(self.flat), E.ptr(self.gbuf), E.ptr(self.exp_avg), E.ptr(self.exp_avg_sq), self.P,
+                                        self.steps, self.lr, self.betas[0], self.betas[1], self.eps, 1.0, None, st), "tnerf_adam_step")
+        if self.prec == E.PREC_F16_TC:
+            self.h.ensure_packed(force=True)
+        return self.loss_view
+
+    def _launch(self, rs, target, n, jitter, global_rays):
+        st = E.stream(self.device)
+        self.gbuf.zero_()
+        denom = 3.0 * float(global_rays if global_rays else n * self.world)
+        E.check(E.lib().tnerf_train_fwd_bwd(self.h.h, C.byref(rs), E.ptr(target), n, self.near, self.far, self.S, E.ptr(jitter),
+                                            int(self.white), self.prec, denom, None, E.ptr(self.loss_view), E.ptr(self.gbuf), st),
+                "tnerf_train_fwd_bwd")
+        return self._finish()
+
+    def step_pixels(self, c2w, H, W, focal, pixel_index, target, jitter=None, global_rays=None):
+        """rays are generated in-kernel from the pose and the pixel ids (a1+a2 fused in); returns the loss (device, shape (1,))."""
+        n = int(pixel_index.shape[0])
+        if jitter is None:
+            jitter = torch.rand((n, self.S), dtype=torch.float32, device=self.device)
+        rs = ray_source(c2w=c2w, H=H, W=W, focal=focal, pixel_index=pixel_index)
+        return self._launch(rs, target, n, jitter, global_rays)
+
+    def step_rays(self, rays_o, rays_d, target, jitter=None, global_rays=None):
+        n = int(rays_d.shape[0])
+        if jitter is None:
+            jitter = torch.rand((n, self.S), dtype=torch.float32, device=self.device)
+        ro, o_stride = origin_arg(rays_o)
+        rd = E.f32c(rays_d)
+        tg = E.f32c(target)
+        rs = ray_source(ro, o_stride, rd)
+        return self._launch(rs, tg, n, jitter, global_rays)
+
+    # ---- torch.optim.Adam-compatible state ---------------------------------------------------------
+    def state_dict(self):
+        state, off = {}, 0
+        for i, p in enumerate(self.model._params()):
+            n = p.numel()
+            state[i] = {"step": torch.tensor(float(self.steps)), "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
+            off += n
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+                 "params": list(range(len(state)))}
+        return {"state": state if self.steps else {}, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        off = 0
+        for i, p in enumerate(self.model._params()):
+            n = p.numel()
+            st = sd["state"].get(i)
+            if st is not None:
+                self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                self.steps = int(st["step"])
+            off += n
+        if sd.get("param_groups"):
+            g = sd["param_groups"][0]
+            self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
+
+    def refresh(self):
+        """call after parameters were changed from outside (load_state_dict on the model)"""
+        self.h.bind()
+        if self.prec == E.PREC_F16_TC:
+            self.h.ensure_packed(force=True)
