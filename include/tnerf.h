@@ -142,11 +142,14 @@ int tnerf_render_fwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long lo
 
 /* Backward of tnerf_render_fwd w.r.t. the MLP parameters with activations recomputed on chip
  * (implicit backward of src/train.py:126).  Upstream grads as in tnerf_composite_bwd.
- * grads (param_count) is ACCUMULATED into. */
+ * grads (param_count) is ACCUMULATED into.  The tensor-core path carries gradients as fp16 operands:
+ * they are multiplied by a power-of-two loss scale on entry and divided on exit -- grad_scale_dev
+ * (1 device float) if non-NULL, else grad_scale (<= 0 means 1). */
 int tnerf_render_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long long n_rays,
                      float near_, float far_, int n_samples, const float* jitter, int white_bkgd,
                      int precision, const float* g_comp, const float* g_depth, const float* g_acc,
-                     const float* g_weights, float grad_scale, float* grads, void* stream);
+                     const float* g_weights, float grad_scale, const float* grad_scale_dev, float* grads,
+                     void* stream);
 
 /* Whole training step body: forward, MSE against target (n,3), backward   (src/train.py:114-126)
  * loss_denom: the divisor of the summed squared error (3*n_rays for one process, 3*global rays

@@ -117,8 +117,10 @@ def test_fused_render_black_background_and_broadcast_origin(dev, prec):
 
 
 # ------------------------------------------------------------------------------------------ gradients
-@pytest.mark.parametrize("prec", ["f32"])
-@pytest.mark.parametrize("case", [dict(cfg=(63, 128, 4, 2), S=64, n=256), dict(cfg=(39, 128, 3, 1), S=32, n=100)])
+@pytest.mark.parametrize("prec", ["f32", "f16"])
+@pytest.mark.parametrize("case", [dict(cfg=(63, 128, 4, 2), S=64, n=256), dict(cfg=(39, 128, 3, 1), S=32, n=100),
+                                  dict(cfg=(63, 128, 4, 2), S=128, n=37), dict(cfg=(39, 128, 4, 2), S=16, n=1000),
+                                  dict(cfg=(63, 128, 4, 2), S=64, n=2500)])
 def test_fused_train_grads_vs_oracle(dev, prec, case):
     import engine
     from encoding import PositionalEncoding
@@ -133,9 +135,79 @@ def test_fused_train_grads_vs_oracle(dev, prec, case):
     loss = ((comp - target.to(dev)) ** 2).mean()
     loss.backward()
     l_ref, g_ref, _ = O.loss_and_grads(p, ro, rd, target, 2.0, 6.0, S, u, num_freqs=L, depth=case["cfg"][2], skip_at=case["cfg"][3])
-    assert abs(loss.item() - l_ref.item()) < 1e-5
-    for k, v in model.named_parameters():
-        assert rel_l2(v.grad.cpu(), g_ref[k]) < 1e-3, k
+    assert abs(loss.item() - l_ref.item()) < (1e-5 if prec == "f32" else 1e-3)
+    tol = 1e-3 if prec == "f32" else 1e-2          # north-star bar: gradients within 1e-2 relative
+    errs = {k: rel_l2(v.grad.cpu(), g_ref[k]) for k, v in model.named_parameters()}
+    assert max(errs.values()) < tol, errs
+
+
+@pytest.mark.parametrize("prec", ["f32", "f16"])
+@pytest.mark.parametrize("white", [True, False])
+def test_train_fwd_bwd_entry_point_vs_oracle(dev, prec, white):
+    """tnerf_train_fwd_bwd (MSE inside the kernel, rays generated in-kernel from pose + pixel ids):
+    loss, rendered colour and the flat gradient against the oracle's autograd."""
+    import ctypes as C
+    import _engine as E
+    import engine
+    from encoding import PositionalEncoding
+    enc = PositionalEncoding(10, True).to(dev)
+    model, p = make_model((63, 128, 4, 2), 51, dev, 2.0)
+    H, W, focal, n, S = 40, 50, 60.0, 700, 64
+    pose = O.look_at_pose(0.9, 0.45)
+    g = torch.Generator().manual_seed(52)
+    pix = torch.randint(0, H * W, (n,), generator=g)
+    u, target = torch.rand(n, S, generator=g), torch.rand(n, 3, generator=g)
+    h = E.handle_for(model, dev)
+    h.set_encoding(10, True)
+    h.ensure_packed(force=True)
+    pose_d, pix_d, u_d, t_d = pose.to(dev), pix.to(dev), u.to(dev), target.to(dev)
+    grads = torch.zeros(h.param_count, device=dev)
+    loss = torch.zeros(1, device=dev)
+    comp = torch.empty(n, 3, device=dev)
+    rs = engine.ray_source(c2w=pose_d, H=H, W=W, focal=focal, pixel_index=pix_d)
+    E.check(E.lib().tnerf_train_fwd_bwd(h.h, C.byref(rs), E.ptr(t_d), n, 2.0, 6.0, S, E.ptr(u_d), int(white), engine._PREC[prec],
+                                        3.0 * n, E.ptr(comp), E.ptr(loss), E.ptr(grads), E.stream(dev)))
+    oro, ord_ = O.get_rays(H, W, focal, pose)
+    l_ref, g_ref, (oc, _, _) = O.loss_and_grads(p, oro[pix], ord_[pix], target, 2.0, 6.0, S, u, white_bkgd=white)
+    keep = O.last_sample_sigma_pre(p, oro[pix], ord_[pix], 2.0, 6.0, S, u).abs() > (1e-5 if prec == "f32" else 4e-3)
+    assert keep.float().mean() > 0.97
+    assert (comp.cpu() - oc)[keep].abs().max() < (2e-5 if prec == "f32" else 2e-3)
+    assert abs(loss.item() - l_ref.item()) < (1e-5 if prec == "f32" else 2e-3 * max(1.0, l_ref.item()))
+    flat_ref = torch.cat([g_ref[k].reshape(-1) for k, _ in O.mlp_param_shapes(63, 128, 4, 2)])
+    off = 0
+    for k, shp in O.mlp_param_shapes(63, 128, 4, 2):
+        cnt = g_ref[k].numel()
+        err = rel_l2(grads[off:off + cnt].cpu(), flat_ref[off:off + cnt])
+        assert err < (1e-3 if prec == "f32" else 1e-2), (k, err)
+        off += cnt
+
+
+def test_trainer_steps_match_oracle_adam(dev):
+    """three fused optimisation steps (train kernel + Adam kernel + re-pack) vs oracle loss_and_grads + adam_step"""
+    import engine
+    from encoding import PositionalEncoding
+    enc = PositionalEncoding(10, True).to(dev)
+    model, p = make_model((63, 128, 4, 2), 61, dev, 1.5)
+    tr = engine.Trainer(model, enc, n_samples=32, precision="f32")
+    m = {k: torch.zeros_like(v) for k, v in p.items()}
+    v = {k: torch.zeros_like(x) for k, x in p.items()}
+    H, W, focal, n, S = 30, 30, 45.0, 384, 32
+    pose = O.look_at_pose(2.2, 0.35)
+    oro, ord_ = O.get_rays(H, W, focal, pose)
+    g = torch.Generator().manual_seed(62)
+    for step in range(3):
+        pix = torch.randint(0, H * W, (n,), generator=g)
+        u, target = torch.rand(n, S, generator=g), torch.rand(n, 3, generator=g)
+        loss = tr.step_pixels(pose.to(dev), H, W, focal, pix.to(dev), target.to(dev), u.to(dev))
+        l_ref, g_ref, _ = O.loss_and_grads(p, oro[pix], ord_[pix], target, 2.0, 6.0, S, u)
+        O.adam_step(p, g_ref, m, v, step + 1)
+        assert abs(loss.item() - l_ref.item()) < 1e-5
+        for k, prm in model.named_parameters():
+            assert (prm.detach().cpu() - p[k]).abs().max() < 5e-6, (step, k)
+    sd = tr.state_dict()
+    assert sorted(sd["state"].keys()) == list(range(12)) and float(sd["state"][0]["step"]) == 3.0
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    opt.load_state_dict(sd)                                    # interchangeable with torch.optim.Adam (checkpoints)
 
 
 # ------------------------------------------------------------------------------------------ deferred fusion

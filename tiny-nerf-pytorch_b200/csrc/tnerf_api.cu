@@ -271,14 +271,14 @@ int tnerf_render_fwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long lo
 
 int tnerf_render_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long long n_rays, float near_, float far_, int n_samples,
                      const float* jitter, int white_bkgd, int precision, const float* g_comp, const float* g_depth, const float* g_acc,
-                     const float* g_weights, float grad_scale, float* grads, void* stream) {
+                     const float* g_weights, float grad_scale, const float* grad_scale_dev, float* grads, void* stream) {
     if (n_rays == 0) return 0;
     if (!h || h->params.empty() || !grads || n_rays < 0 || n_samples < 1) return bad("tnerf_render_bwd: invalid argument");
     if (int e = check_source(rays_host)) return e;
     const RaySource rs = to_device_source(rays_host);
     if (precision == TNERF_PREC_F16_TC)
         return fused_train(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, nullptr, 1.f, g_comp, g_depth, g_acc, g_weights,
-                           grad_scale, nullptr, nullptr, grads, (cudaStream_t)stream);
+                           grad_scale, grad_scale_dev, nullptr, nullptr, grads, (cudaStream_t)stream);
     F32Job job{};
     job.mode = 1; job.gC = g_comp; job.gD = g_depth; job.gA = g_acc; job.gW = g_weights; job.grads = grads;
     return run_f32(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, job, (cudaStream_t)stream);
@@ -294,7 +294,7 @@ int tnerf_train_fwd_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, cons
     const RaySource rs = to_device_source(rays_host);
     if (precision == TNERF_PREC_F16_TC)
         return fused_train(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, target, loss_denom, nullptr, nullptr, nullptr,
-                           nullptr, 0.f, comp_rgb, loss_sum, grads, (cudaStream_t)stream);
+                           nullptr, 0.f, nullptr, comp_rgb, loss_sum, grads, (cudaStream_t)stream);
     F32Job job{};
     job.mode = 2; job.target = target; job.loss_denom = loss_denom; job.comp = comp_rgb; job.loss_sum = loss_sum; job.grads = grads;
     return run_f32(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, job, (cudaStream_t)stream);

@@ -1,0 +1,101 @@
+// Shared pieces of the tensor-core fused kernels (forward: tnerf_fused.cu, train: tnerf_train.cu).
+#pragma once
+#include "tnerf_internal.cuh"
+#include "tnerf_ptx.cuh"
+
+namespace tnerf {
+using namespace ptx;
+
+// ================================================================================================
+// Operand images.  Every fp16 operand matrix X(r, k) (r = M or N index, k = reduction index) is stored
+// in the SWIZZLE_NONE canonical form  idx(r,k) = ((k/8)*R + r)*8 + k%8  (R rows): 8x8 core matrices
+// of 128 contiguous bytes, K-major view: LBO = R*16 B, SBO = 128 B.  The same bytes read as the
+// transposed operand (r' = k, k' = r) are the MN-major canonical form with LBO = 128 B, SBO = R*16 B,
+// which is what the backward kernel uses for dgrad/wgrad without a second copy.
+__host__ __device__ inline long long img_idx(int r, int k, int R) { return ((long long)(k >> 3) * R + r) * 8 + (k & 7); }
+
+enum { SEG_ACT = 0, SEG_X = 1, SEG_ONES = 2 };
+
+struct LayerPlan {
+    uint32_t b_off;      // byte offset of this layer's B image inside the packed image
+    uint32_t idesc;
+    uint16_t N;
+    uint8_t nseg;
+    uint8_t seg_kind[3];
+    uint8_t seg_steps[3];   // K=16 steps per segment
+};
+
+struct FusedPlan {
+    int depth, D, Kx, L, include_input, H;
+    int bias_in_x;          // x layers carry their bias in the pad column D of the encoding
+    uint32_t image_bytes;
+    LayerPlan layer[kMaxDepth + 1];   // hidden layers, then the head
+};
+
+struct FwdParams {
+    RaySource rs;
+    long long n_rays, n_units;
+    int S, G, R, white;
+    float near_, far_;
+    const float* jitter;
+    float *comp, *depth, *acc, *weights, *rays_d_out;
+    const __half* image;
+    FusedPlan plan;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Fourier features of one point into 64 fp16 slots (packed pairs), column order of
+// src/encoding.py:27-33 ([x, sin f0, cos f0, sin f1, ...], 3 axes each).  sin/cos of the base
+// frequency use a 2-term Cody-Waite reduction (|x| < ~50) + minimax polynomials; higher octaves use
+// the double-angle recurrence s' = 2sc, c' = (c-s)(c+s): max abs error 5e-5 at 2^9, below fp16 rounding.
+__device__ __forceinline__ void sincos_small(float x, float& s, float& c) {
+    const float n = rintf(x * 0.6366197723675814f);
+    float r = fmaf(-n, 1.5707963705062866f, x);
+    r = fmaf(-n, -4.371138828673793e-08f, r);
+    const float r2 = r * r;
+    const float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f) * r2, r, r);
+    const float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f) * r2, r2,
+                          fmaf(-0.5f, r2, 1.f));
+    const int q = (int)n & 3;
+    const float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cc : cc;
+}
+
+template <int KX, bool INC>
+__device__ __forceinline__ void encode_point(const float p[3], int L, uint32_t (&pk)[KX / 2]) {
+    float f[KX];
+#pragma unroll
+    for (int i = 0; i < KX; ++i) f[i] = 0.f;
+    constexpr int base = INC ? 3 : 0;
+    if (INC) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) f[a] = p[a];
+    }
+    float s[3], c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) sincos_small(p[a], s[a], c[a]);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        const bool on = k < L;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (base + 6 * k + 3 + a < KX - 1) {
+                f[base + 6 * k + a] = on ? s[a] : 0.f;
+                f[base + 6 * k + 3 + a] = on ? c[a] : 0.f;
+            }
+            const float s2 = s[a] + s[a];
+            const float cn = (c[a] - s[a]) * (c[a] + s[a]);
+            s[a] = s2 * c[a];
+            c[a] = cn;
+        }
+    }
+    f[KX - 1] = 1.f;   // constant-1 pad column: carries the bias of the x-consuming layers
+#pragma unroll
+    for (int i = 0; i < KX / 2; ++i) pk[i] = pack_h2(f[2 * i], f[2 * i + 1]);
+}
+
+
+bool build_plan(const tnerf_handle* h, FusedPlan& pl);
+
+}  // namespace tnerf

@@ -21,7 +21,7 @@ def default_precision() -> int:
 
 
 def default_bwd_precision() -> int:
-    return _PREC[os.environ.get("TNERF_BWD_PRECISION", "f32").lower()]
+    return _PREC[os.environ.get("TNERF_BWD_PRECISION", os.environ.get("TNERF_PRECISION", "f16")).lower()]
 
 
 def ray_source(rays_o=None, o_stride=3, rays_d=None, c2w=None, H=0, W=0, focal=0.0, pixel_index=None, first_ray=0):
@@ -71,8 +71,13 @@ class _FusedRender(torch.autograd.Function):
         grads = torch.zeros(h.param_count, dtype=torch.float32, device=dev)
         rs = ray_source(ro, o_stride, rd)
         gC, gD, gA = (E.f32c(g) if g is not None else None for g in (gC, gD, gA))
+        scale_dev = None
+        if prec == E.PREC_F16_TC:
+            # power-of-two loss scale chosen on the device (no host sync): largest upstream gradient -> ~64
+            amax = torch.stack([g.abs().max() for g in (gC, gD, gA) if g is not None]).max().clamp_min(1e-30)
+            scale_dev = torch.exp2(torch.floor(torch.log2(64.0 / amax))).clamp(2.0 ** -24, 2.0 ** 40).reshape(1).float()
         E.check(E.lib().tnerf_render_bwd(h.h, C.byref(rs), n, near, far, S, E.ptr(jitter), int(white), prec, E.ptr(gC), E.ptr(gD),
-                                         E.ptr(gA), None, 0.0, E.ptr(grads), E.stream(dev)), "tnerf_render_bwd")
+                                         E.ptr(gA), None, 0.0, E.ptr(scale_dev), E.ptr(grads), E.stream(dev)), "tnerf_render_bwd")
         views = E.flat_grad_views(module, grads)
         return (None,) * 12 + tuple(v if p.requires_grad else None for v, p in zip(views, ps))
 
@@ -88,17 +93,31 @@ def fused_supported(module, encoder, S: int, device) -> bool:
     return h.fused_ok and module.hidden == 128 and S // g <= 8
 
 
+def train_supported(module, encoder, S: int, device) -> bool:
+    """the tensor-core fused backward covers the reference MLP (depth 4, skip after layer 1, hidden 128) and
+    ray tiles of whole rays (n_samples divides 128); everything else takes the fp32 path"""
+    return (fused_supported(module, encoder, S, device) and module.depth == 4 and module.skip_at == 2
+            and 1 <= int(S) <= 128 and 128 % int(S) == 0)
+
+
+def pick_precisions(model, encoder, S, device, precision=None):
+    prec = _PREC[precision.lower()] if precision else default_precision()
+    bprec = _PREC[precision.lower()] if precision else default_bwd_precision()
+    if prec == E.PREC_F16_TC and not fused_supported(model, encoder, S, device):
+        prec = E.PREC_F32_SIMT
+    if bprec == E.PREC_F16_TC and not train_supported(model, encoder, S, device):
+        bprec = E.PREC_F32_SIMT
+    return prec, bprec
+
+
 def render_rays(model, encoder, rays_o, rays_d, near: float, far: float, n_samples: int, t_rand: Optional[torch.Tensor] = None,
                 white_bkgd: bool = True, precision: Optional[str] = None):
     """Fused a3->a6: returns (comp_rgb (N,3), depth (N,1), acc (N,1)).  Differentiable w.r.t. the MLP
     parameters.  ``t_rand`` (N,S) enables stratified jitter; None = deterministic depths."""
     dev = E.need_cuda(rays_o, rays_d)
-    prec = _PREC[precision.lower()] if precision else default_precision()
-    bprec = _PREC[precision.lower()] if precision else default_bwd_precision()
     h = E.handle_for(model, dev)
     h.set_encoding(encoder.num_freqs, encoder.include_input)
-    if prec == E.PREC_F16_TC and not fused_supported(model, encoder, n_samples, dev):
-        prec = bprec = E.PREC_F32_SIMT
+    prec, bprec = pick_precisions(model, encoder, n_samples, dev, precision)
     ro, o_stride = origin_arg(rays_o)
     rd = E.f32c(rays_d)
     jit = E.f32c(t_rand) if t_rand is not None else None
@@ -152,9 +171,7 @@ class Trainer:
         self.exp_avg_sq = torch.zeros(self.P, dtype=torch.float32, device=dev)
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.near, self.far, self.S, self.white = float(near), float(far), int(n_samples), bool(white_bkgd)
-        self.prec = _PREC[precision.lower()] if precision else default_bwd_precision()
-        if self.prec == E.PREC_F16_TC and not fused_supported(model, encoder, self.S, dev):
-            self.prec = E.PREC_F32_SIMT
+        self.prec = pick_precisions(model, encoder, self.S, dev, precision)[1]
         self.pg = process_group
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):

@@ -73,10 +73,8 @@ def _try_fused(rgb, sigma, z_vals, rays_d, white_bkgd):
     if not _lazy.same_tensor(z_vals, s.z_vals) or rays_d.data_ptr() != s.rd.data_ptr() or tuple(rays_d.shape) != (s.n, 3):
         return None
     model, enc = node.model, node.encoder
-    prec, bprec = engine.default_precision(), engine.default_bwd_precision()
     E.handle_for(model, s.rd.device).set_encoding(enc.num_freqs, enc.include_input)
-    if prec == E.PREC_F16_TC and not engine.fused_supported(model, enc, s.S, s.rd.device):
-        prec = bprec = E.PREC_F32_SIMT
+    prec, bprec = engine.pick_precisions(model, enc, s.S, s.rd.device)
     comp, depth, acc = engine._FusedRender.apply(model, s.ro, s.o_stride, s.rd, s.n, s.S, s.near, s.far, s.jitter,
                                                  bool(white_bkgd), prec, bprec, *model._params())
     wnode = _LazyWeights((model, s.ro, s.o_stride, s.rd, s.n, s.S, s.near, s.far, s.jitter, bool(white_bkgd), prec))
