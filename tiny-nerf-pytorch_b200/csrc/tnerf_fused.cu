@@ -174,20 +174,35 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fused_fwd_kernel(const __grid_
                 if (!has0 && !has1) break;
                 for (int g = 0; g < p.G; ++g) {
                     for (int step = 0; step <= p.plan.depth; ++step) {
+                        // everything that does not change inside the K loop lives in registers: the issue loop is
+                        // {UTCHMMA, two adds}, so the issuer stays ahead of the 64-cycle MMAs
                         const LayerPlan& lp = p.plan.layer[step];
+                        const uint32_t idesc = lp.idesc, N = lp.N, nseg = lp.nseg;
+                        const uint32_t b_stride = (N * 32u) >> 4;
+                        const uint32_t b_lo0 = (((wbase + lp.b_off) >> 4) & 0x3FFFu) | (((N * 16u) >> 4) << 16);
+                        const uint32_t b_hi = (128u >> 4) | (1u << 14);          // SBO | descriptor version
+                        const uint32_t d_off = (step == p.plan.depth) ? TM_HEAD : TM_ACC;
+                        uint32_t seg_a[3], seg_n[3];
+#pragma unroll
+                        for (int sgi = 0; sgi < 3; ++sgi) {
+                            const uint32_t kind = lp.seg_kind[sgi];
+                            seg_a[sgi] = kind == SEG_ACT ? TM_ACT : kind == SEG_X ? TM_X : TM_ONES;
+                            seg_n[sgi] = sgi < (int)nseg ? lp.seg_steps[sgi] : 0u;
+                        }
                         for (int w = 0; w < 2; ++w) {
                             if (!(w ? has1 : has0)) continue;
                             mbar_wait(smem_u32(&sm.bar_a[w]), phase[w]);
                             phase[w] ^= 1;
                             tc_fence_after();
                             const uint32_t tw = tmem + w * TM_WG_STRIDE;
-                            const uint32_t d_t = tw + (step == p.plan.depth ? TM_HEAD : TM_ACC);
-                            uint32_t kstep = 0;
-                            for (int sgi = 0; sgi < lp.nseg; ++sgi) {
-                                const uint32_t a0 = tw + (lp.seg_kind[sgi] == SEG_ACT ? TM_ACT : lp.seg_kind[sgi] == SEG_X ? TM_X : TM_ONES);
-                                for (int j = 0; j < lp.seg_steps[sgi]; ++j, ++kstep) {
-                                    const uint64_t bd = make_desc(wbase + lp.b_off + kstep * (uint32_t)lp.N * 32u, (uint32_t)lp.N * 16u, 128u);
-                                    mma_ts(d_t, a0 + j * 8, bd, lp.idesc, kstep > 0);
+                            const uint32_t d_t = tw + d_off;
+                            uint32_t lo = b_lo0, acc = 0;
+#pragma unroll
+                            for (int sgi = 0; sgi < 3; ++sgi) {
+                                uint32_t a = tw + seg_a[sgi];
+                                for (uint32_t j = 0; j < seg_n[sgi]; ++j) {
+                                    mma_ts(d_t, a, ((uint64_t)b_hi << 32) | lo, idesc, acc);
+                                    a += 8; lo += b_stride; acc = 1;
                                 }
                             }
                             tc_commit(smem_u32(&sm.bar_acc[w]));
@@ -256,14 +271,18 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fused_fwd_kernel(const __grid_
                     phase ^= 1;
                     tc_fence_after();
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t v[32];
-                        tmem_ld32(tw + TM_ACC + c * 32, v);
+                    for (int c = 0; c < 4; c += 2) {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32(tw + TM_ACC + c * 32, v0);
+                        tmem_ld32(tw + TM_ACC + c * 32 + 32, v1);
                         tc_wait_ld();
-                        uint32_t h[16];
+                        uint32_t h0[16], h1[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) h[i] = pack_relu_h2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-                        tmem_st16(tw + TM_ACT + c * 16, h);
+                        for (int i = 0; i < 16; ++i) h0[i] = pack_relu_h2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+                        tmem_st16(tw + TM_ACT + c * 16, h0);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) h1[i] = pack_relu_h2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+                        tmem_st16(tw + TM_ACT + c * 16 + 16, h1);
                     }
                     tc_wait_st();
                     tc_fence_before();

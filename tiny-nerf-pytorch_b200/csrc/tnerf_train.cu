@@ -283,15 +283,22 @@ __global__ void __launch_bounds__(TR_THREADS, 1) fused_train_kernel(const __grid
                         ++g;
                     }
                     const uint32_t d_t = tmem + jb.d_col;
-                    uint32_t k = 0;
-                    for (int s = 0; s < jb.nseg; ++s) {
-                        const Seg& sg = jb.seg[s];
-                        const uint32_t a0 = sbase + sg.a_off;
-                        const uint32_t b0 = sbase + (sg.b_w ? SM_WBUF + cur_buf * WBUF_BYTES : 0u) + sg.b_off;
-                        for (uint32_t i = 0; i < sg.steps; ++i, ++k) {
-                            const uint64_t ad = make_desc(a0 + i * ((uint32_t)sg.a_adv << 4), (uint32_t)sg.a_lbo << 4, (uint32_t)sg.a_sbo << 4);
-                            const uint64_t bd = make_desc(b0 + i * ((uint32_t)sg.b_adv << 4), (uint32_t)sg.b_lbo << 4, (uint32_t)sg.b_sbo << 4);
-                            mma_ss(d_t, ad, bd, jb.idesc, (k > 0) || (jb.resident && t > 0));
+                    const uint32_t idesc = jb.idesc;
+                    uint32_t acc = (jb.resident && t > 0) ? 1u : 0u;
+                    const uint32_t wb = sbase + SM_WBUF + cur_buf * WBUF_BYTES;
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        if (s < jb.nseg) {
+                            const Seg& sg = jb.seg[s];
+                            // descriptor words: lo = start>>4 | LBO<<16 ; hi = SBO | version<<14 ; only lo advances
+                            uint32_t a_lo = (((sbase + sg.a_off) >> 4) & 0x3FFFu) | ((uint32_t)sg.a_lbo << 16);
+                            uint32_t b_lo = ((((sg.b_w ? wb : sbase) + sg.b_off) >> 4) & 0x3FFFu) | ((uint32_t)sg.b_lbo << 16);
+                            const uint32_t a_hi = (uint32_t)sg.a_sbo | (1u << 14), b_hi = (uint32_t)sg.b_sbo | (1u << 14);
+                            const uint32_t a_adv = sg.a_adv, b_adv = sg.b_adv, steps = sg.steps;
+                            for (uint32_t i = 0; i < steps; ++i) {
+                                mma_ss(d_t, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, acc);
+                                a_lo += a_adv; b_lo += b_adv; acc = 1;
+                            }
                         }
                     }
                     if (jb.w_release) tc_commit(smem_u32(&ms.bar_empty[cur_buf]));
