@@ -86,6 +86,9 @@ long long tnerf_param_count(const tnerf_handle* h);
 /* The fused entry points generate the Fourier features themselves.  By default the encoding is
  * inferred from in_dim (6L+3 -> include_input); call this to state it explicitly. */
 int  tnerf_set_encoding(tnerf_handle* h, int num_freqs, int include_input);
+/* Developer hook: a device buffer of 1024 int64 that receives clock64() phase stamps of CTA 0 of the fused
+ * forward kernel (tools/trace_fwd.py); NULL disables it. */
+int  tnerf_set_debug_buffer(tnerf_handle* h, void* buf);
 /* 1 when the tcgen05 fused kernels support this handle's (in_dim, hidden, depth, skip_at) */
 int  tnerf_fused_supported(const tnerf_handle* h);
 /* Re-derive the packed fp16 operand image used by the tensor-core kernels from the bound fp32
@@ -176,6 +179,8 @@ int tnerf_check_finite(const float* grads, long long n, int* found_inf, void* st
 
 /* test hook: D(128xN) = A(128xK) * B(NxK)^T through the same tcgen05 descriptors the fused
  * kernels use.  mode 0: A from shared memory, 1: A from tensor memory, 2: B MN-major. */
+/* developer probe: cycles for `reps` back-to-back 128 x n x 16 MMAs (out2[0] = to completion, out2[1] = issue only) */
+int tnerf_umma_rate(int n, int reps, int variant, long long* out2, void* stream);
 int tnerf_umma_selftest(const float* a, const float* b, int n, int k, int mode, float* d, void* stream);
 
 #ifdef __cplusplus

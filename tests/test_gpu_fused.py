@@ -221,7 +221,7 @@ def test_trainer_steps_match_oracle_adam(dev):
         for k, prm in model.named_parameters():
             solid = g_ref[k].abs() > 1e-3 * g_ref[k].abs().max()
             diff = (prm.detach().cpu() - p[k]).abs()
-            assert diff[solid].max() < 5e-6 and diff.max() <= 2.1 * 5e-4, (step, k, diff[solid].max().item(), diff.max().item())
+            assert diff[solid].max() < 1e-5 and diff.max() <= 2.1 * 5e-4, (step, k, diff[solid].max().item(), diff.max().item())
     sd = tr.state_dict()
     assert sorted(sd["state"].keys()) == list(range(12)) and float(sd["state"][0]["step"]) == 3.0
     opt = torch.optim.Adam(model.parameters(), lr=5e-4)

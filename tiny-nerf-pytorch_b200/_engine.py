@@ -45,6 +45,7 @@ _SIGS = {
     "tnerf_bind_params": (_i, [_p, C.POINTER(_p), _i]),
     "tnerf_param_count": (_ll, [_p]),
     "tnerf_set_encoding": (_i, [_p, _i, _i]),
+    "tnerf_set_debug_buffer": (_i, [_p, _p]),
     "tnerf_fused_supported": (_i, [_p]),
     "tnerf_pack_weights": (_i, [_p, _p]),
     "tnerf_mlp_fwd": (_i, [_p, _p, _ll, _p, _p, _p, _p]),
@@ -58,6 +59,7 @@ _SIGS = {
     "tnerf_mse_psnr": (_i, [_p, _p, _ll, _p, _p]),
     "tnerf_adam_step": (_i, [_p, _p, _p, _p, _ll, _i, _f, _f, _f, _f, _f, _p, _p]),
     "tnerf_check_finite": (_i, [_p, _ll, _p, _p]),
+    "tnerf_umma_rate": (_i, [_i, _i, _i, _p, _p]),
     "tnerf_umma_selftest": (_i, [_p, _p, _i, _i, _i, _p, _p]),
 }
 

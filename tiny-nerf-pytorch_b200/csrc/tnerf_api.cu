@@ -204,6 +204,11 @@ int tnerf_set_encoding(tnerf_handle* h, int num_freqs, int include_input) {
     h->fused_ok = fused_shape_supported(h);
     return 0;
 }
+int tnerf_set_debug_buffer(tnerf_handle* h, void* buf) {
+    if (!h) return bad("NULL handle");
+    h->debug = buf;
+    return 0;
+}
 int tnerf_bind_params(tnerf_handle* h, const float* const* params_host, int n_params) {
     if (!h || !params_host || n_params != h->n_params) return bad("tnerf_bind_params: expected 2*depth+4 pointers");
     h->params.assign(params_host, params_host + n_params);
@@ -312,6 +317,10 @@ int tnerf_adam_step(float* params, const float* grads, float* exp_avg, float* ex
 int tnerf_check_finite(const float* grads, long long n, int* found_inf, void* stream) {
     if (!grads || !found_inf || n < 0) return bad("tnerf_check_finite: invalid argument");
     return launch_check_finite(grads, n, found_inf, (cudaStream_t)stream);
+}
+int tnerf_umma_rate(int n, int reps, int variant, long long* out2, void* stream) {
+    if (!out2) return bad("tnerf_umma_rate: invalid argument");
+    return umma_rate(n, reps, variant, out2, (cudaStream_t)stream);
 }
 int tnerf_umma_selftest(const float* a, const float* b, int n, int k, int mode, float* d, void* stream) {
     if (!a || !b || !d) return bad("tnerf_umma_selftest: invalid argument");

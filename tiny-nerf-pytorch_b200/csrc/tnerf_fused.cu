@@ -72,7 +72,7 @@ __global__ void pack_weights_kernel(PackArgs a, __half* __restrict__ img) {
 // ------------------------------------------------------------------------------------------------
 // Fused forward kernel.  288 threads: warps 0-3 = warpgroup A, warps 4-7 = warpgroup B (each owns one
 // 128-row tile at a time: thread <-> sample row <-> TMEM lane), warp 8 = MMA issuer + weight loader.
-constexpr int FWD_THREADS = 288;
+constexpr int FWD_THREADS = 320;   // 2 x 4 row warps + one MMA-issuer warp per warpgroup
 constexpr int TM_ACC = 0, TM_ACT = 128, TM_X = 192, TM_HEAD = 224, TM_ONES = 240, TM_WG_STRIDE = 256;
 constexpr int MAX_G = 8;
 
@@ -151,62 +151,58 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fused_fwd_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_slot;
+    long long* dbg = (p.debug && blockIdx.x == 0 && warp != 9) ? p.debug : nullptr;
+    int dbg_n = 0;
+#define STAMP(base) do { if (dbg && dbg_n < 500) dbg[(base) + dbg_n++] = clock64(); } while (0)
 
     // units are dealt round-robin: (cta, warpgroup) pair j takes units j, j + 2*grid, ...
     const long long stride = 2LL * gridDim.x;
 
-    if (warp == 8) {
-        // ------------------------------ MMA issuer ------------------------------
+    if (warp >= 8) {
+        // ------------------------------ MMA issuers: warp 8 serves warpgroup 0, warp 9 warpgroup 1 ------------------------------
+        const int w = warp - 8;
         if (lane == 0) {
-            mbar_expect_tx(bar_w, p.plan.image_bytes);
-            uint32_t off = 0;
-            while (off < p.plan.image_bytes) {
-                const uint32_t n = min(32768u, p.plan.image_bytes - off);
-                bulk_g2s(smem_u32(smem) + off, reinterpret_cast<const uint8_t*>(p.image) + off, n, bar_w);
-                off += n;
+            if (w == 0) {
+                mbar_expect_tx(bar_w, p.plan.image_bytes);
+                uint32_t off = 0;
+                while (off < p.plan.image_bytes) {
+                    const uint32_t n = min(32768u, p.plan.image_bytes - off);
+                    bulk_g2s(smem_u32(smem) + off, reinterpret_cast<const uint8_t*>(p.image) + off, n, bar_w);
+                    off += n;
+                }
             }
             mbar_wait(bar_w, 0);
-            uint32_t phase[2] = {0, 0};
+            uint32_t phase = 0;
             const uint32_t wbase = smem_u32(smem);
-            long long u0 = 2LL * blockIdx.x;
-            for (;; u0 += stride) {
-                const bool has0 = u0 < p.n_units, has1 = u0 + 1 < p.n_units;
-                if (!has0 && !has1) break;
+            const uint32_t tw = tmem + w * TM_WG_STRIDE;
+            const uint32_t bar_a = smem_u32(&sm.bar_a[w]), bar_acc = smem_u32(&sm.bar_acc[w]);
+            for (long long u = 2LL * blockIdx.x + w; u < p.n_units; u += stride) {
                 for (int g = 0; g < p.G; ++g) {
                     for (int step = 0; step <= p.plan.depth; ++step) {
-                        // everything that does not change inside the K loop lives in registers: the issue loop is
-                        // {UTCHMMA, two adds}, so the issuer stays ahead of the 64-cycle MMAs
                         const LayerPlan& lp = p.plan.layer[step];
-                        const uint32_t idesc = lp.idesc, N = lp.N, nseg = lp.nseg;
-                        const uint32_t b_stride = (N * 32u) >> 4;
-                        const uint32_t b_lo0 = (((wbase + lp.b_off) >> 4) & 0x3FFFu) | (((N * 16u) >> 4) << 16);
+                        const uint32_t idesc = lp.idesc, N = lp.N;
+                        const uint32_t b_adv = (N * 32u) >> 4;
+                        uint32_t b_lo = (((wbase + lp.b_off) >> 4) & 0x3FFFu) | (((N * 16u) >> 4) << 16);
                         const uint32_t b_hi = (128u >> 4) | (1u << 14);          // SBO | descriptor version
-                        const uint32_t d_off = (step == p.plan.depth) ? TM_HEAD : TM_ACC;
-                        uint32_t seg_a[3], seg_n[3];
+                        const uint32_t d_t = tw + ((step == p.plan.depth) ? TM_HEAD : TM_ACC);
+                        const int nseg = lp.nseg;
+                        uint32_t seg_a[3];
+                        int seg_n[3];
 #pragma unroll
                         for (int sgi = 0; sgi < 3; ++sgi) {
                             const uint32_t kind = lp.seg_kind[sgi];
-                            seg_a[sgi] = kind == SEG_ACT ? TM_ACT : kind == SEG_X ? TM_X : TM_ONES;
-                            seg_n[sgi] = sgi < (int)nseg ? lp.seg_steps[sgi] : 0u;
+                            seg_a[sgi] = tw + (kind == SEG_ACT ? TM_ACT : kind == SEG_X ? TM_X : TM_ONES);
+                            seg_n[sgi] = sgi < nseg ? lp.seg_steps[sgi] : 0;
                         }
-                        for (int w = 0; w < 2; ++w) {
-                            if (!(w ? has1 : has0)) continue;
-                            mbar_wait(smem_u32(&sm.bar_a[w]), phase[w]);
-                            phase[w] ^= 1;
-                            tc_fence_after();
-                            const uint32_t tw = tmem + w * TM_WG_STRIDE;
-                            const uint32_t d_t = tw + d_off;
-                            uint32_t lo = b_lo0, acc = 0;
+                        mbar_wait(bar_a, phase);
+                        phase ^= 1;
+                        tc_fence_after();
+                        STAMP(512);
+                        uint32_t acc = 0;
 #pragma unroll
-                            for (int sgi = 0; sgi < 3; ++sgi) {
-                                uint32_t a = tw + seg_a[sgi];
-                                for (uint32_t j = 0; j < seg_n[sgi]; ++j) {
-                                    mma_ts(d_t, a, ((uint64_t)b_hi << 32) | lo, idesc, acc);
-                                    a += 8; lo += b_stride; acc = 1;
-                                }
-                            }
-                            tc_commit(smem_u32(&sm.bar_acc[w]));
-                        }
+                        for (int sgi = 0; sgi < 3; ++sgi) issue_ts_n(seg_n[sgi], d_t, seg_a[sgi], b_lo, b_hi, b_adv, idesc, acc);
+                        tc_commit(bar_acc);
+                        STAMP(512);
                     }
                 }
             }
@@ -228,9 +224,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fused_fwd_kernel(const __grid_
         }
         uint32_t phase = 0;
         const bool jit = p.jitter != nullptr;
+        if (!(wg == 0 && row == 0)) dbg = nullptr;
         for (long long u = 2LL * blockIdx.x + wg; u < p.n_units; u += stride) {
             const long long ray0 = u * p.R;
             for (int g = 0; g < p.G; ++g) {
+                STAMP(0);
                 const int urow = g * 128 + row;            // row inside the unit
                 const long long ray = ray0 + urow / p.S;
                 const int si = urow % p.S;
@@ -266,10 +264,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fused_fwd_kernel(const __grid_
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(bar_a);
+                STAMP(0);
                 for (int l = 0; l < p.plan.depth; ++l) {
                     mbar_wait(bar_acc, phase);
                     phase ^= 1;
                     tc_fence_after();
+                    STAMP(0);
 #pragma unroll
                     for (int c = 0; c < 4; c += 2) {
                         uint32_t v0[32], v1[32];
@@ -287,10 +287,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fused_fwd_kernel(const __grid_
                     tc_wait_st();
                     tc_fence_before();
                     mbar_arrive(bar_a);
+                    STAMP(0);
                 }
                 mbar_wait(bar_acc, phase);
                 phase ^= 1;
                 tc_fence_after();
+                STAMP(0);
                 {
                     uint32_t v[4];
                     tmem_ld4(tw + TM_HEAD, v);
@@ -303,9 +305,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fused_fwd_kernel(const __grid_
                     st[urow] = o4;
                 }
             }
+            STAMP(0);
             bar_sync(1 + wg, 128);
             composite_unit(p, st, sz, ray0, q, lane);
             bar_sync(1 + wg, 128);
+            STAMP(0);
         }
     }
     tc_fence_before();
@@ -401,6 +405,58 @@ int umma_selftest(const float* a, const float* b, int n, int k, int mode, float*
     return count_launch();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// MMA rate probe: `reps` back-to-back tcgen05.mma (M=128, N, K=16) from one thread, timed with clock64 from
+// first issue to commit completion.  variant 0: A from TMEM, one accumulator; 1: A from SMEM; 2: A from TMEM,
+// two accumulators alternating; 3: A from TMEM, fully unrolled by 8.  out[0] = cycles, out[1] = issue-only cycles.
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int N, int reps, int variant, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int i = t; i < (128 * 16 + 256 * 16) / 2; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u;
+    if (t == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    if (warp == 0) { tmem_alloc(smem_u32(&slot), 512); tmem_relinquish(); }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    if (t == 0) {
+        const uint32_t idesc = make_idesc_f16(128, N, 0, 0);
+        const uint32_t sa = smem_u32(smem), sb = sa + 4096;
+        const uint64_t ad = make_desc(sa, 2048, 128), bd = make_desc(sb, N * 16, 128);
+        const long long c0 = clock64();
+        if (variant == 3) {
+            for (int i = 0; i < reps; i += 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mma_ts(tmem, tmem + 448, bd, idesc, 1);
+            }
+        } else {
+            for (int i = 0; i < reps; ++i) {
+                if (variant == 1) mma_ss(tmem, ad, bd, idesc, 1);
+                else if (variant == 2) mma_ts(tmem + ((i & 1) ? 0 : 0) + (N <= 128 ? (i & 1) * N : 0), tmem + 448, bd, idesc, 1);
+                else mma_ts(tmem, tmem + 448, bd, idesc, 1);
+            }
+        }
+        const long long c1 = clock64();
+        tc_commit(smem_u32(&bar));
+        mbar_wait(smem_u32(&bar), 0);
+        const long long c2 = clock64();
+        out[0] = c2 - c0; out[1] = c1 - c0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+int umma_rate(int n, int reps, int variant, long long* out, cudaStream_t s) {
+    if (n < 16 || n > 256 || n % 16 || reps < 8 || reps % 8) { set_error("umma_rate: bad arguments"); return -1; }
+    umma_rate_kernel<<<1, 128, 16384, s>>>(n, reps, variant, out);
+    return count_launch();
+}
+
 // ================================================================================================
 // host side
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -476,9 +532,11 @@ int fused_render_fwd(tnerf_handle* h, const RaySource& rs, long long n, float nr
     p.rs = rs; p.n_rays = n; p.n_units = (n + p.R - 1) / p.R; p.S = S; p.white = white; p.near_ = nr; p.far_ = fr;
     p.jitter = jitter; p.comp = comp; p.depth = depth; p.acc = acc; p.weights = weights; p.rays_d_out = rays_d_out;
     p.image = reinterpret_cast<const __half*>(h->packed);
+    p.debug = reinterpret_cast<long long*>(h->debug);
     const size_t smem = ((p.plan.image_bytes + 1023u) & ~1023u) + sizeof(FwdSmem);
     long long grid = (p.n_units + 1) / 2;
     if (grid > h->sm_count) grid = h->sm_count;
+    if (S % 32 == 0 && !(weights && p.G > 1)) return fused_render_fwd_fast(p, (int)grid, s);
     auto kern = p.plan.Kx == 64 ? fused_fwd_kernel<64> : p.plan.Kx == 48 ? fused_fwd_kernel<48> : p.plan.Kx == 32 ? fused_fwd_kernel<32> : fused_fwd_kernel<16>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("fused fwd: shared memory request rejected"); return (int)e; }

@@ -40,6 +40,7 @@ struct FwdParams {
     const float* jitter;
     float *comp, *depth, *acc, *weights, *rays_d_out;
     const __half* image;
+    long long* debug;          // optional clock64 phase stamps of CTA 0 (tools/trace_fwd.py)
     FusedPlan plan;
 };
 
@@ -97,5 +98,54 @@ __device__ __forceinline__ void encode_point(const float p[3], int L, uint32_t (
 
 
 bool build_plan(const tnerf_handle* h, FusedPlan& pl);
+int fused_render_fwd_fast(const FwdParams& p, int grid, cudaStream_t s);   // tnerf_fused_fast.cu (n_samples % 32 == 0)
+
+// ---- unrolled MMA issue -------------------------------------------------------------------------
+// A rolled issue loop costs ~120 cycles per tcgen05.mma (tools/umma_rate.py); unrolled, the issuer
+// sustains the 64-cycle N=128 rate.  lo/hi are the two 32-bit words of the B (or A) shared-memory descriptor;
+// only the start-address field of `lo` advances.
+template <int STEPS>
+__device__ __forceinline__ void issue_ts(uint32_t d, uint32_t a, uint32_t& b_lo, uint32_t b_hi, uint32_t b_adv, uint32_t idesc, uint32_t& acc) {
+#pragma unroll
+    for (int j = 0; j < STEPS; ++j)
+        mma_ts(d, a + 8 * j, ((uint64_t)b_hi << 32) | (b_lo + j * b_adv), idesc, j == 0 ? acc : 1u);
+    b_lo += STEPS * b_adv;
+    acc = 1;
+}
+__device__ __forceinline__ void issue_ts_n(int steps, uint32_t d, uint32_t a, uint32_t& b_lo, uint32_t b_hi, uint32_t b_adv, uint32_t idesc, uint32_t& acc) {
+    switch (steps) {
+        case 0: break;
+        case 1: issue_ts<1>(d, a, b_lo, b_hi, b_adv, idesc, acc); break;
+        case 2: issue_ts<2>(d, a, b_lo, b_hi, b_adv, idesc, acc); break;
+        case 3: issue_ts<3>(d, a, b_lo, b_hi, b_adv, idesc, acc); break;
+        case 4: issue_ts<4>(d, a, b_lo, b_hi, b_adv, idesc, acc); break;
+        case 8: issue_ts<8>(d, a, b_lo, b_hi, b_adv, idesc, acc); break;
+        default:
+            for (int j = 0; j < steps; ++j) issue_ts<1>(d, a + 8 * j, b_lo, b_hi, b_adv, idesc, acc);
+    }
+}
+template <int STEPS>
+__device__ __forceinline__ void issue_ss(uint32_t d, uint32_t& a_lo, uint32_t a_hi, uint32_t a_adv, uint32_t& b_lo, uint32_t b_hi, uint32_t b_adv,
+                                         uint32_t idesc, uint32_t& acc) {
+#pragma unroll
+    for (int j = 0; j < STEPS; ++j)
+        mma_ss(d, ((uint64_t)a_hi << 32) | (a_lo + j * a_adv), ((uint64_t)b_hi << 32) | (b_lo + j * b_adv), idesc, j == 0 ? acc : 1u);
+    a_lo += STEPS * a_adv;
+    b_lo += STEPS * b_adv;
+    acc = 1;
+}
+__device__ __forceinline__ void issue_ss_n(int steps, uint32_t d, uint32_t& a_lo, uint32_t a_hi, uint32_t a_adv, uint32_t& b_lo, uint32_t b_hi,
+                                           uint32_t b_adv, uint32_t idesc, uint32_t& acc) {
+    switch (steps) {
+        case 0: break;
+        case 1: issue_ss<1>(d, a_lo, a_hi, a_adv, b_lo, b_hi, b_adv, idesc, acc); break;
+        case 2: issue_ss<2>(d, a_lo, a_hi, a_adv, b_lo, b_hi, b_adv, idesc, acc); break;
+        case 3: issue_ss<3>(d, a_lo, a_hi, a_adv, b_lo, b_hi, b_adv, idesc, acc); break;
+        case 4: issue_ss<4>(d, a_lo, a_hi, a_adv, b_lo, b_hi, b_adv, idesc, acc); break;
+        case 8: issue_ss<8>(d, a_lo, a_hi, a_adv, b_lo, b_hi, b_adv, idesc, acc); break;
+        default:
+            for (int j = 0; j < steps; ++j) issue_ss<1>(d, a_lo, a_hi, a_adv, b_lo, b_hi, b_adv, idesc, acc);
+    }
+}
 
 }  // namespace tnerf

@@ -1,0 +1,331 @@
+// Fused forward kernel, software-pipelined variant for n_samples % 32 == 0 (every BASELINE config).
+// Same math and tensor-memory plan as tnerf_fused.cu; what changes is the schedule:
+//   * one MMA-issuer warp per warpgroup, fully unrolled issue (64 cycles per N=128 MMA);
+//   * the NEXT tile's rays / depths / Fourier features are computed while the current tile's head GEMM runs,
+//     and its inputs are prefetched one stage earlier, so the encoding never sits on the critical path;
+//   * compositing works from registers: a warp holds 32 consecutive samples of one ray, scans them with
+//     shuffles and leaves a 6-float partial (chunk transmittance + weighted sums); rays are stitched from
+//     their chunk partials by one thread -- no per-sample staging in shared memory, one named barrier per unit.
+#include "tnerf_fused.cuh"
+
+namespace tnerf {
+
+constexpr int FF_THREADS = 320;
+constexpr int FTM_ACC = 0, FTM_ACT = 128, FTM_X = 192, FTM_HEAD = 224, FTM_ONES = 240, FTM_WG = 256;
+constexpr int FF_MAX_CHUNKS = 32;
+
+struct FastSmem {
+    float part[2][2][FF_MAX_CHUNKS][8];   // [warpgroup][unit parity][chunk] = {P, sum w r, sum w g, sum w b, sum w z, sum w, -, -}
+    float tin[2][FF_MAX_CHUNKS];          // transmittance entering each chunk (weights output only)
+    uint64_t bar_w, bar_a[2], bar_acc[2], bar_head[2];
+    uint32_t tmem_slot;
+};
+
+struct PreIn {          // prefetched inputs of one sample row
+    float o[3], d[3], u0, u1;
+    long long ray;
+    int si;
+    bool valid;
+};
+
+template <int KX>
+__global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __grid_constant__ FwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    FastSmem& sm = *reinterpret_cast<FastSmem*>(smem + ((p.plan.image_bytes + 1023u) & ~1023u));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_w = smem_u32(&sm.bar_w);
+
+    if (warp == 8 && lane == 0) {
+        mbar_init(bar_w, 1);
+        for (int w = 0; w < 2; ++w) {
+            mbar_init(smem_u32(&sm.bar_a[w]), 128);
+            mbar_init(smem_u32(&sm.bar_acc[w]), 1);
+            mbar_init(smem_u32(&sm.bar_head[w]), 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) { tmem_alloc(smem_u32(&sm.tmem_slot), 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_slot;
+    long long* dbg = (p.debug && blockIdx.x == 0 && threadIdx.x == 0) ? p.debug : nullptr;
+    int dbg_n = 0;
+#define STAMP() do { if (dbg && dbg_n < 500) dbg[dbg_n++] = clock64(); } while (0)
+    const long long stride = 2LL * gridDim.x;
+    const int depth = p.plan.depth;
+
+    if (warp >= 8) {
+        // ------------------------------ MMA issuer of warpgroup w ------------------------------
+        const int w = warp - 8;
+        if (lane == 0) {
+            if (w == 0) {
+                mbar_expect_tx(bar_w, p.plan.image_bytes);
+                uint32_t off = 0;
+                while (off < p.plan.image_bytes) {
+                    const uint32_t n = min(32768u, p.plan.image_bytes - off);
+                    bulk_g2s(smem_u32(smem) + off, reinterpret_cast<const uint8_t*>(p.image) + off, n, bar_w);
+                    off += n;
+                }
+            }
+            mbar_wait(bar_w, 0);
+            uint32_t phase = 0;
+            const uint32_t wbase = smem_u32(smem);
+            const uint32_t tw = tmem + w * FTM_WG;
+            const uint32_t bar_a = smem_u32(&sm.bar_a[w]), bar_acc = smem_u32(&sm.bar_acc[w]), bar_head = smem_u32(&sm.bar_head[w]);
+            for (long long u = 2LL * blockIdx.x + w; u < p.n_units; u += stride) {
+                for (int g = 0; g < p.G; ++g) {
+                    for (int step = 0; step <= depth; ++step) {
+                        const LayerPlan& lp = p.plan.layer[step];
+                        const uint32_t idesc = lp.idesc, N = lp.N;
+                        const uint32_t b_adv = (N * 32u) >> 4;
+                        uint32_t b_lo = (((wbase + lp.b_off) >> 4) & 0x3FFFu) | (((N * 16u) >> 4) << 16);
+                        const uint32_t b_hi = (128u >> 4) | (1u << 14);
+                        const uint32_t d_t = tw + ((step == depth) ? FTM_HEAD : FTM_ACC);
+                        const int nseg = lp.nseg;
+                        uint32_t seg_a[3];
+                        int seg_n[3];
+#pragma unroll
+                        for (int sgi = 0; sgi < 3; ++sgi) {
+                            const uint32_t kind = lp.seg_kind[sgi];
+                            seg_a[sgi] = tw + (kind == SEG_ACT ? FTM_ACT : kind == SEG_X ? FTM_X : FTM_ONES);
+                            seg_n[sgi] = sgi < nseg ? lp.seg_steps[sgi] : 0;
+                        }
+                        mbar_wait(bar_a, phase);
+                        phase ^= 1;
+                        tc_fence_after();
+                        uint32_t acc = 0;
+#pragma unroll
+                        for (int sgi = 0; sgi < 3; ++sgi) issue_ts_n(seg_n[sgi], d_t, seg_a[sgi], b_lo, b_hi, b_adv, idesc, acc);
+                        tc_commit(step == depth ? bar_head : bar_acc);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------ row warpgroups ------------------------------
+        const int wg = warp >> 2, q = warp & 3, row = q * 32 + lane;
+        const uint32_t tw = tmem + wg * FTM_WG + ((uint32_t)(q * 32) << 16);
+        const uint32_t bar_a = smem_u32(&sm.bar_a[wg]), bar_acc = smem_u32(&sm.bar_acc[wg]), bar_head = smem_u32(&sm.bar_head[wg]);
+        {
+            uint32_t ones[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ones[i] = 0u;
+            ones[0] = 0x3C003C00u;
+            tmem_st8(tw + FTM_ONES, ones);
+        }
+        const int S = p.S, cpr = S >> 5;                 // chunks (warps) per ray
+        const bool jit = p.jitter != nullptr;
+        const bool camera = p.rs.rays_d == nullptr;
+        float cam[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) cam[i] = camera ? p.rs.c2w[i] : 0.f;
+        const float lin_step = (S > 1) ? __fdiv_rn(1.f, (float)(S - 1)) : 0.f;
+        const float near_ = p.near_, far_ = p.far_;
+
+        auto bin = [&](int i) -> float {      // bit-exact torch.linspace / z formula (src/sampling.py:16-17)
+            const float t = (S <= 1) ? 0.f : ((i < S / 2) ? __fmul_rn(lin_step, (float)i) : __fmaf_rn(-lin_step, (float)(S - 1 - i), 1.f));
+            return __fadd_rn(__fmul_rn(near_, __fsub_rn(1.f, t)), __fmul_rn(far_, t));
+        };
+        auto zsample = [&](int i, float uu) -> float {
+            const float zc = bin(i);
+            if (!jit) return zc;
+            const float lo = (i == 0) ? zc : __fmul_rn(0.5f, __fadd_rn(bin(i - 1), zc));
+            const float hi = (i == S - 1) ? zc : __fmul_rn(0.5f, __fadd_rn(zc, bin(i + 1)));
+            return __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), uu));
+        };
+        auto prefetch = [&](long long u, int g) -> PreIn {
+            PreIn in;
+            const int chunk = g * 4 + q;
+            in.ray = u * p.R + chunk / cpr;
+            in.si = (chunk % cpr) * 32 + lane;
+            in.valid = in.ray < p.n_rays;
+            in.u0 = in.u1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { in.o[c] = 0.f; in.d[c] = 0.f; }
+            if (in.valid) {
+                if (jit) {
+                    in.u0 = p.jitter[in.ray * S + in.si];
+                    in.u1 = (in.si + 1 < S) ? p.jitter[in.ray * S + in.si + 1] : 0.f;
+                }
+                if (!camera) {
+                    const float* po = p.rs.rays_o + p.rs.o_stride * in.ray;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { in.d[c] = p.rs.rays_d[3 * in.ray + c]; in.o[c] = po[c]; }
+                } else {
+                    const long long k = p.rs.pixel_index ? p.rs.pixel_index[in.ray] : p.rs.first_ray + in.ray;
+                    const unsigned kk = (unsigned)k, Wd = (unsigned)p.rs.W;
+                    const unsigned prow = kk / Wd, pcol = kk - prow * Wd;
+                    const float cx = __fdiv_rn((float)pcol - (float)p.rs.W * 0.5f, p.rs.focal);
+                    const float cy = -__fdiv_rn((float)prow - (float)p.rs.H * 0.5f, p.rs.focal);
+                    const float wx = fmaf(-1.f, cam[2], fmaf(cy, cam[1], cx * cam[0]));
+                    const float wy = fmaf(-1.f, cam[6], fmaf(cy, cam[5], cx * cam[4]));
+                    const float wz = fmaf(-1.f, cam[10], fmaf(cy, cam[9], cx * cam[8]));
+                    const float nrm = fmaxf(sqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx))), 1e-12f);
+                    in.d[0] = __fdiv_rn(wx, nrm); in.d[1] = __fdiv_rn(wy, nrm); in.d[2] = __fdiv_rn(wz, nrm);
+                    in.o[0] = cam[3]; in.o[1] = cam[7]; in.o[2] = cam[11];
+                }
+            }
+            return in;
+        };
+        // depth, point, features -> tensor memory; returns z and gap*|d| of this sample (src/volume.py:18-23)
+        auto encode = [&](const PreIn& in, float& z_out, float& gapdn_out) {
+            float pt[3] = {0.f, 0.f, 0.f};
+            float z = 0.f, gd = 0.f;
+            if (in.valid) {
+                z = zsample(in.si, in.u0);
+                const float znext = (in.si == S - 1) ? 0.f : zsample(in.si + 1, in.u1);
+                const float dn = sqrtf(in.d[0] * in.d[0] + in.d[1] * in.d[1] + in.d[2] * in.d[2]);
+                gd = ((in.si == S - 1) ? kLastDelta : (znext - z)) * dn;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) pt[c] = __fadd_rn(in.o[c], __fmul_rn(in.d[c], z));
+                if (p.rays_d_out && in.si == 0) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) p.rays_d_out[3 * in.ray + c] = in.d[c];
+                }
+            }
+            z_out = z; gapdn_out = gd;
+            uint32_t pk[KX / 2];
+            if (p.plan.include_input) encode_point<KX, true>(pt, p.plan.L, pk); else encode_point<KX, false>(pt, p.plan.L, pk);
+#pragma unroll
+            for (int c = 0; c < KX / 32; ++c) {
+                uint32_t chunk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) chunk[i] = pk[c * 16 + i];
+                tmem_st16(tw + FTM_X + c * 16, chunk);
+            }
+            if (KX % 32) {
+                uint32_t chunk[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) chunk[i] = pk[(KX / 32) * 16 + i];
+                tmem_st8(tw + FTM_X + (KX / 32) * 16, chunk);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_a);
+        };
+
+        uint32_t ph_acc = 0, ph_head = 0;
+        int parity = 0;
+        long long u = 2LL * blockIdx.x + wg;
+        int g = 0;
+        if (u < p.n_units) {
+            PreIn cur = prefetch(u, g);
+            float z_c, gd_c;
+            encode(cur, z_c, gd_c);
+            while (true) {
+                long long un = u;
+                int gn = g + 1;
+                if (gn == p.G) { gn = 0; un += stride; }
+                const bool has_next = un < p.n_units;
+                STAMP();
+                PreIn nxt = cur;
+                if (has_next) nxt = prefetch(un, gn);           // loads in flight under the hidden layers
+                STAMP();
+                for (int l = 0; l < depth; ++l) {
+                    mbar_wait(bar_acc, ph_acc);
+                    ph_acc ^= 1;
+                    tc_fence_after();
+                    STAMP();
+#pragma unroll
+                    for (int c = 0; c < 4; c += 2) {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32(tw + FTM_ACC + c * 32, v0);
+                        tmem_ld32(tw + FTM_ACC + c * 32 + 32, v1);
+                        tc_wait_ld();
+                        uint32_t h0[16], h1[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) h0[i] = pack_relu_h2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+                        tmem_st16(tw + FTM_ACT + c * 16, h0);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) h1[i] = pack_relu_h2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+                        tmem_st16(tw + FTM_ACT + c * 16 + 16, h1);
+                    }
+                    tc_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(bar_a);
+                    STAMP();
+                }
+                // the head GEMM of this tile is now queued: build the next tile's operand under it
+                float z_n = 0.f, gd_n = 0.f;
+                if (has_next) encode(nxt, z_n, gd_n);
+                STAMP();
+                mbar_wait(bar_head, ph_head);
+                ph_head ^= 1;
+                tc_fence_after();
+                STAMP();
+                uint32_t hv[4];
+                tmem_ld4(tw + FTM_HEAD, hv);
+                tc_wait_ld();
+                tc_fence_before();
+                const float sigma = fmaxf(__uint_as_float(hv[0]), 0.f);
+                const float cr = 1.f / (1.f + __expf(-__uint_as_float(hv[1])));
+                const float cg = 1.f / (1.f + __expf(-__uint_as_float(hv[2])));
+                const float cb = 1.f / (1.f + __expf(-__uint_as_float(hv[3])));
+                // chunk-local compositing (this warp = 32 consecutive samples of one ray)
+                const float alpha = cur.valid ? 1.f - expf(-sigma * gd_c) : 0.f;
+                const float qv = 1.f - alpha + kEpsT;
+                float incl = qv;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const float up = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl *= up;
+                }
+                float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = 1.f;
+                const float wl = alpha * excl;
+                const float s0 = warp_sum(wl * cr), s1 = warp_sum(wl * cg), s2 = warp_sum(wl * cb), s3 = warp_sum(wl * z_c), s4 = warp_sum(wl);
+                const float P = __shfl_sync(0xffffffffu, incl, 31);
+                const int chunk = g * 4 + q;
+                if (lane == 0) {
+                    float* pp = sm.part[wg][parity][chunk];
+                    pp[0] = P; pp[1] = s0; pp[2] = s1; pp[3] = s2; pp[4] = s3; pp[5] = s4;
+                }
+                if (g == p.G - 1) {
+                    bar_sync(1 + wg, 128);
+                    if (row < p.R) {
+                        const long long ray = u * p.R + row;
+                        if (ray < p.n_rays) {
+                            float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dd = 0.f, A = 0.f;
+                            for (int c = 0; c < cpr; ++c) {
+                                const float* pp = sm.part[wg][parity][row * cpr + c];
+                                if (p.weights) sm.tin[wg][row * cpr + c] = T;
+                                C0 = fmaf(T, pp[1], C0); C1 = fmaf(T, pp[2], C1); C2 = fmaf(T, pp[3], C2);
+                                Dd = fmaf(T, pp[4], Dd); A = fmaf(T, pp[5], A);
+                                T *= pp[0];
+                            }
+                            const float bg = p.white ? 1.f - A : 0.f;
+                            p.comp[3 * ray] = C0 + bg; p.comp[3 * ray + 1] = C1 + bg; p.comp[3 * ray + 2] = C2 + bg;
+                            if (p.depth) p.depth[ray] = Dd;
+                            if (p.acc) p.acc[ray] = A;
+                        }
+                    }
+                    if (p.weights) {      // host guarantees G == 1 here: every chunk of the unit belongs to this tile
+                        bar_sync(1 + wg, 128);
+                        if (cur.valid) p.weights[cur.ray * S + cur.si] = wl * sm.tin[wg][chunk];
+                    }
+                    parity ^= 1;
+                }
+                STAMP();
+                if (!has_next) break;
+                u = un; g = gn; cur = nxt; z_c = z_n; gd_c = gd_n;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+int fused_render_fwd_fast(const FwdParams& p, int grid, cudaStream_t s) {
+    const size_t smem = ((p.plan.image_bytes + 1023u) & ~1023u) + sizeof(FastSmem);
+    auto kern = p.plan.Kx == 64 ? fused_fwd_fast_kernel<64> : p.plan.Kx == 48 ? fused_fwd_fast_kernel<48>
+              : p.plan.Kx == 32 ? fused_fwd_fast_kernel<32> : fused_fwd_fast_kernel<16>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("fused fwd (fast): shared memory request rejected"); return (int)e; }
+    kern<<<(unsigned)grid, FF_THREADS, smem, s>>>(p);
+    return count_launch();
+}
+
+}  // namespace tnerf

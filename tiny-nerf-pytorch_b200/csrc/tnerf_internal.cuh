@@ -47,6 +47,7 @@ struct tnerf_handle {
     int sm_count = 0;
     bool fused_ok = false;
     int num_freqs = 0;                    // (in_dim-3)/6 when in_dim = 3+6L
+    void* debug = nullptr;                // optional device buffer (1024 int64) for kernel phase stamps
 };
 
 namespace tnerf {
@@ -79,5 +80,6 @@ int fused_render_fwd(tnerf_handle* h, const RaySource& rs, long long n, float nr
 int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, float fr, int S, const float* jitter, int white,
                 const float* target, float loss_denom, const float* gC, const float* gD, const float* gA, const float* gW,
                 float grad_scale, const float* grad_scale_dev, float* comp, float* loss_sum, float* grads, cudaStream_t s);
+int umma_rate(int n, int reps, int variant, long long* out, cudaStream_t s);
 int umma_selftest(const float* a, const float* b, int n, int k, int mode, float* d, cudaStream_t s);
 }  // namespace tnerf

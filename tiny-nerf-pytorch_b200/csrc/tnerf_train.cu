@@ -294,11 +294,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) fused_train_kernel(const __grid
                             uint32_t a_lo = (((sbase + sg.a_off) >> 4) & 0x3FFFu) | ((uint32_t)sg.a_lbo << 16);
                             uint32_t b_lo = ((((sg.b_w ? wb : sbase) + sg.b_off) >> 4) & 0x3FFFu) | ((uint32_t)sg.b_lbo << 16);
                             const uint32_t a_hi = (uint32_t)sg.a_sbo | (1u << 14), b_hi = (uint32_t)sg.b_sbo | (1u << 14);
-                            const uint32_t a_adv = sg.a_adv, b_adv = sg.b_adv, steps = sg.steps;
-                            for (uint32_t i = 0; i < steps; ++i) {
-                                mma_ss(d_t, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, acc);
-                                a_lo += a_adv; b_lo += b_adv; acc = 1;
-                            }
+                            issue_ss_n(sg.steps, d_t, a_lo, a_hi, sg.a_adv, b_lo, b_hi, sg.b_adv, idesc, acc);
                         }
                     }
                     if (jb.w_release) tc_commit(smem_u32(&ms.bar_empty[cur_buf]));
