@@ -451,9 +451,54 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int N, int reps, int 
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// variant >= 8: (variant - 8 + 1) warps issue concurrently, warp-uniform code with one elected lane (the pattern of the
+// two-stream training kernel), A and B from shared memory, one accumulator per warp.  out[2w] = cycles to completion of
+// warp w's MMAs, out[2w+1] = issue-only cycles.
+__global__ void __launch_bounds__(128, 1) umma_rate2_kernel(int N, int reps, int nw, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar[4];
+    __shared__ uint32_t slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int i = t; i < (128 * 16 + 256 * 16) / 2; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u;
+    if (t == 0) { for (int w = 0; w < 4; ++w) mbar_init(smem_u32(&bar[w]), 1); fence_barrier_init(); }
+    if (warp == 0) { tmem_alloc(smem_u32(&slot), 512); tmem_relinquish(); }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    if (warp < nw) {
+        const uint32_t idesc = make_idesc_f16(128, N, 0, 0);
+        const uint32_t sa = smem_u32(smem), sb = sa + 4096;
+        const uint32_t alo = ((sa >> 4) & 0x3FFFu) | (128u << 16), blo = ((sb >> 4) & 0x3FFFu) | ((uint32_t)N << 16), hi = 8u | (1u << 14);
+        const uint32_t d = tmem + (N * nw <= 512 ? warp * N : 0);
+        const long long c0 = clock64();
+        for (int i = 0; i < reps; i += 8) {
+            if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mma_ss(d, ((uint64_t)hi << 32) | alo, ((uint64_t)hi << 32) | blo, idesc, 1);
+            }
+            __syncwarp();
+        }
+        const long long c1 = clock64();
+        if (elect_one()) tc_commit(smem_u32(&bar[warp]));
+        __syncwarp();
+        mbar_wait(smem_u32(&bar[warp]), 0);
+        const long long c2 = clock64();
+        if ((t & 31) == 0) { out[2 * warp] = c2 - c0; out[2 * warp + 1] = c1 - c0; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 int umma_rate(int n, int reps, int variant, long long* out, cudaStream_t s) {
     if (n < 16 || n > 256 || n % 16 || reps < 8 || reps % 8) { set_error("umma_rate: bad arguments"); return -1; }
-    umma_rate_kernel<<<1, 128, 16384, s>>>(n, reps, variant, out);
+    if (variant >= 8) {
+        if (variant > 11) { set_error("umma_rate: bad variant"); return -1; }
+        umma_rate2_kernel<<<1, 128, 16384, s>>>(n, reps, variant - 7, out);
+    } else
+        umma_rate_kernel<<<1, 128, 16384, s>>>(n, reps, variant, out);
     return count_launch();
 }
 

@@ -1,0 +1,636 @@
+// Fused training kernel, two-stream variant (sm_100a).  Same contract as tnerf_train.cu (forward recompute +
+// composite + loss gradient + full backward of src/train.py:114-126 in ONE launch), different schedule:
+//
+//   * feature-major ("transposed") GEMMs: every layer is  D[feature x sample] = W[feature x k] . H[k x sample],
+//     so the weights are the M=128 operand and a tile may hold any number of samples.  A tile is 64 samples
+//     (N = 64), which halves the activation footprint and lets TWO independent tiles ("streams") be in flight
+//     per CTA: while one stream's accumulator is being drained the other stream's GEMM owns the tensor pipe.
+//   * the fp16 weight image (132 KB) is RESIDENT in shared memory (one bulk copy per CTA), nothing is streamed;
+//   * per stream: X (8 KB) + two 16 KB activation slots; H1 is parked in registers of the drain threads between
+//     its two uses, H0 is recomputed (K = 64), dZ_l overwrites H_l in place;
+//   * biases of layers 1/3 are added in fp32 by the drain threads (thread <-> feature row), their gradients are
+//     row sums of the same threads; layers 0/2 keep their bias in the constant-1 column of the encoding;
+//   * tensor memory: dW3 (128 cols) + dW2 (128+Kx) + dW0 (Kx) stay resident, one 64-column accumulator per
+//     stream; dW1 lives in registers, half of its columns in each drain warpgroup.
+//
+// Warp roles (512 threads): warpgroup 0/1 = drain threads of stream 0/1 (thread <-> feature <-> TMEM lane);
+// warps 8-9 / 10-11 = sample threads of stream 0/1 (rays, depths, Fourier features, compositing fwd+bwd);
+// warp 12/13 lane 0 = MMA issuer of stream 0/1; warp 14 loads the weights.
+#include "tnerf_train.cuh"
+
+namespace tnerf {
+namespace t2 {
+
+constexpr int THREADS = 512;
+constexpr int C_DW3 = 0, C_DW2 = 128, C_DW0 = 320, C_D = 384;   // tensor-memory columns; accumulator of stream s at C_D + 64 s
+constexpr uint32_t S_W0 = 0, S_W1 = 16384, S_W2 = 49152, S_W3 = 98304, S_WH = 131072;
+constexpr uint32_t S_P0 = 135168, S_Q0 = 151552, S_P1 = 167936, S_Q1 = 184320;   // order matters: see the head GEMM
+constexpr uint32_t S_X0 = 200704, S_X1 = 208896, S_DZH0 = 217088, S_DZH1 = 219136, S_MISC = 221184;
+
+struct Misc {
+    float xch[2][24];          // per stream: cross-warp carries of the compositing scans (one ray spanning two warps)
+    uint64_t bar_w, bar_x[2], bar_in[2], bar_d[2], bar_head[2], bar_dzh[2], bar_g[2][2], bar_gfree[2], bar_xfree[2];
+    uint32_t tmem_slot;
+};
+
+#define T2_STAMP() do { if (dbg && dbg_n < 255) dbg[dbg_n++] = clock64(); } while (0)
+
+struct WCopy { uint32_t src, dst, bytes; };
+struct Extra { WCopy w[5]; };
+
+// ---- operand descriptors --------------------------------------------------------------------------
+// image of X(r, c), R rows: byte((c/8)*R + r)*16 + (c%8)*2.  "kmaj": r is the M/N index, c the reduction index;
+// "mnmaj": c is the M/N index, r the reduction index.
+struct Op { uint32_t lo, hi, adv; };
+// sb16 = (shared-memory base) >> 4 (the base is 1024-byte aligned and below 256 KB, so the start-address field is a plain
+// add of compile-time constants: the issuer re-materialises descriptors instead of keeping dozens of them in registers)
+__device__ __forceinline__ Op kmaj(uint32_t sb16, uint32_t off, uint32_t R) { return {sb16 + ((off >> 4) + (R << 16)), 8u | (1u << 14), R * 2u}; }
+__device__ __forceinline__ Op mnmaj(uint32_t sb16, uint32_t off, uint32_t R) { return {sb16 + ((off >> 4) + (8u << 16)), R | (1u << 14), 16u}; }
+
+template <int STEPS>
+__device__ __forceinline__ void gemm(uint32_t d, const Op a, const Op b, uint32_t idesc, uint32_t acc) {
+    const uint32_t alo = a.lo, blo = b.lo;
+#pragma unroll
+    for (int j = 0; j < STEPS; ++j)
+        mma_ss(d, ((uint64_t)a.hi << 32) | (alo + j * a.adv), ((uint64_t)b.hi << 32) | (blo + j * b.adv), idesc, j == 0 ? acc : 1u);
+}
+
+// ---- Fourier features, packed as they are produced (keeps the live set small) ---------------------
+template <int KX, bool INC>
+__device__ __forceinline__ void encode_stream(const float p[3], int L, uint32_t (&pk)[KX / 2]) {
+    constexpr int base = INC ? 3 : 0;
+    float pend = 0.f;
+    auto put = [&](int i, float v) {
+        if (i & 1) pk[i >> 1] = pack_h2(pend, v); else pend = v;
+    };
+    if (INC) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) put(a, p[a]);
+    }
+    float s[3], c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) sincos_small(p[a], s[a], c[a]);
+    int next = base;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        if (base + 6 * k + 5 < KX - 1) {
+            const bool on = k < L;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) put(base + 6 * k + a, on ? s[a] : 0.f);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) put(base + 6 * k + 3 + a, on ? c[a] : 0.f);
+            next = base + 6 * k + 6;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float s2 = s[a] + s[a];
+                const float cn = (c[a] - s[a]) * (c[a] + s[a]);
+                s[a] = s2 * c[a];
+                c[a] = cn;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < KX; ++i)
+        if (i >= next && i < KX - 1) put(i, 0.f);
+    put(KX - 1, 1.f);          // constant-1 column: bias of the layers that consume the encoding
+}
+
+// ---- drains (thread <-> feature row f; accumulator columns = the 64 samples of the tile) ------------
+// forward: + bias, relu, fp16, image row f of the slot (16 B = 8 consecutive samples)
+template <bool STASH>
+__device__ __forceinline__ void drain_fwd(uint32_t D, uint8_t* slot, int f, float bias, uint32_t (&stash)[32]) {
+    uint32_t va[2][32];
+    tmem_ld32(D, va[0]);
+    tc_wait_ld();
+    tmem_ld32(D + 32, va[1]);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (c == 1) tc_wait_ld();
+        const uint32_t (&v)[32] = va[c];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_relu_h2(__uint_as_float(v[8 * j + 0]) + bias, __uint_as_float(v[8 * j + 1]) + bias);
+            o.y = pack_relu_h2(__uint_as_float(v[8 * j + 2]) + bias, __uint_as_float(v[8 * j + 3]) + bias);
+            o.z = pack_relu_h2(__uint_as_float(v[8 * j + 4]) + bias, __uint_as_float(v[8 * j + 5]) + bias);
+            o.w = pack_relu_h2(__uint_as_float(v[8 * j + 6]) + bias, __uint_as_float(v[8 * j + 7]) + bias);
+            *reinterpret_cast<uint4*>(slot + ((size_t)((c * 4 + j) * 128 + f) << 4)) = o;
+            if (STASH) { stash[(c * 4 + j) * 4 + 0] = o.x; stash[(c * 4 + j) * 4 + 1] = o.y; stash[(c * 4 + j) * 4 + 2] = o.z; stash[(c * 4 + j) * 4 + 3] = o.w; }
+        }
+    }
+}
+__device__ __forceinline__ float h2sum(uint32_t h) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h));
+    return a.x + a.y;
+}
+// backward: dZ = dH * (H > 0) over H in place; optionally returns the row sum (bias gradient of this feature)
+template <bool SUM>
+__device__ __forceinline__ float drain_bwd(uint32_t D, uint8_t* slot, int f) {
+    float sum = 0.f;
+    uint32_t va[2][32];
+    tmem_ld32(D, va[0]);
+    tc_wait_ld();
+    tmem_ld32(D + 32, va[1]);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (c == 1) tc_wait_ld();
+        const uint32_t (&v)[32] = va[c];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4* p = reinterpret_cast<uint4*>(slot + ((size_t)((c * 4 + j) * 128 + f) << 4));
+            const uint4 h = *p;
+            uint4 o;
+            o.x = pack_sat_h2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])) & relu_mask(h.x);
+            o.y = pack_sat_h2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])) & relu_mask(h.y);
+            o.z = pack_sat_h2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])) & relu_mask(h.z);
+            o.w = pack_sat_h2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])) & relu_mask(h.w);
+            *p = o;
+            if (SUM) sum += (h2sum(o.x) + h2sum(o.y)) + (h2sum(o.z) + h2sum(o.w));
+        }
+    }
+    return sum;
+}
+
+// ---- MMA issuer of stream S (one thread).  S is a template parameter so that every shared-memory offset folds into
+// an immediate: the issuer runs with 40 registers.
+template <int KX, int S>
+__device__ __forceinline__ void issuer_loop(Misc& ms, uint32_t sbase, uint32_t tmem, long long n_tiles_mine, long long* dbg) {
+    int dbg_n = 0;
+    constexpr int s = S;
+    constexpr int XS = KX / 16;
+    const uint32_t bar_x = smem_u32(&ms.bar_x[s]), bar_in = smem_u32(&ms.bar_in[s]), bar_d = smem_u32(&ms.bar_d[s]);
+    const uint32_t bar_head = smem_u32(&ms.bar_head[s]), bar_dzh = smem_u32(&ms.bar_dzh[s]), bar_gfree = smem_u32(&ms.bar_gfree[s]);
+    const uint32_t bar_g0 = smem_u32(&ms.bar_g[s][0]), bar_g1 = smem_u32(&ms.bar_g[s][1]), bar_xfree = smem_u32(&ms.bar_xfree[s]);
+    const uint32_t P = s ? S_P1 : S_P0, Q = s ? S_Q1 : S_Q0, X = s ? S_X1 : S_X0, DZH = s ? S_DZH1 : S_DZH0;   // byte offsets
+    const uint32_t D = tmem + C_D + 64 * s;
+    const uint32_t i64kk = make_idesc_f16(128, 64, 0, 0), i64kt = make_idesc_f16(128, 64, 0, 1), i64tk = make_idesc_f16(128, 64, 1, 0),
+                   i64tt = make_idesc_f16(128, 64, 1, 1), i16tk = make_idesc_f16(128, 16, 1, 0), i16kt = make_idesc_f16(128, 16, 0, 1),
+                   i128kk = make_idesc_f16(128, 128, 0, 0), iXkt = make_idesc_f16(128, KX, 0, 1);
+    uint32_t ph_x = 0, ph_in = 0, ph_dzh = 0, ph_gf = 0;
+#define T2_WAIT(bar, ph) do { T2_STAMP(); mbar_wait(bar, ph); ph ^= 1; tc_fence_after(); T2_STAMP(); } while (0)
+    // the whole warp runs this loop with warp-uniform values; one elected lane issues (operands stay in uniform registers)
+#define T2_ISSUE(...) do { if (elect_one()) { __VA_ARGS__ } __syncwarp(); } while (0)
+    mbar_wait(smem_u32(&ms.bar_w), 0);
+    for (long long t = 0; t < n_tiles_mine; ++t) {
+        // descriptors are rebuilt from an opaque copy of the base every tile: hoisted out of the loop they would
+        // occupy ~100 registers, rebuilt they are one uniform add each
+        uint32_t sb = sbase >> 4;
+        asm volatile("" : "+r"(sb));
+        // operands (descriptor words); weights are rows = output features
+        const Op aW0 = kmaj(sb, S_W0, 128), aW1 = kmaj(sb, S_W1, 128), aW2h = kmaj(sb, S_W2, 128),
+                 aW2x = kmaj(sb, S_W2 + 32768, 128), aW3 = kmaj(sb, S_W3, 128);
+        const Op aW1t = mnmaj(sb, S_W1, 128), aW2t = mnmaj(sb, S_W2, 128), aW3t = mnmaj(sb, S_W3, 128);
+        const Op bWH = kmaj(sb, S_WH, 16), aWHt = mnmaj(sb, S_WH, 16);
+        const Op bXk = kmaj(sb, X, 64), bXt = mnmaj(sb, X, 64);
+        const Op bP = mnmaj(sb, P, 128), bQ = mnmaj(sb, Q, 128);     // [sample x feature] readers (forward / dgrad)
+        const Op aP = kmaj(sb, P, 128), aQ = kmaj(sb, Q, 128);       // [feature x sample] readers (wgrad)
+        const Op bP_lo = kmaj(sb, P, 128), bP_hi = kmaj(sb, P + 1024, 128);
+        // head GEMM reads H3 as the M operand with samples on the rows: 128 rows are fetched, the tile's 64 samples
+        // land on accumulator lanes 64 s .. 64 s + 63 (stream 1 starts one slot early), the other rows are ignored
+        const Op aQhead = mnmaj(sb, s ? Q - 16384 : Q, 128);
+        const Op bDZHt = mnmaj(sb, DZH, 64), bDZHk = kmaj(sb, DZH, 64);
+        T2_WAIT(bar_x, ph_x);
+        T2_ISSUE(gemm<XS>(D, aW0, bXk, i64kk, 0); tc_commit(bar_d););                                   // F0: H0
+        T2_WAIT(bar_in, ph_in);
+        T2_ISSUE(gemm<8>(D, aW1, bP, i64kt, 0); tc_commit(bar_d););                                     // F1: H1
+        T2_WAIT(bar_in, ph_in);
+        T2_ISSUE(gemm<8>(D, aW2h, bQ, i64kt, 0); gemm<XS>(D, aW2x, bXk, i64kk, 1); tc_commit(bar_d););  // F2: H2
+        T2_WAIT(bar_in, ph_in);
+        T2_ISSUE(gemm<8>(D, aW3, bP, i64kt, 0); tc_commit(bar_d););                                     // F3: H3
+        T2_WAIT(bar_in, ph_in);
+        T2_ISSUE(gemm<8>(D, aQhead, bWH, i16tk, 0); tc_commit(bar_head););                              // heads (samples on lanes)
+        T2_WAIT(bar_dzh, ph_dzh);
+        T2_ISSUE(gemm<4>(D + 16, aQ, bDZHt, i16kt, 0); tc_commit(bar_d););                              // head wgrad: H3 . dZh
+        T2_WAIT(bar_in, ph_in);
+        T2_ISSUE(gemm<1>(D, aWHt, bDZHk, i64tk, 0); tc_commit(bar_d););                                 // head dgrad -> dH3
+        T2_WAIT(bar_in, ph_in);
+        T2_ISSUE(gemm<4>(tmem + C_DW3, aQ, aP, i128kk, 1);                                              // dW3 += dZ3 . H2^T
+                 gemm<8>(D, aW3t, bQ, i64tt, 0); tc_commit(bar_d););                                    // dH2
+        T2_WAIT(bar_in, ph_in);
+        T2_ISSUE(gemm<4>(tmem + C_DW2, aP, aQ, i128kk, 1);                                              // dW2[:, :128] += dZ2 . H1^T
+                 gemm<4>(tmem + C_DW2 + 128, aP, bXt, iXkt, 1);                                         // dW2[:, 128:] += dZ2 . X^T
+                 gemm<8>(D, aW2t, bP, i64tt, 0); tc_commit(bar_d););                                    // dH1
+        T2_WAIT(bar_in, ph_in);
+        T2_ISSUE(gemm<XS>(D, aW0, bXk, i64kk, 0); tc_commit(bar_d););                                   // recompute H0
+        T2_WAIT(bar_in, ph_in);
+        T2_ISSUE(gemm<4>(D, aQ, bP_lo, i64kk, 0); tc_commit(bar_g0););                                  // dW1[:, :64] partial
+        T2_WAIT(bar_gfree, ph_gf);
+        T2_ISSUE(gemm<4>(D, aQ, bP_hi, i64kk, 0); tc_commit(bar_g1););                                  // dW1[:, 64:] partial
+        T2_WAIT(bar_gfree, ph_gf);
+        T2_ISSUE(gemm<8>(D, aW1t, bQ, i64tt, 0); tc_commit(bar_d););                                    // dH0
+        T2_WAIT(bar_in, ph_in);
+        T2_ISSUE(gemm<4>(tmem + C_DW0, aP, bXt, iXkt, 1); tc_commit(bar_xfree););                       // dW0 += dZ0 . X^T ; tile done
+    }
+#undef T2_ISSUE
+#undef T2_WAIT
+}
+
+template <int KX>
+__global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_constant__ TrainParams p, const __grid_constant__ Extra ex) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    Misc& ms = *reinterpret_cast<Misc*>(smem + S_MISC);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wg = warp >> 2;
+    const uint32_t sbase = smem_u32(smem);
+
+    if (warp == 12 && lane == 0) {
+        mbar_init(smem_u32(&ms.bar_w), 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&ms.bar_x[s]), 64);
+            mbar_init(smem_u32(&ms.bar_in[s]), 128);
+            mbar_init(smem_u32(&ms.bar_d[s]), 1);
+            mbar_init(smem_u32(&ms.bar_head[s]), 1);
+            mbar_init(smem_u32(&ms.bar_dzh[s]), 64);
+            mbar_init(smem_u32(&ms.bar_g[s][0]), 1);
+            mbar_init(smem_u32(&ms.bar_g[s][1]), 1);
+            mbar_init(smem_u32(&ms.bar_gfree[s]), 128);
+            mbar_init(smem_u32(&ms.bar_xfree[s]), 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) { tmem_alloc(smem_u32(&ms.tmem_slot), 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = ms.tmem_slot;
+    if (warp < 8) {   // zero the resident weight-gradient accumulators (both streams accumulate into them from the first tile)
+        const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = 0u;
+        for (int c0 = (warp >> 2) * 192; c0 < (warp >> 2) * 192 + 192; c0 += 16) tmem_st16(tl + c0, z);
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // tiles are dealt round-robin over (cta, stream) pairs
+    const long long nstreams = 2LL * gridDim.x;
+    long long n_my[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const long long j = 2LL * blockIdx.x + s;
+        n_my[s] = (j < p.n_tiles) ? (p.n_tiles - j + nstreams - 1) / nstreams : 0;
+    }
+    float* slab = p.slabs + (size_t)blockIdx.x * p.sm.total;
+
+    if (wg == 3) {
+        TN_SETMAXNREG_DEC(24);
+        if (warp == 14 && lane == 0) {
+            const uint32_t bar_w = smem_u32(&ms.bar_w);
+            uint32_t total = 0;
+            for (int i = 0; i < 5; ++i) total += ex.w[i].bytes;
+            mbar_expect_tx(bar_w, total);
+            for (int i = 0; i < 5; ++i) {
+                uint32_t off = 0;
+                while (off < ex.w[i].bytes) {
+                    const uint32_t n = min(16384u, ex.w[i].bytes - off);
+                    bulk_g2s(sbase + ex.w[i].dst + off, reinterpret_cast<const uint8_t*>(p.image) + ex.w[i].src + off, n, bar_w);
+                    off += n;
+                }
+            }
+        }
+        if (warp == 12) issuer_loop<KX, 0>(ms, sbase, tmem, n_my[0], (p.debug && blockIdx.x == 0 && lane == 0) ? p.debug + 256 : nullptr);
+        if (warp == 13) issuer_loop<KX, 1>(ms, sbase, tmem, n_my[1], nullptr);
+        __syncthreads();                                          // (A)
+        __syncthreads();                                          // (B)
+    } else if (wg == 2) {
+        // ------------------------------ sample threads: warps 8-9 stream 0, warps 10-11 stream 1 ------------------------------
+        TN_SETMAXNREG_DEC(104);
+        const int s = (warp - 8) >> 1, wp = (warp - 8) & 1, i = wp * 32 + lane;
+        const uint32_t Dh = tmem + ((uint32_t)((warp & 3) * 32) << 16) + C_D + 64 * s;
+        uint8_t* X = smem + (s ? S_X1 : S_X0);
+        uint8_t* DZH = smem + (s ? S_DZH1 : S_DZH0);
+        const uint32_t bar_x = smem_u32(&ms.bar_x[s]), bar_head = smem_u32(&ms.bar_head[s]), bar_dzh = smem_u32(&ms.bar_dzh[s]),
+                       bar_xfree = smem_u32(&ms.bar_xfree[s]);
+        float* xch = ms.xch[s];
+        *reinterpret_cast<uint4*>(DZH + ((size_t)(64 + i) << 4)) = make_uint4(0u, 0u, 0u, 0u);   // head columns 8..15 stay zero
+        const bool jit = p.jitter != nullptr;
+        const float gscale = p.scale_dev ? *p.scale_dev : p.scale;
+        const float bs = p.b_sigma[0], br = p.b_rgb[0], bg = p.b_rgb[1], bb = p.b_rgb[2];
+        float hb[4] = {0.f, 0.f, 0.f, 0.f}, loss_acc = 0.f;
+        const long long j0 = 2LL * blockIdx.x + s;
+        const int S = p.S, W = S < 32 ? S : 32, sl = lane & (W - 1), si = i % S;
+        const bool two = S == 64;                    // one ray spans both warps of the pair
+        const bool camera = p.rs.rays_d == nullptr;
+        float cam[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) cam[k] = camera ? p.rs.c2w[k] : 0.f;
+        const float lin_step = (S > 1) ? __fdiv_rn(1.f, (float)(S - 1)) : 0.f;
+        const float near_ = p.near_, far_ = p.far_;
+        auto bin = [&](int k) -> float {      // bit-exact torch.linspace / z formula (src/sampling.py:16-17)
+            const float t = (S <= 1) ? 0.f : ((k < S / 2) ? __fmul_rn(lin_step, (float)k) : __fmaf_rn(-lin_step, (float)(S - 1 - k), 1.f));
+            return __fadd_rn(__fmul_rn(near_, __fsub_rn(1.f, t)), __fmul_rn(far_, t));
+        };
+        auto zsample = [&](int k, float uu) -> float {   // src/sampling.py:21-25
+            const float zc = bin(k);
+            if (!jit) return zc;
+            const float lo = (k == 0) ? zc : __fmul_rn(0.5f, __fadd_rn(bin(k - 1), zc));
+            const float hi = (k == S - 1) ? zc : __fmul_rn(0.5f, __fadd_rn(zc, bin(k + 1)));
+            return __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), uu));
+        };
+        uint32_t pk[KX / 2];
+        // rays (src/rays.py:21-31), depth (sampling.py), Fourier features of sample i of `tile`; returns z and delta*|d| (volume.py:18-23)
+        auto encode = [&](long long tile, float& z_out, float& gap_out) {
+            const long long ray = tile * p.R + i / S;
+            float pt[3] = {0.f, 0.f, 0.f};
+            float z = 0.f, gd = 0.f;
+            if (ray < p.n_rays) {
+                float o[3], d[3];
+                if (!camera) load_ray(p.rs, ray, o, d);
+                else {
+                    const long long k = p.rs.pixel_index ? p.rs.pixel_index[ray] : p.rs.first_ray + ray;
+                    const unsigned kk = (unsigned)k, Wd = (unsigned)p.rs.W;
+                    const unsigned prow = kk / Wd, pcol = kk - prow * Wd;
+                    const float cx = __fdiv_rn((float)pcol - (float)p.rs.W * 0.5f, p.rs.focal);
+                    const float cy = -__fdiv_rn((float)prow - (float)p.rs.H * 0.5f, p.rs.focal);
+                    const float wx = fmaf(-1.f, cam[2], fmaf(cy, cam[1], cx * cam[0]));
+                    const float wy = fmaf(-1.f, cam[6], fmaf(cy, cam[5], cx * cam[4]));
+                    const float wz = fmaf(-1.f, cam[10], fmaf(cy, cam[9], cx * cam[8]));
+                    const float nrm = fmaxf(sqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx))), 1e-12f);
+                    d[0] = __fdiv_rn(wx, nrm); d[1] = __fdiv_rn(wy, nrm); d[2] = __fdiv_rn(wz, nrm);
+                    o[0] = cam[3]; o[1] = cam[7]; o[2] = cam[11];
+                }
+                float u0 = 0.f, u1 = 0.f;
+                if (jit) { u0 = p.jitter[ray * S + si]; if (si + 1 < S) u1 = p.jitter[ray * S + si + 1]; }
+                z = zsample(si, u0);
+                const float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                gd = ((si == S - 1) ? kLastDelta : (zsample(si + 1, u1) - z)) * dn;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) pt[c] = __fadd_rn(o[c], __fmul_rn(d[c], z));
+            }
+            z_out = z; gap_out = gd;
+            if (p.include_input) encode_stream<KX, true>(pt, p.L, pk); else encode_stream<KX, false>(pt, p.L, pk);
+        };
+        auto store_x = [&]() {
+#pragma unroll
+            for (int c = 0; c < KX / 8; ++c)
+                *reinterpret_cast<uint4*>(X + ((size_t)(c * 64 + i) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            fence_proxy_async();
+            mbar_arrive(bar_x);
+        };
+        auto segsum = [&](float v) -> float {      // sum over the W lanes of this thread's ray segment
+            for (int o = W >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            return v;
+        };
+        uint32_t ph_head = 0, ph_xfree = 0;
+        float z_cur = 0.f, gap_cur = 0.f;
+        long long* dbg = (p.debug && blockIdx.x == 0 && warp == 8 && lane == 0) ? p.debug + 512 : nullptr;
+        int dbg_n = 0;
+        if (n_my[s] > 0) { encode(j0, z_cur, gap_cur); store_x(); }
+        for (long long t = 0; t < n_my[s]; ++t) {
+            const long long tile = j0 + t * nstreams;
+            const bool more = t + 1 < n_my[s];
+            float z_next = 0.f, gap_next = 0.f;
+            T2_STAMP();
+            if (more) encode(tile + nstreams, z_next, gap_next);          // under the forward GEMMs of this tile
+            T2_STAMP();
+            // per-ray inputs of the loss are fetched before the heads are ready
+            const long long ray = tile * p.R + i / S;
+            const bool valid = ray < p.n_rays;
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f, gd = 0.f, ga = 0.f;
+            if (valid) {
+                if (p.target) { t0 = p.target[3 * ray]; t1 = p.target[3 * ray + 1]; t2 = p.target[3 * ray + 2]; }
+                else {
+                    if (p.gC) { t0 = p.gC[3 * ray]; t1 = p.gC[3 * ray + 1]; t2 = p.gC[3 * ray + 2]; }
+                    if (p.gD) gd = p.gD[ray];
+                    if (p.gA) ga = p.gA[ray];
+                }
+            }
+            mbar_wait(bar_head, ph_head); ph_head ^= 1;
+            T2_STAMP();
+            tc_fence_after();
+            float4 own;
+            {
+                uint32_t v[4];
+                tmem_ld4(Dh, v);
+                tc_wait_ld();
+                own.x = fmaxf(__uint_as_float(v[0]) + bs, 0.f);
+                own.y = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(v[1]) + br)));
+                own.z = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(v[2]) + bg)));
+                own.w = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(v[3]) + bb)));
+            }
+            // ---- compositing forward + loss gradient + reverse scan, one sample per thread, all in registers
+            //      (src/volume.py:18-44 and its backward) ----
+            const float e = valid ? __expf(-own.x * gap_cur) : 1.f;
+            const float alpha = valid ? 1.f - e : 0.f;
+            const float q = valid ? 1.f - alpha + kEpsT : 1.f;
+            float incl = q;
+            for (int off = 1; off < W; off <<= 1) {
+                const float up = __shfl_up_sync(0xffffffffu, incl, off, W);
+                if (sl >= off) incl *= up;
+            }
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1, W);
+            if (sl == 0) excl = 1.f;
+            const float wl = alpha * excl;
+            float c0 = segsum(wl * own.y), c1 = segsum(wl * own.z), c2 = segsum(wl * own.w), asum = segsum(wl);
+            float Tc = 1.f;
+            if (two) {
+                const float Pw = __shfl_sync(0xffffffffu, incl, 31);
+                if (lane == 0) { float* x = xch + wp * 8; x[0] = Pw; x[1] = c0; x[2] = c1; x[3] = c2; x[4] = asum; }
+                bar_sync(1 + s, 64);
+                const float P0 = xch[0];
+                c0 = fmaf(P0, xch[9], xch[1]); c1 = fmaf(P0, xch[10], xch[2]); c2 = fmaf(P0, xch[11], xch[3]); asum = fmaf(P0, xch[12], xch[4]);
+                if (wp == 1) Tc = P0;
+            }
+            const float Ti = Tc * excl, w = alpha * Ti;
+            const float bgc = p.white ? 1.f - asum : 0.f;
+            const float C0 = c0 + bgc, C1 = c1 + bgc, C2 = c2 + bgc;
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+            const bool leader = sl == 0 && !(two && wp == 1);
+            if (valid) {
+                if (p.target) {
+                    const float e0 = C0 - t0, e1 = C1 - t1, e2 = C2 - t2;
+                    g0 = 2.f * e0 * p.inv_denom; g1 = 2.f * e1 * p.inv_denom; g2 = 2.f * e2 * p.inv_denom;
+                    if (leader) loss_acc += (e0 * e0 + e1 * e1 + e2 * e2) * p.inv_denom;
+                } else { g0 = t0; g1 = t1; g2 = t2; }
+                if (p.comp && leader) { p.comp[3 * ray] = C0; p.comp[3 * ray + 1] = C1; p.comp[3 * ray + 2] = C2; }
+            }
+            const float gconst = ga - (p.white ? (g0 + g1 + g2) : 0.f);
+            const float g = valid ? (g0 * own.y + g1 * own.z + g2 * own.w + gd * z_cur + gconst) : 0.f;
+            float Aa = g * alpha, Qq = q;        // suffix composition of the maps R -> g a + q R
+            for (int off = 1; off < W; off <<= 1) {
+                const float An = __shfl_down_sync(0xffffffffu, Aa, off, W);
+                const float Qn = __shfl_down_sync(0xffffffffu, Qq, off, W);
+                if (sl + off < W) { Aa = fmaf(Qq, An, Aa); Qq *= Qn; }
+            }
+            float Rc = 0.f;
+            if (two) {
+                if (wp == 1 && lane == 0) xch[16] = Aa;
+                bar_sync(1 + s, 64);
+                if (wp == 0) Rc = xch[16];
+            }
+            const float Rprev = fmaf(Qq, Rc, Aa);
+            float Ri = __shfl_down_sync(0xffffffffu, Rprev, 1, W);
+            if (sl == W - 1) Ri = Rc;
+            {
+                const float dsig = Ti * (g - Ri) * gap_cur * e;
+                const float s0 = (own.x > 0.f) ? dsig * gscale : 0.f;
+                const float s1 = w * g0 * own.y * (1.f - own.y) * gscale;
+                const float s2 = w * g1 * own.z * (1.f - own.z) * gscale;
+                const float s3 = w * g2 * own.w * (1.f - own.w) * gscale;
+                *reinterpret_cast<uint4*>(DZH + ((size_t)i << 4)) = make_uint4(pack_sat_h2(s0, s1), pack_sat_h2(s2, s3), 0u, 0u);
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(bar_dzh);
+                T2_STAMP();
+                hb[0] += s0; hb[1] += s1; hb[2] += s2; hb[3] += s3;      // head bias gradients: per-thread partials, reduced at the end
+            }
+            mbar_wait(bar_xfree, ph_xfree); ph_xfree ^= 1;       // last GEMM of the tile has completed: X may be replaced
+            T2_STAMP();
+            if (more) { store_x(); z_cur = z_next; gap_cur = gap_next; }
+        }
+        loss_acc = warp_sum(loss_acc);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hb[k] = warp_sum(hb[k]);
+        tc_fence_before();
+        __syncthreads();                                          // (A) every GEMM of both streams has completed
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) slab[p.sm.hb + (warp - 8) * 4 + k] = hb[k];
+            if (p.loss_sum && loss_acc != 0.f) atomicAdd(p.loss_sum, loss_acc);
+        }
+        __syncthreads();                                          // (B)
+    } else {
+        // ------------------------------ drain threads of stream s (thread <-> feature row) ------------------------------
+        TN_SETMAXNREG_INC(192);
+        const int s = wg, f = (warp & 3) * 32 + lane;
+        const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t D_own = tl + C_D + 64 * s, D_oth = tl + C_D + 64 * (1 - s);
+        uint8_t* P = smem + (s ? S_P1 : S_P0);
+        uint8_t* Q = smem + (s ? S_Q1 : S_Q0);
+        const uint32_t bar_in = smem_u32(&ms.bar_in[s]), bar_d = smem_u32(&ms.bar_d[s]);
+        const uint32_t bar_g_own = smem_u32(&ms.bar_g[s][s]), bar_g_oth = smem_u32(&ms.bar_g[1 - s][s]);
+        const uint32_t bar_gfree_own = smem_u32(&ms.bar_gfree[s]), bar_gfree_oth = smem_u32(&ms.bar_gfree[1 - s]);
+        float dw1[64];                  // dW1[f][64 s + j]: this warpgroup's half of the columns, BOTH streams
+#pragma unroll
+        for (int j = 0; j < 64; ++j) dw1[j] = 0.f;
+        uint32_t stash[32];             // H1 row of this feature, parked between layer 2 forward and layer 2 wgrad
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stash[j] = 0u;
+        float dwh[4] = {0.f, 0.f, 0.f, 0.f}, db1 = 0.f, db3 = 0.f;
+        const float b1 = p.b1[f], b3 = p.b3[f];
+        uint32_t ph_d = 0, ph_g_own = 0, ph_g_oth = 0;
+        long long g_oth_left = n_my[1 - s];
+        long long* dbg = (p.debug && blockIdx.x == 0 && (warp & 3) == 0 && lane == 0) ? p.debug + (s ? 768 : 0) : nullptr;
+        int dbg_n = 0;
+
+        auto drain_g = [&](uint32_t D) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(D + c * 32, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dw1[c * 32 + j] += __uint_as_float(v[j]);
+            }
+        };
+        // The other stream's dW1 half is drained at a fixed point of this stream's tile: right after the layer-3 drain, where
+        // this warpgroup would otherwise sleep through its own compositing.  The rendezvous keeps the two streams about
+        // half a tile apart (one stream's backward GEMMs run under the other's compositing); blocking waits only.
+        auto service = [&]() {
+            T2_STAMP();
+            mbar_wait(bar_g_oth, ph_g_oth);
+            tc_fence_after();
+            T2_STAMP();
+            drain_g(D_oth);
+            tc_fence_before();
+            mbar_arrive(bar_gfree_oth);
+            ph_g_oth ^= 1;
+            --g_oth_left;
+        };
+        auto wait_poll = [&](uint32_t bar, uint32_t& ph) {
+            T2_STAMP();
+            mbar_wait(bar, ph);
+            ph ^= 1;
+            tc_fence_after();
+            T2_STAMP();
+        };
+#define T2_SIGNAL() do { fence_proxy_async(); tc_fence_before(); mbar_arrive(bar_in); } while (0)
+
+        for (long long t = 0; t < n_my[s]; ++t) {
+            wait_poll(bar_d, ph_d); drain_fwd<false>(D_own, P, f, 0.f, stash); T2_SIGNAL();      // H0 -> P
+            wait_poll(bar_d, ph_d); drain_fwd<true>(D_own, Q, f, b1, stash); T2_SIGNAL();        // H1 -> Q (+ registers)
+            wait_poll(bar_d, ph_d); drain_fwd<false>(D_own, P, f, 0.f, stash); T2_SIGNAL();      // H2 -> P
+            wait_poll(bar_d, ph_d); drain_fwd<false>(D_own, Q, f, b3, stash); T2_SIGNAL();       // H3 -> Q
+            if ((s == 1 || t >= 1) && g_oth_left > 0) service();                                 // stream 1: tile t of stream 0; stream 0: tile t-1 of stream 1
+            wait_poll(bar_d, ph_d);                                                              // head wgrad
+            {
+                uint32_t v[4];
+                tmem_ld4(D_own + 16, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dwh[k] += __uint_as_float(v[k]);
+            }
+            T2_SIGNAL();
+            wait_poll(bar_d, ph_d); db3 += drain_bwd<true>(D_own, Q, f); T2_SIGNAL();            // dZ3 over H3 (Q)
+            wait_poll(bar_d, ph_d); drain_bwd<false>(D_own, P, f);                               // dZ2 over H2 (P)
+#pragma unroll
+            for (int c = 0; c < 8; ++c)                                                          // H1 back into Q (dZ3 is dead)
+                *reinterpret_cast<uint4*>(Q + ((size_t)(c * 128 + f) << 4)) = make_uint4(stash[4 * c], stash[4 * c + 1], stash[4 * c + 2], stash[4 * c + 3]);
+            T2_SIGNAL();
+            wait_poll(bar_d, ph_d); db1 += drain_bwd<true>(D_own, Q, f); T2_SIGNAL();            // dZ1 over H1 (Q)
+            wait_poll(bar_d, ph_d); drain_fwd<false>(D_own, P, f, 0.f, stash); T2_SIGNAL();      // H0 -> P (dZ2 is dead)
+            wait_poll(bar_g_own, ph_g_own); drain_g(D_own); tc_fence_before(); mbar_arrive(bar_gfree_own);
+            wait_poll(bar_d, ph_d); drain_bwd<false>(D_own, P, f); T2_SIGNAL();                  // dZ0 over H0 (P)
+        }
+        while (g_oth_left > 0) service();
+#undef T2_SIGNAL
+        tc_fence_before();
+        __syncthreads();                                          // (A)
+        tc_fence_after();
+        // ---- flush this CTA's weight-gradient slab (coalesced: consecutive rows) ----
+        auto flush_tmem = [&](int tcol, int ncols, int off) {
+            for (int c0 = 0; c0 < ncols; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(tl + tcol + c0, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 16; ++k) slab[off + (c0 + k) * 128 + f] = __uint_as_float(v[k]);
+            }
+        };
+        if (s == 0) { flush_tmem(C_DW3, 128, p.sm.dw3); flush_tmem(C_DW0, KX, p.sm.dw0); }
+        else flush_tmem(C_DW2, 128 + KX, p.sm.dw2);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) slab[p.sm.dw1 + (64 * s + j) * 128 + f] = dw1[j];
+        float* xch = reinterpret_cast<float*>(smem + S_P0);     // activation slots are free now
+        if (s == 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xch[k * 128 + f] = dwh[k];
+            xch[4 * 128 + f] = db1; xch[5 * 128 + f] = db3;
+        }
+        __syncthreads();                                          // (B) stream 1's partial sums are visible
+        if (s == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) slab[p.sm.dwh + k * 128 + f] = dwh[k] + xch[k * 128 + f];
+            slab[p.sm.db1 + f] = db1 + xch[4 * 128 + f];
+            slab[p.sm.db3 + f] = db3 + xch[5 * 128 + f];
+        }
+        tc_fence_before();
+    }
+    __syncthreads();                                              // (C)
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace t2
+
+int fused_train2(tnerf_handle* h, const FusedPlan& fp, const TrainParams& p, int Kx, int grid, cudaStream_t s) {
+    t2::Extra ex{};
+    // sub-ranges of the packed forward image (tnerf_fused.cu): the first `fan-in` reduction columns of every layer
+    // ([k/8][n][k%8] layout puts them first); the bias steps of layers 1/3 and of the heads are not used here
+    const uint32_t kx = (uint32_t)Kx;
+    ex.w[0] = {fp.layer[0].b_off, t2::S_W0, kx * 256u};
+    ex.w[1] = {fp.layer[1].b_off, t2::S_W1, 32768u};
+    ex.w[2] = {fp.layer[2].b_off, t2::S_W2, (128u + kx) * 256u};
+    ex.w[3] = {fp.layer[3].b_off, t2::S_W3, 32768u};
+    ex.w[4] = {fp.layer[4].b_off, t2::S_WH, 4096u};
+    const size_t smem = t2::S_MISC + sizeof(t2::Misc);
+    auto kern = Kx == 64 ? t2::fused_train2_kernel<64> : Kx == 48 ? t2::fused_train2_kernel<48> : Kx == 32 ? t2::fused_train2_kernel<32>
+                                                                                                            : t2::fused_train2_kernel<16>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("fused train (two-stream): shared memory request rejected"); return (int)e; }
+    kern<<<(unsigned)grid, t2::THREADS, smem, s>>>(p, ex);
+    return count_launch();
+}
+
+}  // namespace tnerf

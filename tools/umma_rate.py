@@ -1,16 +1,23 @@
-"""tcgen05.mma issue/execute rate probe (developer tool, GPU box)."""
-import os, sys
+"""tcgen05.mma issue / completion rate probe (developer tool, run on the GPU box)."""
+import os
+import sys
+
 import torch
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tiny-nerf-pytorch_b200"))
-import _engine as E
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tiny-nerf-pytorch_b200"))
+import _engine as E  # noqa: E402
+
 dev = torch.device("cuda:0")
-out = torch.zeros(2, dtype=torch.int64, device=dev)
-for variant, name in ((0, "TS 1 acc"), (1, "SS 1 acc"), (2, "TS 2 acc"), (3, "TS unroll8")):
+out = torch.zeros(8, dtype=torch.int64, device=dev)
+for name, variant in (("A=TMEM rolled", 0), ("A=SMEM rolled", 1), ("A=TMEM unroll8", 3), ("elect 1 warp", 8), ("elect 2 warps", 9), ("elect 4 warps", 11)):
     for n in (16, 64, 128, 256):
-        for reps in (64, 256):
+        for reps in (64, 512):
             for _ in range(2):
+                out.zero_()
                 E.check(E.lib().tnerf_umma_rate(n, reps, variant, E.ptr(out), E.stream(dev)))
                 torch.cuda.synchronize()
-            tot, iss = out.tolist()
-            print(f"{name:10s} N={n:3d} reps={reps:3d}: {tot / reps:6.1f} cyc/MMA to completion, {iss / reps:6.1f} cyc/MMA issue  (floor {128 * n / 256:.0f})")
+            o = out.tolist()
+            nw = variant - 7 if variant >= 8 else 1
+            tot = max(o[0:2 * nw:2]); iss = max(o[1:2 * nw:2])
+            print(f"{name:15s} N={n:3d} reps={reps:3d}x{nw}: {tot / (reps * nw):6.1f} cyc/MMA to completion, {iss / reps:6.1f} cyc/MMA issue per warp (floor {128 * n / 256:.0f})")
