@@ -97,6 +97,47 @@ __device__ __forceinline__ void encode_point(const float p[3], int L, uint32_t (
 }
 
 
+// ---- Fourier features, packed as they are produced (keeps the live set small) ---------------------
+template <int KX, bool INC>
+__device__ __forceinline__ void encode_stream(const float p[3], int L, uint32_t (&pk)[KX / 2]) {
+    constexpr int base = INC ? 3 : 0;
+    float pend = 0.f;
+    auto put = [&](int i, float v) {
+        if (i & 1) pk[i >> 1] = pack_h2(pend, v); else pend = v;
+    };
+    if (INC) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) put(a, p[a]);
+    }
+    float s[3], c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) sincos_small(p[a], s[a], c[a]);
+    int next = base;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        if (base + 6 * k + 5 < KX - 1) {
+            const bool on = k < L;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) put(base + 6 * k + a, on ? s[a] : 0.f);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) put(base + 6 * k + 3 + a, on ? c[a] : 0.f);
+            next = base + 6 * k + 6;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float s2 = s[a] + s[a];
+                const float cn = (c[a] - s[a]) * (c[a] + s[a]);
+                s[a] = s2 * c[a];
+                c[a] = cn;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < KX; ++i)
+        if (i >= next && i < KX - 1) put(i, 0.f);
+    put(KX - 1, 1.f);          // constant-1 column: bias of the layers that consume the encoding
+}
+
+
 bool build_plan(const tnerf_handle* h, FusedPlan& pl);
 int fused_render_fwd_fast(const FwdParams& p, int grid, cudaStream_t s);   // tnerf_fused_fast.cu (n_samples % 32 == 0)
 

@@ -1,23 +1,29 @@
-// Fused forward kernel, software-pipelined variant for n_samples % 32 == 0 (every BASELINE config).
-// Same math and tensor-memory plan as tnerf_fused.cu; what changes is the schedule:
-//   * one MMA-issuer warp per warpgroup, fully unrolled issue (64 cycles per N=128 MMA);
-//   * the NEXT tile's rays / depths / Fourier features are computed while the current tile's head GEMM runs,
-//     and its inputs are prefetched one stage earlier, so the encoding never sits on the critical path;
-//   * compositing works from registers: a warp holds 32 consecutive samples of one ray, scans them with
-//     shuffles and leaves a 6-float partial (chunk transmittance + weighted sums); rays are stitched from
-//     their chunk partials by one thread -- no per-sample staging in shared memory, one named barrier per unit.
+// Fused forward (render) kernel, role-split variant for n_samples % 32 == 0 (every BASELINE config).
+// Same math and tensor-memory plan as tnerf_fused.cu; what changes is who does what:
+//
+//   * two tile slots per CTA.  Per slot: one MMA-issuer warp, one EPILOGUE warpgroup (tensor memory -> relu -> fp16 ->
+//     tensor memory, nothing else) and one SAMPLE warpgroup (rays, depths, Fourier features of the NEXT tile, and the
+//     compositing of the finished one).  The serial chain of a slot is only  GEMM -> epilogue -> GEMM ... -> head GEMM;
+//     encoding and compositing run beside it, so the next tile's layer 0 is issued right behind this tile's head GEMM;
+//   * issuers are whole warps running warp-uniform code with one elected lane: tcgen05 operands stay in uniform registers
+//     and a layer's MMAs are issued back to back (a lane-0 branch makes the compiler wrap every MMA in a uniformisation loop);
+//   * compositing works from registers: a warp holds 32 consecutive samples of one ray, scans them with shuffles and leaves
+//     a 6-float partial (chunk transmittance + weighted sums); rays are stitched from their chunk partials by one thread.
+//
+// Warps: 0-3 / 4-7 epilogue warpgroups of slot 0 / 1, 8-11 / 12-15 sample warpgroups of slot 0 / 1, 16 / 17 MMA issuers
+// (18, 19 only take part in the register re-distribution).
 #include "tnerf_fused.cuh"
 
 namespace tnerf {
 
-constexpr int FF_THREADS = 320;
-constexpr int FTM_ACC = 0, FTM_ACT = 128, FTM_X = 192, FTM_HEAD = 224, FTM_ONES = 240, FTM_WG = 256;
+constexpr int FF_THREADS = 640;
+constexpr int FTM_ACC = 0, FTM_ACT = 128, FTM_X = 192, FTM_HEAD = 224, FTM_SLOT = 240, FTM_ONES = 480;
 constexpr int FF_MAX_CHUNKS = 32;
 
 struct FastSmem {
-    float part[2][2][FF_MAX_CHUNKS][8];   // [warpgroup][unit parity][chunk] = {P, sum w r, sum w g, sum w b, sum w z, sum w, -, -}
+    float part[2][2][FF_MAX_CHUNKS][8];   // [slot][unit parity][chunk] = {P, sum w r, sum w g, sum w b, sum w z, sum w, -, -}
     float tin[2][FF_MAX_CHUNKS];          // transmittance entering each chunk (weights output only)
-    uint64_t bar_w, bar_a[2], bar_acc[2], bar_head[2];
+    uint64_t bar_w, bar_x[2], bar_a[2], bar_acc[2], bar_head[2], bar_xfree[2], bar_hfree[2];
     uint32_t tmem_slot;
 };
 
@@ -35,12 +41,15 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_w = smem_u32(&sm.bar_w);
 
-    if (warp == 8 && lane == 0) {
+    if (warp == 16 && lane == 0) {
         mbar_init(bar_w, 1);
         for (int w = 0; w < 2; ++w) {
+            mbar_init(smem_u32(&sm.bar_x[w]), 128);
             mbar_init(smem_u32(&sm.bar_a[w]), 128);
             mbar_init(smem_u32(&sm.bar_acc[w]), 1);
             mbar_init(smem_u32(&sm.bar_head[w]), 1);
+            mbar_init(smem_u32(&sm.bar_xfree[w]), 1);
+            mbar_init(smem_u32(&sm.bar_hfree[w]), 128);
         }
         fence_barrier_init();
     }
@@ -49,17 +58,32 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_slot;
-    long long* dbg = (p.debug && blockIdx.x == 0 && threadIdx.x == 0) ? p.debug : nullptr;
-    int dbg_n = 0;
-#define STAMP() do { if (dbg && dbg_n < 500) dbg[dbg_n++] = clock64(); } while (0)
+    if (warp < 4) {   // constant-one chunk shared by both slots: adds the biases inside the GEMMs (A[:,0] = A[:,1] = 1)
+        uint32_t ones[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ones[i] = 0u;
+        ones[0] = 0x3C003C00u;
+        tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + FTM_ONES, ones);
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
     const long long stride = 2LL * gridDim.x;
     const int depth = p.plan.depth;
 
-    if (warp >= 8) {
-        // ------------------------------ MMA issuer of warpgroup w ------------------------------
-        const int w = warp - 8;
-        if (lane == 0) {
-            if (w == 0) {
+    if (warp >= 16) {
+        // ------------------------------ MMA issuer of slot w (warp-uniform, one elected lane issues) ------------------------------
+        TN_SETMAXNREG_DEC(40);
+        const int w = warp - 16;
+        if (w < 2) {
+            // the last layer that reads the encoding (the skip layer, else layer 0): once it has completed the next tile's features may land
+            int last_x = 0;
+            for (int l = 0; l < depth; ++l)
+                for (int sgi = 0; sgi < p.plan.layer[l].nseg; ++sgi)
+                    if (p.plan.layer[l].seg_kind[sgi] == SEG_X) last_x = l;
+            if (w == 0 && lane == 0) {
                 mbar_expect_tx(bar_w, p.plan.image_bytes);
                 uint32_t off = 0;
                 while (off < p.plan.image_bytes) {
@@ -68,11 +92,17 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
                     off += n;
                 }
             }
+            __syncwarp();
             mbar_wait(bar_w, 0);
-            uint32_t phase = 0;
+            uint32_t ph_x = 0, ph_a = 0, ph_hf = 0;
+            bool first_head = true;
+            long long* dbg = (p.debug && blockIdx.x == 0 && w == 0 && lane == 0) ? p.debug + 512 : nullptr;
+            int dbg_n = 0;
+#define STAMP() do { if (dbg && dbg_n < 250) dbg[dbg_n++] = clock64(); } while (0)
             const uint32_t wbase = smem_u32(smem);
-            const uint32_t tw = tmem + w * FTM_WG;
-            const uint32_t bar_a = smem_u32(&sm.bar_a[w]), bar_acc = smem_u32(&sm.bar_acc[w]), bar_head = smem_u32(&sm.bar_head[w]);
+            const uint32_t tw = tmem + w * FTM_SLOT;
+            const uint32_t bar_x = smem_u32(&sm.bar_x[w]), bar_a = smem_u32(&sm.bar_a[w]), bar_acc = smem_u32(&sm.bar_acc[w]),
+                           bar_head = smem_u32(&sm.bar_head[w]), bar_xfree = smem_u32(&sm.bar_xfree[w]), bar_hfree = smem_u32(&sm.bar_hfree[w]);
             for (long long u = 2LL * blockIdx.x + w; u < p.n_units; u += stride) {
                 for (int g = 0; g < p.G; ++g) {
                     for (int step = 0; step <= depth; ++step) {
@@ -88,33 +118,72 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
 #pragma unroll
                         for (int sgi = 0; sgi < 3; ++sgi) {
                             const uint32_t kind = lp.seg_kind[sgi];
-                            seg_a[sgi] = tw + (kind == SEG_ACT ? FTM_ACT : kind == SEG_X ? FTM_X : FTM_ONES);
+                            seg_a[sgi] = (kind == SEG_ONES) ? tmem + FTM_ONES : tw + (kind == SEG_ACT ? FTM_ACT : FTM_X);
                             seg_n[sgi] = sgi < nseg ? lp.seg_steps[sgi] : 0;
                         }
-                        mbar_wait(bar_a, phase);
-                        phase ^= 1;
+                        STAMP();
+                        if (step == 0) { mbar_wait(bar_x, ph_x); ph_x ^= 1; }           // features of this tile are in tensor memory
+                        else { mbar_wait(bar_a, ph_a); ph_a ^= 1; }                     // previous layer's activations are in tensor memory
+                        if (step == depth && !first_head) { mbar_wait(bar_hfree, ph_hf); ph_hf ^= 1; }   // previous head outputs were read
                         tc_fence_after();
-                        uint32_t acc = 0;
+                        STAMP();
+                        if (elect_one()) {
+                            uint32_t acc = 0;
 #pragma unroll
-                        for (int sgi = 0; sgi < 3; ++sgi) issue_ts_n(seg_n[sgi], d_t, seg_a[sgi], b_lo, b_hi, b_adv, idesc, acc);
-                        tc_commit(step == depth ? bar_head : bar_acc);
+                            for (int sgi = 0; sgi < 3; ++sgi) issue_ts_n(seg_n[sgi], d_t, seg_a[sgi], b_lo, b_hi, b_adv, idesc, acc);
+                            if (step == depth) tc_commit(bar_head);
+                            else {
+                                tc_commit(bar_acc);
+                                if (step == last_x) tc_commit(bar_xfree);
+                            }
+                        }
+                        __syncwarp();
+                        if (step == depth) first_head = false;
                     }
                 }
             }
         }
-        __syncwarp();
-    } else {
-        // ------------------------------ row warpgroups ------------------------------
-        const int wg = warp >> 2, q = warp & 3, row = q * 32 + lane;
-        const uint32_t tw = tmem + wg * FTM_WG + ((uint32_t)(q * 32) << 16);
-        const uint32_t bar_a = smem_u32(&sm.bar_a[wg]), bar_acc = smem_u32(&sm.bar_acc[wg]), bar_head = smem_u32(&sm.bar_head[wg]);
-        {
-            uint32_t ones[8];
+    } else if (warp < 8) {
+        // ------------------------------ epilogue warpgroup of slot wg ------------------------------
+        TN_SETMAXNREG_DEC(88);
+        const int wg = warp >> 2, q = warp & 3;
+        const uint32_t tw = tmem + wg * FTM_SLOT + ((uint32_t)(q * 32) << 16);
+        const uint32_t bar_a = smem_u32(&sm.bar_a[wg]), bar_acc = smem_u32(&sm.bar_acc[wg]);
+        uint32_t ph_acc = 0;
+        long long* dbg = (p.debug && blockIdx.x == 0 && warp == 0 && lane == 0) ? p.debug + 256 : nullptr;
+        int dbg_n = 0;
+        for (long long u = 2LL * blockIdx.x + wg; u < p.n_units; u += stride) {
+            for (int g = 0; g < p.G; ++g) {
+                for (int l = 0; l < depth; ++l) {
+                    STAMP();
+                    mbar_wait(bar_acc, ph_acc);
+                    ph_acc ^= 1;
+                    tc_fence_after();
+                    STAMP();
+                    uint32_t v[2][32];
+                    tmem_ld32(tw + FTM_ACC, v[0]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) ones[i] = 0u;
-            ones[0] = 0x3C003C00u;
-            tmem_st8(tw + FTM_ONES, ones);
+                    for (int c = 0; c < 4; ++c) {
+                        tc_wait_ld();
+                        if (c < 3) tmem_ld32(tw + FTM_ACC + (c + 1) * 32, v[(c + 1) & 1]);      // next 32 columns in flight
+                        uint32_t h[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) h[i] = pack_relu_h2(__uint_as_float(v[c & 1][2 * i]), __uint_as_float(v[c & 1][2 * i + 1]));
+                        tmem_st16(tw + FTM_ACT + c * 16, h);
+                    }
+                    tc_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(bar_a);
+                }
+            }
         }
+    } else {
+        // ------------------------------ sample warpgroup of slot wg ------------------------------
+        TN_SETMAXNREG_INC(128);
+        const int wg = (warp - 8) >> 2, q = warp & 3, row = q * 32 + lane;
+        const uint32_t tw = tmem + wg * FTM_SLOT + ((uint32_t)(q * 32) << 16);
+        const uint32_t bar_x = smem_u32(&sm.bar_x[wg]), bar_head = smem_u32(&sm.bar_head[wg]), bar_xfree = smem_u32(&sm.bar_xfree[wg]),
+                       bar_hfree = smem_u32(&sm.bar_hfree[wg]);
         const int S = p.S, cpr = S >> 5;                 // chunks (warps) per ray
         const bool jit = p.jitter != nullptr;
         const bool camera = p.rs.rays_d == nullptr;
@@ -123,6 +192,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
         for (int i = 0; i < 12; ++i) cam[i] = camera ? p.rs.c2w[i] : 0.f;
         const float lin_step = (S > 1) ? __fdiv_rn(1.f, (float)(S - 1)) : 0.f;
         const float near_ = p.near_, far_ = p.far_;
+        long long* dbg = (p.debug && blockIdx.x == 0 && warp == 8 && lane == 0) ? p.debug : nullptr;
+        int dbg_n = 0;
 
         auto bin = [&](int i) -> float {      // bit-exact torch.linspace / z formula (src/sampling.py:16-17)
             const float t = (S <= 1) ? 0.f : ((i < S / 2) ? __fmul_rn(lin_step, (float)i) : __fmaf_rn(-lin_step, (float)(S - 1 - i), 1.f));
@@ -169,7 +240,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
             }
             return in;
         };
-        // depth, point, features -> tensor memory; returns z and gap*|d| of this sample (src/volume.py:18-23)
+        uint32_t pk[KX / 2];
+        // depth, point, features (registers); returns z and gap*|d| of this sample (src/volume.py:18-23)
         auto encode = [&](const PreIn& in, float& z_out, float& gapdn_out) {
             float pt[3] = {0.f, 0.f, 0.f};
             float z = 0.f, gd = 0.f;
@@ -186,8 +258,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
                 }
             }
             z_out = z; gapdn_out = gd;
-            uint32_t pk[KX / 2];
-            if (p.plan.include_input) encode_point<KX, true>(pt, p.plan.L, pk); else encode_point<KX, false>(pt, p.plan.L, pk);
+            if (p.plan.include_input) encode_stream<KX, true>(pt, p.plan.L, pk); else encode_stream<KX, false>(pt, p.plan.L, pk);
+        };
+        auto store_x = [&]() {          // features -> tensor memory (A operand of layer 0 and of the skip layer)
 #pragma unroll
             for (int c = 0; c < KX / 32; ++c) {
                 uint32_t chunk[16];
@@ -203,10 +276,10 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
             }
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive(bar_a);
+            mbar_arrive(bar_x);
         };
 
-        uint32_t ph_acc = 0, ph_head = 0;
+        uint32_t ph_head = 0, ph_xfree = 0;
         int parity = 0;
         long long u = 2LL * blockIdx.x + wg;
         int g = 0;
@@ -214,42 +287,22 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
             PreIn cur = prefetch(u, g);
             float z_c, gd_c;
             encode(cur, z_c, gd_c);
+            store_x();
             while (true) {
                 long long un = u;
                 int gn = g + 1;
                 if (gn == p.G) { gn = 0; un += stride; }
                 const bool has_next = un < p.n_units;
                 STAMP();
+                // next tile: inputs, depths and features in registers while this tile runs through the layers
                 PreIn nxt = cur;
-                if (has_next) nxt = prefetch(un, gn);           // loads in flight under the hidden layers
-                STAMP();
-                for (int l = 0; l < depth; ++l) {
-                    mbar_wait(bar_acc, ph_acc);
-                    ph_acc ^= 1;
-                    tc_fence_after();
-                    STAMP();
-#pragma unroll
-                    for (int c = 0; c < 4; c += 2) {
-                        uint32_t v0[32], v1[32];
-                        tmem_ld32(tw + FTM_ACC + c * 32, v0);
-                        tmem_ld32(tw + FTM_ACC + c * 32 + 32, v1);
-                        tc_wait_ld();
-                        uint32_t h0[16], h1[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) h0[i] = pack_relu_h2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
-                        tmem_st16(tw + FTM_ACT + c * 16, h0);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) h1[i] = pack_relu_h2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
-                        tmem_st16(tw + FTM_ACT + c * 16 + 16, h1);
-                    }
-                    tc_wait_st();
-                    tc_fence_before();
-                    mbar_arrive(bar_a);
-                    STAMP();
-                }
-                // the head GEMM of this tile is now queued: build the next tile's operand under it
                 float z_n = 0.f, gd_n = 0.f;
-                if (has_next) encode(nxt, z_n, gd_n);
+                if (has_next) { nxt = prefetch(un, gn); encode(nxt, z_n, gd_n); }
+                STAMP();
+                mbar_wait(bar_xfree, ph_xfree);          // this tile's last reader of the encoding has completed
+                ph_xfree ^= 1;
+                tc_fence_after();
+                if (has_next) store_x();
                 STAMP();
                 mbar_wait(bar_head, ph_head);
                 ph_head ^= 1;
@@ -259,10 +312,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
                 tmem_ld4(tw + FTM_HEAD, hv);
                 tc_wait_ld();
                 tc_fence_before();
+                mbar_arrive(bar_hfree);
                 const float sigma = fmaxf(__uint_as_float(hv[0]), 0.f);
-                const float cr = 1.f / (1.f + __expf(-__uint_as_float(hv[1])));
-                const float cg = 1.f / (1.f + __expf(-__uint_as_float(hv[2])));
-                const float cb = 1.f / (1.f + __expf(-__uint_as_float(hv[3])));
+                const float cr = __fdividef(1.f, 1.f + __expf(-__uint_as_float(hv[1])));
+                const float cg = __fdividef(1.f, 1.f + __expf(-__uint_as_float(hv[2])));
+                const float cb = __fdividef(1.f, 1.f + __expf(-__uint_as_float(hv[3])));
                 // chunk-local compositing (this warp = 32 consecutive samples of one ray)
                 const float alpha = cur.valid ? 1.f - expf(-sigma * gd_c) : 0.f;
                 const float qv = 1.f - alpha + kEpsT;

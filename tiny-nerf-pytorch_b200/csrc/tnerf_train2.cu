@@ -33,7 +33,8 @@ struct Misc {
     uint32_t tmem_slot;
 };
 
-#define T2_STAMP() do { if (dbg && dbg_n < 255) dbg[dbg_n++] = clock64(); } while (0)
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define T2_STAMP() do { if (dbg && dbg_n < 251) dbg[dbg_n++] = clock64(); } while (0)
 
 struct WCopy { uint32_t src, dst, bytes; };
 struct Extra { WCopy w[5]; };
@@ -53,46 +54,6 @@ __device__ __forceinline__ void gemm(uint32_t d, const Op a, const Op b, uint32_
 #pragma unroll
     for (int j = 0; j < STEPS; ++j)
         mma_ss(d, ((uint64_t)a.hi << 32) | (alo + j * a.adv), ((uint64_t)b.hi << 32) | (blo + j * b.adv), idesc, j == 0 ? acc : 1u);
-}
-
-// ---- Fourier features, packed as they are produced (keeps the live set small) ---------------------
-template <int KX, bool INC>
-__device__ __forceinline__ void encode_stream(const float p[3], int L, uint32_t (&pk)[KX / 2]) {
-    constexpr int base = INC ? 3 : 0;
-    float pend = 0.f;
-    auto put = [&](int i, float v) {
-        if (i & 1) pk[i >> 1] = pack_h2(pend, v); else pend = v;
-    };
-    if (INC) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) put(a, p[a]);
-    }
-    float s[3], c[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) sincos_small(p[a], s[a], c[a]);
-    int next = base;
-#pragma unroll
-    for (int k = 0; k < 10; ++k) {
-        if (base + 6 * k + 5 < KX - 1) {
-            const bool on = k < L;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) put(base + 6 * k + a, on ? s[a] : 0.f);
-#pragma unroll
-            for (int a = 0; a < 3; ++a) put(base + 6 * k + 3 + a, on ? c[a] : 0.f);
-            next = base + 6 * k + 6;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const float s2 = s[a] + s[a];
-                const float cn = (c[a] - s[a]) * (c[a] + s[a]);
-                s[a] = s2 * c[a];
-                c[a] = cn;
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < KX; ++i)
-        if (i >= next && i < KX - 1) put(i, 0.f);
-    put(KX - 1, 1.f);          // constant-1 column: bias of the layers that consume the encoding
 }
 
 // ---- drains (thread <-> feature row f; accumulator columns = the 64 samples of the tile) ------------
@@ -514,6 +475,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         long long g_oth_left = n_my[1 - s];
         long long* dbg = (p.debug && blockIdx.x == 0 && (warp & 3) == 0 && lane == 0) ? p.debug + (s ? 768 : 0) : nullptr;
         int dbg_n = 0;
+        if (dbg) dbg[251] = gtimer();
 
         auto drain_g = [&](uint32_t D) {
 #pragma unroll
@@ -576,9 +538,11 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         }
         while (g_oth_left > 0) service();
 #undef T2_SIGNAL
+        if (dbg) dbg[253] = clock64();
         tc_fence_before();
         __syncthreads();                                          // (A)
         tc_fence_after();
+        if (dbg) dbg[254] = clock64();
         // ---- flush this CTA's weight-gradient slab (coalesced: consecutive rows) ----
         auto flush_tmem = [&](int tcol, int ncols, int off) {
             for (int c0 = 0; c0 < ncols; c0 += 16) {
@@ -606,6 +570,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             slab[p.sm.db1 + f] = db1 + xch[4 * 128 + f];
             slab[p.sm.db3 + f] = db3 + xch[5 * 128 + f];
         }
+        if (dbg) { dbg[255] = clock64(); dbg[252] = gtimer(); }
         tc_fence_before();
     }
     __syncthreads();                                              // (C)

@@ -28,9 +28,19 @@ for it in range(3):
     E.check(E.lib().tnerf_set_debug_buffer(h.h, E.ptr(dbg) if it == 2 else None))
     E.check(E.lib().tnerf_render_fwd(h.h, C.byref(rs), n, 2.0, 6.0, S, None, 1, 0, E.ptr(comp), None, None, None, None, E.stream(dev)))
 torch.cuda.synchronize()
-d = [x for x in dbg.cpu().tolist() if x]
-names = ["loop top", "prefetch issued"] + sum([[f"acc{l} ready", f"epi{l} done"] for l in range(4)], []) + ["encode(next) done", "head ready", "composite done"]
+raw = dbg.cpu().tolist()
+d = [x for x in raw[:256] if x]
+names = ["loop top", "next tile encoded (regs)", "xfree + features stored", "head ready", "composite done"]
 t0 = d[0]
-print("WG0 thread 0 (cycles since start, delta):")
-for i, x in enumerate(d[:4 * len(names)]):
-    print(f"  {names[i % len(names)]:20s} {x - t0:8d}  +{(x - d[i - 1]) if i else 0}")
+print("sample warpgroup 0, thread 0 (cycles since start, delta):")
+for i, x in enumerate(d[:6 * len(names)]):
+    print(f"  {names[i % len(names)]:26s} {x - t0:8d}  +{(x - d[i - 1]) if i else 0}")
+
+for name, off in (("epilogue warpgroup 0 (wait begin, wait end)", 256), ("issuer 0 (wait begin, wait end)", 512)):
+    xs = [x for x in raw[off:off + 250] if x]
+    print(name)
+    line = []
+    for i, x in enumerate(xs[20:80]):
+        line.append(f"{x - t0:7d}(+{x - xs[20 + i - 1] if i else 0:5d})")
+        if len(line) == 6:
+            print("  " + " ".join(line)); line = []

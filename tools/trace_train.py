@@ -42,3 +42,9 @@ for name, off in (("drain WG0", 0), ("issuer 0", 256), ("sample warp 0", 512), (
             print("  " + " ".join(line)); line = []
     if line:
         print("  " + " ".join(line))
+
+for name, off in (("drain WG0", 0), ("drain WG1", 768)):
+    print(f"{name}: loop end {d[off + 253] - t0}, all GEMMs done {d[off + 254] - t0}, slab flushed {d[off + 255] - t0}")
+ns = d[252] - d[251]
+cyc = d[255] - d[0]
+print(f"drain WG0 thread 0 lifetime: {cyc} cycles in {ns} ns -> SM clock {cyc / ns * 1e3:.0f} MHz")
