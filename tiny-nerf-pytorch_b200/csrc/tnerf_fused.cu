@@ -454,29 +454,37 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int N, int reps, int 
 // variant >= 8: (variant - 8 + 1) warps issue concurrently, warp-uniform code with one elected lane (the pattern of the
 // two-stream training kernel), A and B from shared memory, one accumulator per warp.  out[2w] = cycles to completion of
 // warp w's MMAs, out[2w+1] = issue-only cycles.
-__global__ void __launch_bounds__(128, 1) umma_rate2_kernel(int N, int reps, int nw, long long* out) {
+template <bool A_TMEM, bool STREAM_B>
+__global__ void __launch_bounds__(256, 1) umma_rate2_kernel(int N, int reps, int nw, int flags, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar[4];
     __shared__ uint32_t slot;
+    __shared__ volatile int stop;
     const int t = threadIdx.x, warp = t >> 5;
-    for (int i = t; i < (128 * 16 + 256 * 16) / 2; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u;
-    if (t == 0) { for (int w = 0; w < 4; ++w) mbar_init(smem_u32(&bar[w]), 1); fence_barrier_init(); }
+    for (int i = t; i < 80 * 1024 / 4; i += 256) reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u;
+    if (t == 0) { for (int w = 0; w < 4; ++w) mbar_init(smem_u32(&bar[w]), 1); fence_barrier_init(); stop = 0; }
     if (warp == 0) { tmem_alloc(smem_u32(&slot), 512); tmem_relinquish(); }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = slot;
+    const bool background = flags & 2;
     if (warp < nw) {
         const uint32_t idesc = make_idesc_f16(128, N, 0, 0);
         const uint32_t sa = smem_u32(smem), sb = sa + 4096;
         const uint32_t alo = ((sa >> 4) & 0x3FFFu) | (128u << 16), blo = ((sb >> 4) & 0x3FFFu) | ((uint32_t)N << 16), hi = 8u | (1u << 14);
-        const uint32_t d = tmem + (N * nw <= 512 ? warp * N : 0);
+        const uint32_t d = tmem + (N * nw <= 256 ? warp * N : 0);
         const long long c0 = clock64();
         for (int i = 0; i < reps; i += 8) {
             if (elect_one()) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) mma_ss(d, ((uint64_t)hi << 32) | alo, ((uint64_t)hi << 32) | blo, idesc, 1);
+                for (int j = 0; j < 8; ++j) {
+                    // STREAM_B: a different 128-row K-step of B every MMA (walks 32 KB of shared memory like a weight matrix)
+                    const uint32_t bj = STREAM_B ? blo + j * (uint32_t)(N * 2) : blo;
+                    if (A_TMEM) mma_ts(d, tmem + 448 + 8 * (j & 3), ((uint64_t)hi << 32) | bj, idesc, 1);
+                    else mma_ss(d, ((uint64_t)hi << 32) | alo, ((uint64_t)hi << 32) | bj, idesc, 1);
+                }
             }
             __syncwarp();
         }
@@ -486,6 +494,19 @@ __global__ void __launch_bounds__(128, 1) umma_rate2_kernel(int N, int reps, int
         mbar_wait(smem_u32(&bar[warp]), 0);
         const long long c2 = clock64();
         if ((t & 31) == 0) { out[2 * warp] = c2 - c0; out[2 * warp + 1] = c1 - c0; }
+        if (warp == 0 && (t & 31) == 0) stop = 1;
+    } else if (warp >= 4 && background) {
+        // epilogue-like tensor-memory traffic on columns the MMAs do not touch: ld 128 columns, st 64 columns, repeat
+        const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256;
+        uint32_t v[32], h[16];
+        for (int i = 0; i < 16; ++i) h[i] = i;
+        while (!stop) {
+            tmem_ld32(tl, v); tmem_ld32(tl + 32, v); tmem_ld32(tl + 64, v); tmem_ld32(tl + 96, v);
+            tc_wait_ld();
+            h[0] = v[0];
+            tmem_st16(tl + 128, h); tmem_st16(tl + 144, h); tmem_st16(tl + 160, h); tmem_st16(tl + 176, h);
+            tc_wait_st();
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -494,9 +515,12 @@ __global__ void __launch_bounds__(128, 1) umma_rate2_kernel(int N, int reps, int
 
 int umma_rate(int n, int reps, int variant, long long* out, cudaStream_t s) {
     if (n < 16 || n > 256 || n % 16 || reps < 8 || reps % 8) { set_error("umma_rate: bad arguments"); return -1; }
-    if (variant >= 8) {
-        if (variant > 11) { set_error("umma_rate: bad variant"); return -1; }
-        umma_rate2_kernel<<<1, 128, 16384, s>>>(n, reps, variant - 7, out);
+    if (variant >= 8) {     // variant = 8 + (warps - 1) + 16 * flags   (flags: 1 = A from tensor memory, 2 = background tcgen05.ld/st traffic)
+        const int nw = ((variant - 8) & 3) + 1, flags = (variant - 8) >> 4;
+        auto kern = (flags & 4) ? ((flags & 1) ? umma_rate2_kernel<true, true> : umma_rate2_kernel<false, true>)
+                                : ((flags & 1) ? umma_rate2_kernel<true, false> : umma_rate2_kernel<false, false>);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+        kern<<<1, 256, 80 * 1024, s>>>(n, reps, nw, flags, out);
     } else
         umma_rate_kernel<<<1, 128, 16384, s>>>(n, reps, variant, out);
     return count_launch();

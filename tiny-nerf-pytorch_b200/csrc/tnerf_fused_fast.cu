@@ -27,6 +27,8 @@ struct FastSmem {
     uint32_t tmem_slot;
 };
 
+#define STAMP() do { if (dbg && dbg_n < 250) dbg[dbg_n++] = clock64(); } while (0)
+
 struct PreIn {          // prefetched inputs of one sample row
     float o[3], d[3], u0, u1;
     long long ray;
@@ -96,13 +98,58 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
             mbar_wait(bar_w, 0);
             uint32_t ph_x = 0, ph_a = 0, ph_hf = 0;
             bool first_head = true;
-            long long* dbg = (p.debug && blockIdx.x == 0 && w == 0 && lane == 0) ? p.debug + 512 : nullptr;
-            int dbg_n = 0;
-#define STAMP() do { if (dbg && dbg_n < 250) dbg[dbg_n++] = clock64(); } while (0)
             const uint32_t wbase = smem_u32(smem);
             const uint32_t tw = tmem + w * FTM_SLOT;
             const uint32_t bar_x = smem_u32(&sm.bar_x[w]), bar_a = smem_u32(&sm.bar_a[w]), bar_acc = smem_u32(&sm.bar_acc[w]),
                            bar_head = smem_u32(&sm.bar_head[w]), bar_xfree = smem_u32(&sm.bar_xfree[w]), bar_hfree = smem_u32(&sm.bar_hfree[w]);
+            // reference MLP (depth 4, skip into layer 2, biases of layers 1/3/heads through the ones chunk): the issue sequence is
+            // spelled out with compile-time step counts; everything the loop needs is a handful of uniform registers.  Reading the
+            // plan with a runtime layer index costs ~600 cycles per layer on this warp's critical path.
+            const bool std_plan = depth == 4 && p.plan.layer[0].nseg == 1 && p.plan.layer[0].seg_steps[0] == KX / 16 &&
+                                  p.plan.layer[1].nseg == 2 && p.plan.layer[1].seg_kind[1] == SEG_ONES &&
+                                  p.plan.layer[2].nseg == 2 && p.plan.layer[2].seg_kind[1] == SEG_X && p.plan.layer[2].seg_steps[1] == KX / 16 &&
+                                  p.plan.layer[3].nseg == 2 && p.plan.layer[3].seg_kind[1] == SEG_ONES &&
+                                  p.plan.layer[4].nseg == 2 && p.plan.layer[4].seg_kind[1] == SEG_ONES;
+            if (std_plan) {
+                constexpr int XS = KX / 16;
+                const uint32_t o0 = p.plan.layer[0].b_off >> 4, o1 = p.plan.layer[1].b_off >> 4, o2 = p.plan.layer[2].b_off >> 4,
+                               o3 = p.plan.layer[3].b_off >> 4, o4 = p.plan.layer[4].b_off >> 4;
+                const uint32_t i128 = make_idesc_f16(128, 128, 0, 0), i16 = make_idesc_f16(128, 16, 0, 0);
+                const uint32_t hi = (128u >> 4) | (1u << 14);
+                const uint32_t tACC = tw + FTM_ACC, tACT = tw + FTM_ACT, tX = tw + FTM_X, tHEAD = tw + FTM_HEAD, tONES = tmem + FTM_ONES;
+#define FF_TS(STEPS, d, a, blo, adv, idesc, accum) do { _Pragma("unroll") for (int j_ = 0; j_ < (STEPS); ++j_) \
+        mma_ts(d, (a) + 8 * j_, ((uint64_t)hi << 32) | ((blo) + j_ * (adv)), idesc, (j_ == 0) ? (accum) : 1u); } while (0)
+                for (long long u = 2LL * blockIdx.x + w; u < p.n_units; u += stride) {
+                    for (int g = 0; g < p.G; ++g) {
+                        uint32_t sb = wbase >> 4;
+                        asm volatile("" : "+r"(sb));          // descriptors are rebuilt per tile (one uniform add each), not kept in registers
+                        const uint32_t b0 = sb + o0 + (128u << 16), b1 = sb + o1 + (128u << 16), b2 = sb + o2 + (128u << 16),
+                                       b3 = sb + o3 + (128u << 16), b4 = sb + o4 + (16u << 16);
+                        mbar_wait(bar_x, ph_x); ph_x ^= 1; tc_fence_after();
+                        if (elect_one()) { FF_TS(XS, tACC, tX, b0, 256u, i128, 0u); tc_commit(bar_acc); }
+                        __syncwarp();
+                        mbar_wait(bar_a, ph_a); ph_a ^= 1; tc_fence_after();
+                        if (elect_one()) { FF_TS(8, tACC, tACT, b1, 256u, i128, 0u); FF_TS(1, tACC, tONES, b1 + 8 * 256u, 256u, i128, 1u); tc_commit(bar_acc); }
+                        __syncwarp();
+                        mbar_wait(bar_a, ph_a); ph_a ^= 1; tc_fence_after();
+                        if (elect_one()) {
+                            FF_TS(8, tACC, tACT, b2, 256u, i128, 0u); FF_TS(XS, tACC, tX, b2 + 8 * 256u, 256u, i128, 1u);
+                            tc_commit(bar_acc); tc_commit(bar_xfree);
+                        }
+                        __syncwarp();
+                        mbar_wait(bar_a, ph_a); ph_a ^= 1; tc_fence_after();
+                        if (elect_one()) { FF_TS(8, tACC, tACT, b3, 256u, i128, 0u); FF_TS(1, tACC, tONES, b3 + 8 * 256u, 256u, i128, 1u); tc_commit(bar_acc); }
+                        __syncwarp();
+                        mbar_wait(bar_a, ph_a); ph_a ^= 1;
+                        if (!first_head) { mbar_wait(bar_hfree, ph_hf); ph_hf ^= 1; }
+                        first_head = false;
+                        tc_fence_after();
+                        if (elect_one()) { FF_TS(8, tHEAD, tACT, b4, 32u, i16, 0u); FF_TS(1, tHEAD, tONES, b4 + 8 * 32u, 32u, i16, 1u); tc_commit(bar_head); }
+                        __syncwarp();
+                    }
+                }
+#undef FF_TS
+            } else
             for (long long u = 2LL * blockIdx.x + w; u < p.n_units; u += stride) {
                 for (int g = 0; g < p.G; ++g) {
                     for (int step = 0; step <= depth; ++step) {
@@ -121,12 +168,10 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
                             seg_a[sgi] = (kind == SEG_ONES) ? tmem + FTM_ONES : tw + (kind == SEG_ACT ? FTM_ACT : FTM_X);
                             seg_n[sgi] = sgi < nseg ? lp.seg_steps[sgi] : 0;
                         }
-                        STAMP();
                         if (step == 0) { mbar_wait(bar_x, ph_x); ph_x ^= 1; }           // features of this tile are in tensor memory
                         else { mbar_wait(bar_a, ph_a); ph_a ^= 1; }                     // previous layer's activations are in tensor memory
                         if (step == depth && !first_head) { mbar_wait(bar_hfree, ph_hf); ph_hf ^= 1; }   // previous head outputs were read
                         tc_fence_after();
-                        STAMP();
                         if (elect_one()) {
                             uint32_t acc = 0;
 #pragma unroll
@@ -145,7 +190,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
         }
     } else if (warp < 8) {
         // ------------------------------ epilogue warpgroup of slot wg ------------------------------
-        TN_SETMAXNREG_DEC(88);
+        TN_SETMAXNREG_INC(112);
         const int wg = warp >> 2, q = warp & 3;
         const uint32_t tw = tmem + wg * FTM_SLOT + ((uint32_t)(q * 32) << 16);
         const uint32_t bar_a = smem_u32(&sm.bar_a[wg]), bar_acc = smem_u32(&sm.bar_acc[wg]);
@@ -179,7 +224,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
         }
     } else {
         // ------------------------------ sample warpgroup of slot wg ------------------------------
-        TN_SETMAXNREG_INC(128);
+        TN_SETMAXNREG_INC(104);
         const int wg = (warp - 8) >> 2, q = warp & 3, row = q * 32 + lane;
         const uint32_t tw = tmem + wg * FTM_SLOT + ((uint32_t)(q * 32) << 16);
         const uint32_t bar_x = smem_u32(&sm.bar_x[wg]), bar_head = smem_u32(&sm.bar_head[wg]), bar_xfree = smem_u32(&sm.bar_xfree[wg]),
@@ -281,28 +326,45 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
 
         uint32_t ph_head = 0, ph_xfree = 0;
         int parity = 0;
+        // Three tiles are in flight on these threads: tile t (running through the layers, composited when its heads arrive),
+        // tile t+1 (features stored to tensor memory as soon as tile t's last reader of the encoding is done) and tile t+2
+        // (rays, depths, features computed into registers while waiting).  Order per iteration: store(t+1), encode(t+2),
+        // composite(t): the encoding work sits in the shadow of tile t's last layers instead of behind its compositing.
+        struct Samp { float z, gd; long long ray; int si; bool valid; };
+        auto next_tile = [&](long long& u_, int& g_) { if (++g_ == p.G) { g_ = 0; u_ += stride; } };
         long long u = 2LL * blockIdx.x + wg;
         int g = 0;
         if (u < p.n_units) {
-            PreIn cur = prefetch(u, g);
-            float z_c, gd_c;
-            encode(cur, z_c, gd_c);
-            store_x();
+            Samp cur, nxt, nn;
+            {
+                const PreIn in = prefetch(u, g);
+                encode(in, cur.z, cur.gd);
+                cur.ray = in.ray; cur.si = in.si; cur.valid = in.valid;
+                store_x();
+            }
+            long long u1 = u; int g1 = g; next_tile(u1, g1);
+            bool has1 = u1 < p.n_units;
+            nxt = cur;
+            if (has1) {
+                const PreIn in = prefetch(u1, g1);
+                encode(in, nxt.z, nxt.gd);
+                nxt.ray = in.ray; nxt.si = in.si; nxt.valid = in.valid;
+            }
             while (true) {
-                long long un = u;
-                int gn = g + 1;
-                if (gn == p.G) { gn = 0; un += stride; }
-                const bool has_next = un < p.n_units;
+                long long u2 = u1; int g2 = g1; next_tile(u2, g2);
+                const bool has2 = has1 && u2 < p.n_units;
                 STAMP();
-                // next tile: inputs, depths and features in registers while this tile runs through the layers
-                PreIn nxt = cur;
-                float z_n = 0.f, gd_n = 0.f;
-                if (has_next) { nxt = prefetch(un, gn); encode(nxt, z_n, gd_n); }
-                STAMP();
-                mbar_wait(bar_xfree, ph_xfree);          // this tile's last reader of the encoding has completed
+                mbar_wait(bar_xfree, ph_xfree);          // tile t's last reader of the encoding has completed
                 ph_xfree ^= 1;
                 tc_fence_after();
-                if (has_next) store_x();
+                if (has1) store_x();                     // features of tile t+1
+                STAMP();
+                nn = nxt;
+                if (has2) {
+                    const PreIn in = prefetch(u2, g2);
+                    encode(in, nn.z, nn.gd);             // features of tile t+2 stay in registers
+                    nn.ray = in.ray; nn.si = in.si; nn.valid = in.valid;
+                }
                 STAMP();
                 mbar_wait(bar_head, ph_head);
                 ph_head ^= 1;
@@ -318,7 +380,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
                 const float cg = __fdividef(1.f, 1.f + __expf(-__uint_as_float(hv[2])));
                 const float cb = __fdividef(1.f, 1.f + __expf(-__uint_as_float(hv[3])));
                 // chunk-local compositing (this warp = 32 consecutive samples of one ray)
-                const float alpha = cur.valid ? 1.f - expf(-sigma * gd_c) : 0.f;
+                const float alpha = cur.valid ? 1.f - expf(-sigma * cur.gd) : 0.f;
                 const float qv = 1.f - alpha + kEpsT;
                 float incl = qv;
 #pragma unroll
@@ -329,7 +391,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
                 float excl = __shfl_up_sync(0xffffffffu, incl, 1);
                 if (lane == 0) excl = 1.f;
                 const float wl = alpha * excl;
-                const float s0 = warp_sum(wl * cr), s1 = warp_sum(wl * cg), s2 = warp_sum(wl * cb), s3 = warp_sum(wl * z_c), s4 = warp_sum(wl);
+                const float s0 = warp_sum(wl * cr), s1 = warp_sum(wl * cg), s2 = warp_sum(wl * cb), s3 = warp_sum(wl * cur.z), s4 = warp_sum(wl);
                 const float P = __shfl_sync(0xffffffffu, incl, 31);
                 const int chunk = g * 4 + q;
                 if (lane == 0) {
@@ -362,8 +424,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
                     parity ^= 1;
                 }
                 STAMP();
-                if (!has_next) break;
-                u = un; g = gn; cur = nxt; z_c = z_n; gd_c = gd_n;
+                if (!has1) break;
+                u = u1; g = g1; u1 = u2; g1 = g2; has1 = has2; cur = nxt; nxt = nn;
             }
         }
     }

@@ -30,17 +30,17 @@ for it in range(3):
 torch.cuda.synchronize()
 raw = dbg.cpu().tolist()
 d = [x for x in raw[:256] if x]
-names = ["loop top", "next tile encoded (regs)", "xfree + features stored", "head ready", "composite done"]
+names = ["loop top", "xfree(t) + features(t+1) stored", "features(t+2) in registers", "heads(t) ready", "composite(t) done"]
 t0 = d[0]
 print("sample warpgroup 0, thread 0 (cycles since start, delta):")
 for i, x in enumerate(d[:6 * len(names)]):
-    print(f"  {names[i % len(names)]:26s} {x - t0:8d}  +{(x - d[i - 1]) if i else 0}")
+    print(f"  {names[i % len(names)]:34s} {x - t0:8d}  +{(x - d[i - 1]) if i else 0}")
 
 for name, off in (("epilogue warpgroup 0 (wait begin, wait end)", 256), ("issuer 0 (wait begin, wait end)", 512)):
     xs = [x for x in raw[off:off + 250] if x]
     print(name)
     line = []
-    for i, x in enumerate(xs[20:80]):
-        line.append(f"{x - t0:7d}(+{x - xs[20 + i - 1] if i else 0:5d})")
+    for i, x in enumerate(xs[0:120]):
+        line.append(f"{x - t0:7d}(+{x - xs[i - 1] if i else 0:5d})")
         if len(line) == 6:
             print("  " + " ".join(line)); line = []
