@@ -98,8 +98,8 @@ __device__ __forceinline__ void encode_point(const float p[3], int L, uint32_t (
 
 
 // ---- Fourier features, packed as they are produced (keeps the live set small) ---------------------
-template <int KX, bool INC>
-__device__ __forceinline__ void encode_stream(const float p[3], int L, uint32_t (&pk)[KX / 2]) {
+template <int KX, bool INC, bool ALL_ON>
+__device__ __forceinline__ void encode_stream_impl(const float p[3], int L, uint32_t (&pk)[KX / 2]) {
     constexpr int base = INC ? 3 : 0;
     float pend = 0.f;
     auto put = [&](int i, float v) {
@@ -116,7 +116,7 @@ __device__ __forceinline__ void encode_stream(const float p[3], int L, uint32_t 
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
         if (base + 6 * k + 5 < KX - 1) {
-            const bool on = k < L;
+            const bool on = ALL_ON || k < L;
 #pragma unroll
             for (int a = 0; a < 3; ++a) put(base + 6 * k + a, on ? s[a] : 0.f);
 #pragma unroll
@@ -136,7 +136,13 @@ __device__ __forceinline__ void encode_stream(const float p[3], int L, uint32_t 
         if (i >= next && i < KX - 1) put(i, 0.f);
     put(KX - 1, 1.f);          // constant-1 column: bias of the layers that consume the encoding
 }
-
+// number of octaves that fit in KX-1 feature columns; when L covers all of them the per-octave on/off selects disappear
+template <int KX, bool INC>
+__device__ __forceinline__ void encode_stream(const float p[3], int L, uint32_t (&pk)[KX / 2]) {
+    constexpr int fit = (KX - 1 - (INC ? 3 : 0)) / 6;
+    if (L >= (fit < 10 ? fit : 10)) encode_stream_impl<KX, INC, true>(p, L, pk);
+    else encode_stream_impl<KX, INC, false>(p, L, pk);
+}
 
 bool build_plan(const tnerf_handle* h, FusedPlan& pl);
 int fused_render_fwd_fast(const FwdParams& p, int grid, cudaStream_t s);   // tnerf_fused_fast.cu (n_samples % 32 == 0)

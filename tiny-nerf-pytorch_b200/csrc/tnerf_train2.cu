@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
 #pragma unroll
         for (int k = 0; k < 12; ++k) cam[k] = camera ? p.rs.c2w[k] : 0.f;
         const float lin_step = (S > 1) ? __fdiv_rn(1.f, (float)(S - 1)) : 0.f;
+        const float inv_focal = camera ? __frcp_rn(p.rs.focal) : 0.f, half_w = (float)p.rs.W * 0.5f, half_h = (float)p.rs.H * 0.5f;
         const float near_ = p.near_, far_ = p.far_;
         auto bin = [&](int k) -> float {      // bit-exact torch.linspace / z formula (src/sampling.py:16-17)
             const float t = (S <= 1) ? 0.f : ((k < S / 2) ? __fmul_rn(lin_step, (float)k) : __fmaf_rn(-lin_step, (float)(S - 1 - k), 1.f));
@@ -303,13 +304,15 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                     const long long k = p.rs.pixel_index ? p.rs.pixel_index[ray] : p.rs.first_ray + ray;
                     const unsigned kk = (unsigned)k, Wd = (unsigned)p.rs.W;
                     const unsigned prow = kk / Wd, pcol = kk - prow * Wd;
-                    const float cx = __fdiv_rn((float)pcol - (float)p.rs.W * 0.5f, p.rs.focal);
-                    const float cy = -__fdiv_rn((float)prow - (float)p.rs.H * 0.5f, p.rs.focal);
+                    // src/rays.py:21-31 with the divisions turned into multiplications by once-computed reciprocals
+                    // (<= 3 ulp on the direction, inside the 1e-6 bar of the stand-alone get_rays kernel)
+                    const float cx = ((float)pcol - half_w) * inv_focal;
+                    const float cy = -((float)prow - half_h) * inv_focal;
                     const float wx = fmaf(-1.f, cam[2], fmaf(cy, cam[1], cx * cam[0]));
                     const float wy = fmaf(-1.f, cam[6], fmaf(cy, cam[5], cx * cam[4]));
                     const float wz = fmaf(-1.f, cam[10], fmaf(cy, cam[9], cx * cam[8]));
-                    const float nrm = fmaxf(sqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx))), 1e-12f);
-                    d[0] = __fdiv_rn(wx, nrm); d[1] = __fdiv_rn(wy, nrm); d[2] = __fdiv_rn(wz, nrm);
+                    const float inv_n = rsqrtf(fmaxf(fmaf(wz, wz, fmaf(wy, wy, wx * wx)), 1e-24f));
+                    d[0] = wx * inv_n; d[1] = wy * inv_n; d[2] = wz * inv_n;
                     o[0] = cam[3]; o[1] = cam[7]; o[2] = cam[11];
                 }
                 float u0 = 0.f, u1 = 0.f;
