@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
                 except Exception:  # noqa: BLE001
                     pass
                 self.running.set()
-                time.sleep(0.0005)
+                time.sleep(0.002)
             else:
                 try:
                     out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits", "-i",

@@ -174,6 +174,18 @@ int tnerf_mse_psnr(const float* pred, const float* target, long long n, float* o
 int tnerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                     int step, float lr, float beta1, float beta2, float eps, float inv_scale,
                     const int* found_inf, void* stream);
+/* (e) multi-GPU exchange step (new work defined by BASELINE config 3; the reference is single-process):
+ * one-shot all-reduce(sum) of the ranks' flat [gradient(n) | loss(1)] vectors over NVLink peer memory fused with the Adam
+ * step above -- what ddp would do with ncclAllReduce + optimizer.step() (src/train.py:126-127 per rank).
+ * peer_grads[r] / peer_flags[r]: HOST arrays of `world` DEVICE pointers, peer-mapped into this process (e.g. CUDA IPC or
+ * torch symmetric memory): rank r's vector of n+1 floats for this epoch and rank r's flag array (>= world uint32, zeroed
+ * once).  epoch: same strictly increasing value (>= 1) on every rank for the same step; vectors must be double-buffered by
+ * epoch parity.  The sum is formed in rank order, so every rank computes bit-identical parameters.  reduced_out (n+1 floats
+ * or NULL) receives the reduced vector.  A peer that never arrives traps after ~3 s instead of hanging the device. */
+int tnerf_allreduce_adam_step(float* params, float* exp_avg, float* exp_avg_sq, long long n,
+                              const float* const* peer_grads, unsigned int* const* peer_flags, int world, int rank,
+                              unsigned int epoch, int step, float lr, float beta1, float beta2, float eps,
+                              float* reduced_out, void* stream);
 /* sets *found_inf (device int) to 1 if any grad is non-finite (device-side GradScaler check) */
 int tnerf_check_finite(const float* grads, long long n, int* found_inf, void* stream);
 

@@ -314,6 +314,16 @@ int tnerf_adam_step(float* params, const float* grads, float* exp_avg, float* ex
     if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || step < 1) return bad("tnerf_adam_step: invalid argument");
     return launch_adam(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, inv_scale, found_inf, (cudaStream_t)stream);
 }
+int tnerf_allreduce_adam_step(float* params, float* exp_avg, float* exp_avg_sq, long long n, const float* const* peer_grads,
+                              unsigned int* const* peer_flags, int world, int rank, unsigned int epoch, int step, float lr,
+                              float beta1, float beta2, float eps, float* reduced_out, void* stream) {
+    if (!params || !exp_avg || !exp_avg_sq || !peer_grads || !peer_flags || n < 0 || step < 1) return bad("tnerf_allreduce_adam_step: invalid argument");
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || epoch == 0) return bad("tnerf_allreduce_adam_step: need 1 <= world <= 8, 0 <= rank < world, epoch >= 1");
+    for (int r = 0; r < world; ++r)
+        if (!peer_grads[r] || !peer_flags[r]) return bad("tnerf_allreduce_adam_step: NULL peer pointer");
+    return launch_allreduce_adam(params, exp_avg, exp_avg_sq, n, peer_grads, peer_flags, world, rank, epoch, step, lr, beta1, beta2, eps,
+                                 reduced_out, (cudaStream_t)stream);
+}
 int tnerf_check_finite(const float* grads, long long n, int* found_inf, void* stream) {
     if (!grads || !found_inf || n < 0) return bad("tnerf_check_finite: invalid argument");
     return launch_check_finite(grads, n, found_inf, (cudaStream_t)stream);

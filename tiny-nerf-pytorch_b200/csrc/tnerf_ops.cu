@@ -356,6 +356,56 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
     p[i] = p[i] - lr_over_bc1 * (mi / denom);
 }
+// (e) ray-sharded data parallel: one-shot all-reduce of the flat [gradient | loss] vectors over NVLink peer memory, fused with
+// the Adam step (replaces ncclAllReduce + adam_kernel).  Every rank runs this kernel on its own GPU.
+//   1. block 0 publishes "my vector for epoch e is complete" into every peer's flag array (release, system scope);
+//   2. every block waits until all ranks have published epoch e (acquire, system scope), bounded spin;
+//   3. thread i sums element i over the ranks IN RANK ORDER (bit-identical result on every rank, so the replicas never
+//      drift), applies Adam to parameter i; element n is the loss.
+// The vectors are double-buffered by the caller (epoch parity): a rank can be at most one step ahead of its peers.
+struct PeerSet { const float* grads[8]; unsigned int* flags[8]; };
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void allreduce_adam_kernel(PeerSet ps, int world, int rank, unsigned int epoch, float* __restrict__ p,
+                                      float* __restrict__ m, float* __restrict__ v, long long n, float lr_over_bc1,
+                                      float inv_sqrt_bc2, float b1, float b2, float eps, float* __restrict__ reduced_out) {
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) timed_out = 0;
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(ps.flags[threadIdx.x] + rank, epoch);
+    }
+    if (threadIdx.x < world) {
+        const unsigned int* mine = ps.flags[rank] + threadIdx.x;
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
+            if (clock64() - t0 > 6000000000LL) { timed_out = 1; break; }   // a peer never arrived (~3 s): fail loudly, do not hang
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (timed_out) { __trap(); }
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i > n) return;
+    float g = 0.f;
+    for (int r = 0; r < world; ++r) g += __ldcv(ps.grads[r] + i);
+    if (reduced_out) reduced_out[i] = g;
+    if (i == n) return;                                             // the loss element
+    const float mi = fmaf(1.f - b1, g - m[i], m[i]);
+    const float vi = fmaf(v[i], b2, (1.f - b2) * g * g);
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] = p[i] - lr_over_bc1 * (mi / denom);
+}
+
 __global__ void check_finite_kernel(const float* __restrict__ g, long long n, int* __restrict__ flag) {
     bool bad = false;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -462,6 +512,17 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, int s
     const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
     adam_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, g, m, v, n, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), b1, b2,
                                                     eps, inv_scale, found_inf);
+    return count_launch();
+}
+int launch_allreduce_adam(float* p, float* m, float* v, long long n, const float* const* peer_grads, unsigned int* const* peer_flags,
+                          int world, int rank, unsigned int epoch, int step, float lr, float b1, float b2, float eps, float* reduced_out,
+                          cudaStream_t s) {
+    if (n <= 0) return 0;
+    PeerSet ps{};
+    for (int r = 0; r < world; ++r) { ps.grads[r] = peer_grads[r]; ps.flags[r] = peer_flags[r]; }
+    const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+    allreduce_adam_kernel<<<blocks_for(n + 1, 256), 256, 0, s>>>(ps, world, rank, epoch, p, m, v, n, (float)((double)lr / bc1),
+                                                                 (float)(1.0 / sqrt(bc2)), b1, b2, eps, reduced_out);
     return count_launch();
 }
 int launch_check_finite(const float* g, long long n, int* flag, cudaStream_t s) {

@@ -29,7 +29,7 @@ constexpr uint32_t S_X0 = 200704, S_X1 = 208896, S_DZH0 = 217088, S_DZH1 = 21913
 
 struct Misc {
     float xch[2][24];          // per stream: cross-warp carries of the compositing scans (one ray spanning two warps)
-    uint64_t bar_w, bar_x[2], bar_in[2], bar_d[2], bar_head[2], bar_dzh[2], bar_g[2][2], bar_gfree[2], bar_xfree[2];
+    uint64_t bar_w, bar_x[2], bar_in[2], bar_d[2], bar_head[2], bar_dzh[2], bar_g[2][2], bar_gfree[2], bar_xfree[2], bar_wg[2], bar_dread[2];
     uint32_t tmem_slot;
 };
 
@@ -114,6 +114,37 @@ __device__ __forceinline__ float drain_bwd(uint32_t D, uint8_t* slot, int f) {
 
 // ---- MMA issuer of stream S (one thread).  S is a template parameter so that every shared-memory offset folds into
 // an immediate: the issuer runs with 40 registers.
+// two-phase variant: the masked, packed dZ row is computed into registers while the wgrad GEMM that still reads the slot
+// (H as its operand) runs; drain_store() writes it once that GEMM has committed.  `dread_bar` (optional) is arrived on as
+// soon as the accumulator has been read, so a GEMM that only needs the accumulator may be issued under the rest of the drain.
+template <bool SUM>
+__device__ __forceinline__ float drain_bwd_compute(uint32_t D, const uint8_t* slot, int f, uint32_t (&o)[32], uint32_t dread_bar) {
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(D + c * 32, v);
+        tc_wait_ld();
+        if (c == 1 && dread_bar) { tc_fence_before(); mbar_arrive(dread_bar); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 h = *reinterpret_cast<const uint4*>(slot + ((size_t)((c * 4 + j) * 128 + f) << 4));
+            uint32_t* oo = &o[(c * 4 + j) * 4];
+            oo[0] = pack_sat_h2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])) & relu_mask(h.x);
+            oo[1] = pack_sat_h2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])) & relu_mask(h.y);
+            oo[2] = pack_sat_h2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])) & relu_mask(h.z);
+            oo[3] = pack_sat_h2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])) & relu_mask(h.w);
+            if (SUM) sum += (h2sum(oo[0]) + h2sum(oo[1])) + (h2sum(oo[2]) + h2sum(oo[3]));
+        }
+    }
+    return sum;
+}
+__device__ __forceinline__ void drain_store(uint8_t* slot, int f, const uint32_t (&o)[32]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(slot + ((size_t)(c * 128 + f) << 4)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+}
+
 template <int KX, int S>
 __device__ __forceinline__ void issuer_loop(Misc& ms, uint32_t sbase, uint32_t tmem, long long n_tiles_mine, long long* dbg) {
     int dbg_n = 0;
@@ -122,12 +153,13 @@ __device__ __forceinline__ void issuer_loop(Misc& ms, uint32_t sbase, uint32_t t
     const uint32_t bar_x = smem_u32(&ms.bar_x[s]), bar_in = smem_u32(&ms.bar_in[s]), bar_d = smem_u32(&ms.bar_d[s]);
     const uint32_t bar_head = smem_u32(&ms.bar_head[s]), bar_dzh = smem_u32(&ms.bar_dzh[s]), bar_gfree = smem_u32(&ms.bar_gfree[s]);
     const uint32_t bar_g0 = smem_u32(&ms.bar_g[s][0]), bar_g1 = smem_u32(&ms.bar_g[s][1]), bar_xfree = smem_u32(&ms.bar_xfree[s]);
+    const uint32_t bar_wg = smem_u32(&ms.bar_wg[s]), bar_dread = smem_u32(&ms.bar_dread[s]);
     const uint32_t P = s ? S_P1 : S_P0, Q = s ? S_Q1 : S_Q0, X = s ? S_X1 : S_X0, DZH = s ? S_DZH1 : S_DZH0;   // byte offsets
     const uint32_t D = tmem + C_D + 64 * s;
     const uint32_t i64kk = make_idesc_f16(128, 64, 0, 0), i64kt = make_idesc_f16(128, 64, 0, 1), i64tk = make_idesc_f16(128, 64, 1, 0),
                    i64tt = make_idesc_f16(128, 64, 1, 1), i16tk = make_idesc_f16(128, 16, 1, 0), i16kt = make_idesc_f16(128, 16, 0, 1),
                    i128kk = make_idesc_f16(128, 128, 0, 0), iXkt = make_idesc_f16(128, KX, 0, 1);
-    uint32_t ph_x = 0, ph_in = 0, ph_dzh = 0, ph_gf = 0;
+    uint32_t ph_x = 0, ph_in = 0, ph_dzh = 0, ph_gf = 0, ph_dr = 0;
 #define T2_WAIT(bar, ph) do { T2_STAMP(); mbar_wait(bar, ph); ph ^= 1; tc_fence_after(); T2_STAMP(); } while (0)
     // the whole warp runs this loop with warp-uniform values; one elected lane issues (operands stay in uniform registers)
 #define T2_ISSUE(...) do { if (elect_one()) { __VA_ARGS__ } __syncwarp(); } while (0)
@@ -165,14 +197,17 @@ __device__ __forceinline__ void issuer_loop(Misc& ms, uint32_t sbase, uint32_t t
         T2_WAIT(bar_in, ph_in);
         T2_ISSUE(gemm<1>(D, aWHt, bDZHk, i64tk, 0); tc_commit(bar_d););                                 // head dgrad -> dH3
         T2_WAIT(bar_in, ph_in);
-        T2_ISSUE(gemm<4>(tmem + C_DW3, aQ, aP, i128kk, 1);                                              // dW3 += dZ3 . H2^T
-                 gemm<8>(D, aW3t, bQ, i64tt, 0); tc_commit(bar_d););                                    // dH2
+        // layers 3 and 2: dgrad first on its own barrier, the wgrad GEMMs behind it -- the drain threads turn dH into the
+        // packed dZ row while the wgrad still reads the slot, and store once the wgrad has committed
+        T2_ISSUE(gemm<8>(D, aW3t, bQ, i64tt, 0); tc_commit(bar_d);                                      // dH2
+                 gemm<4>(tmem + C_DW3, aQ, aP, i128kk, 1); tc_commit(bar_wg););                         // dW3 += dZ3 . H2^T
         T2_WAIT(bar_in, ph_in);
-        T2_ISSUE(gemm<4>(tmem + C_DW2, aP, aQ, i128kk, 1);                                              // dW2[:, :128] += dZ2 . H1^T
-                 gemm<4>(tmem + C_DW2 + 128, aP, bXt, iXkt, 1);                                         // dW2[:, 128:] += dZ2 . X^T
-                 gemm<8>(D, aW2t, bP, i64tt, 0); tc_commit(bar_d););                                    // dH1
-        T2_WAIT(bar_in, ph_in);
-        T2_ISSUE(gemm<XS>(D, aW0, bXk, i64kk, 0); tc_commit(bar_d););                                   // recompute H0
+        T2_ISSUE(gemm<8>(D, aW2t, bP, i64tt, 0); tc_commit(bar_d);                                      // dH1
+                 gemm<4>(tmem + C_DW2, aP, aQ, i128kk, 1);                                              // dW2[:, :128] += dZ2 . H1^T
+                 gemm<4>(tmem + C_DW2 + 128, aP, bXt, iXkt, 1); tc_commit(bar_wg););                    // dW2[:, 128:] += dZ2 . X^T
+        T2_WAIT(bar_dread, ph_dr);                                                                      // dH1 has been read out
+        T2_ISSUE(gemm<XS>(D, aW0, bXk, i64kk, 0); tc_commit(bar_d););                                   // recompute H0 under the dZ1 drain
+        T2_WAIT(bar_in, ph_in);                                                                         // dZ1 stored
         T2_WAIT(bar_in, ph_in);
         T2_ISSUE(gemm<4>(D, aQ, bP_lo, i64kk, 0); tc_commit(bar_g0););                                  // dW1[:, :64] partial
         T2_WAIT(bar_gfree, ph_gf);
@@ -205,6 +240,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             mbar_init(smem_u32(&ms.bar_g[s][1]), 1);
             mbar_init(smem_u32(&ms.bar_gfree[s]), 128);
             mbar_init(smem_u32(&ms.bar_xfree[s]), 1);
+            mbar_init(smem_u32(&ms.bar_wg[s]), 1);
+            mbar_init(smem_u32(&ms.bar_dread[s]), 128);
         }
         fence_barrier_init();
     }
@@ -463,7 +500,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         const uint32_t D_own = tl + C_D + 64 * s, D_oth = tl + C_D + 64 * (1 - s);
         uint8_t* P = smem + (s ? S_P1 : S_P0);
         uint8_t* Q = smem + (s ? S_Q1 : S_Q0);
-        const uint32_t bar_in = smem_u32(&ms.bar_in[s]), bar_d = smem_u32(&ms.bar_d[s]);
+        const uint32_t bar_in = smem_u32(&ms.bar_in[s]), bar_d = smem_u32(&ms.bar_d[s]), bar_wg = smem_u32(&ms.bar_wg[s]), bar_dread = smem_u32(&ms.bar_dread[s]);
         const uint32_t bar_g_own = smem_u32(&ms.bar_g[s][s]), bar_g_oth = smem_u32(&ms.bar_g[1 - s][s]);
         const uint32_t bar_gfree_own = smem_u32(&ms.bar_gfree[s]), bar_gfree_oth = smem_u32(&ms.bar_gfree[1 - s]);
         float dw1[64];                  // dW1[f][64 s + j]: this warpgroup's half of the columns, BOTH streams
@@ -474,21 +511,23 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         for (int j = 0; j < 32; ++j) stash[j] = 0u;
         float dwh[4] = {0.f, 0.f, 0.f, 0.f}, db1 = 0.f, db3 = 0.f;
         const float b1 = p.b1[f], b3 = p.b3[f];
-        uint32_t ph_d = 0, ph_g_own = 0, ph_g_oth = 0;
+        uint32_t ph_d = 0, ph_g_own = 0, ph_g_oth = 0, ph_wg = 0;
         long long g_oth_left = n_my[1 - s];
         long long* dbg = (p.debug && blockIdx.x == 0 && (warp & 3) == 0 && lane == 0) ? p.debug + (s ? 768 : 0) : nullptr;
         int dbg_n = 0;
         if (dbg) dbg[251] = gtimer();
 
-        auto drain_g = [&](uint32_t D) {
+        auto drain_g = [&](uint32_t D, uint32_t free_bar) {     // the accumulator is released as soon as it has been read
+            uint32_t v[2][32];
+            tmem_ld32(D, v[0]);
+            tmem_ld32(D + 32, v[1]);
+            tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(free_bar);
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                tmem_ld32(D + c * 32, v);
-                tc_wait_ld();
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) dw1[c * 32 + j] += __uint_as_float(v[j]);
-            }
+                for (int j = 0; j < 32; ++j) dw1[c * 32 + j] += __uint_as_float(v[c][j]);
         };
         // The other stream's dW1 half is drained at a fixed point of this stream's tile: right after the layer-3 drain, where
         // this warpgroup would otherwise sleep through its own compositing.  The rendezvous keeps the two streams about
@@ -498,9 +537,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             mbar_wait(bar_g_oth, ph_g_oth);
             tc_fence_after();
             T2_STAMP();
-            drain_g(D_oth);
-            tc_fence_before();
-            mbar_arrive(bar_gfree_oth);
+            drain_g(D_oth, bar_gfree_oth);
             ph_g_oth ^= 1;
             --g_oth_left;
         };
@@ -529,14 +566,20 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             }
             T2_SIGNAL();
             wait_poll(bar_d, ph_d); db3 += drain_bwd<true>(D_own, Q, f); T2_SIGNAL();            // dZ3 over H3 (Q)
-            wait_poll(bar_d, ph_d); drain_bwd<false>(D_own, P, f);                               // dZ2 over H2 (P)
-#pragma unroll
-            for (int c = 0; c < 8; ++c)                                                          // H1 back into Q (dZ3 is dead)
-                *reinterpret_cast<uint4*>(Q + ((size_t)(c * 128 + f) << 4)) = make_uint4(stash[4 * c], stash[4 * c + 1], stash[4 * c + 2], stash[4 * c + 3]);
-            T2_SIGNAL();
-            wait_poll(bar_d, ph_d); db1 += drain_bwd<true>(D_own, Q, f); T2_SIGNAL();            // dZ1 over H1 (Q)
+            {
+                uint32_t o[32];
+                wait_poll(bar_d, ph_d); drain_bwd_compute<false>(D_own, P, f, o, 0u);                // dZ2 = dH2 * (H2 > 0), in registers
+                wait_poll(bar_wg, ph_wg);                                                            // dW3 GEMM no longer reads H2 / dZ3
+                drain_store(P, f, o);                                                                // dZ2 over H2 (P)
+                drain_store(Q, f, stash);                                                            // H1 back into Q (dZ3 is dead)
+                T2_SIGNAL();
+                wait_poll(bar_d, ph_d); db1 += drain_bwd_compute<true>(D_own, Q, f, o, bar_dread);   // dZ1 = dH1 * (H1 > 0)
+                wait_poll(bar_wg, ph_wg);                                                            // dW2 GEMMs no longer read H1 / dZ2
+                drain_store(Q, f, o);                                                                // dZ1 over H1 (Q)
+                T2_SIGNAL();
+            }
             wait_poll(bar_d, ph_d); drain_fwd<false>(D_own, P, f, 0.f, stash); T2_SIGNAL();      // H0 -> P (dZ2 is dead)
-            wait_poll(bar_g_own, ph_g_own); drain_g(D_own); tc_fence_before(); mbar_arrive(bar_gfree_own);
+            wait_poll(bar_g_own, ph_g_own); drain_g(D_own, bar_gfree_own);
             wait_poll(bar_d, ph_d); drain_bwd<false>(D_own, P, f); T2_SIGNAL();                  // dZ0 over H0 (P)
         }
         while (g_oth_left > 0) service();

@@ -150,7 +150,7 @@ class Trainer:
     format, so checkpoints interchange with the reference (src/train.py:85-92,142-156)."""
 
     def __init__(self, model, encoder, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, near=2.0, far=6.0, n_samples=64,
-                 white_bkgd=True, precision: Optional[str] = None, process_group=None):
+                 white_bkgd=True, precision: Optional[str] = None, process_group=None, comm: Optional[str] = None):
         self.model, self.encoder = model, encoder
         ps = model._params()
         dev = E.need_cuda(*ps)
@@ -180,25 +180,70 @@ class Trainer:
         self.h.bind()
         if self.prec == E.PREC_F16_TC:
             self.h.ensure_packed(force=True)
+        # gradient exchange of ray-sharded data parallel: "p2p" = one kernel that all-reduces over NVLink peer memory and
+        # applies Adam (tnerf_allreduce_adam_step); "nccl" = torch.distributed.all_reduce + tnerf_adam_step
+        self.comm = "none"
+        if self.world > 1:
+            want = comm or os.environ.get("TNERF_COMM", "p2p")
+            self.comm = "nccl"
+            if want == "p2p":
+                try:
+                    self._setup_p2p()
+                    self.comm = "p2p"
+                except Exception as e:  # noqa: BLE001  (no peer access / symmetric memory unavailable: NCCL does the exchange)
+                    if comm == "p2p":
+                        raise
+                    print(f"[tnerf] peer-memory gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL", flush=True)
+
+    def _setup_p2p(self):
+        """symmetric [grad | loss] buffers (double-buffered by step parity) + arrival flags, mapped into every rank"""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.pg if self.pg is not None else dist.group.WORLD
+        self.rank = dist.get_rank(group)
+        stride = (self.P + 1 + 63) // 64 * 64
+        self._sym_stride = stride
+        self.sym = symm_mem.empty(2 * stride + 64, dtype=torch.float32, device=self.device)
+        self.sym.zero_()
+        hdl = symm_mem.rendezvous(self.sym, group)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)
+        self._symh = hdl
+        bases = [int(p) for p in hdl.buffer_ptrs]
+        VP = C.c_void_p * self.world
+        self._peer_grads = [VP(*[b + 4 * k * stride for b in bases]) for k in range(2)]
+        self._peer_flags = VP(*[b + 4 * 2 * stride for b in bases])
+        self._gviews = [self.sym[k * stride:k * stride + self.P + 1] for k in range(2)]
+        self.reduced = torch.zeros(self.P + 1, dtype=torch.float32, device=self.device)
 
     # ---- one optimisation step ------------------------------------------------------------------
     def _finish(self):
-        if self.world > 1:
-            torch.distributed.all_reduce(self.gbuf, group=self.pg)
         self.steps += 1
         st = E.stream(self.device)
-        E.check(E.lib().tnerf_adam_step(E.ptr(self.flat), E.ptr(self.gbuf), E.ptr(self.exp_avg), E.ptr(self.exp_avg_sq), self.P,
-                                        self.steps, self.lr, self.betas[0], self.betas[1], self.eps, 1.0, None, st), "tnerf_adam_step")
+        if self.comm == "p2p":
+            k = self.steps & 1
+            E.check(E.lib().tnerf_allreduce_adam_step(E.ptr(self.flat), E.ptr(self.exp_avg), E.ptr(self.exp_avg_sq), self.P,
+                                                      self._peer_grads[k], self._peer_flags, self.world, self.rank, self.steps, self.steps,
+                                                      self.lr, self.betas[0], self.betas[1], self.eps, E.ptr(self.reduced), st),
+                    "tnerf_allreduce_adam_step")
+            loss = self.reduced[self.P:]
+        else:
+            if self.world > 1:
+                torch.distributed.all_reduce(self.gbuf, group=self.pg)
+            E.check(E.lib().tnerf_adam_step(E.ptr(self.flat), E.ptr(self.gbuf), E.ptr(self.exp_avg), E.ptr(self.exp_avg_sq), self.P,
+                                            self.steps, self.lr, self.betas[0], self.betas[1], self.eps, 1.0, None, st), "tnerf_adam_step")
+            loss = self.loss_view
         if self.prec == E.PREC_F16_TC:
             self.h.ensure_packed(force=True)
-        return self.loss_view
+        return loss
 
     def _launch(self, rs, target, n, jitter, global_rays):
         st = E.stream(self.device)
-        self.gbuf.zero_()
+        gbuf = self._gviews[(self.steps + 1) & 1] if self.comm == "p2p" else self.gbuf      # [gradient | loss] of this step
+        gbuf.zero_()
         denom = 3.0 * float(global_rays if global_rays else n * self.world)
         E.check(E.lib().tnerf_train_fwd_bwd(self.h.h, C.byref(rs), E.ptr(target), n, self.near, self.far, self.S, E.ptr(jitter),
-                                            int(self.white), self.prec, denom, None, E.ptr(self.loss_view), E.ptr(self.gbuf), st),
+                                            int(self.white), self.prec, denom, None, E.ptr(gbuf[self.P:]), E.ptr(gbuf), st),
                 "tnerf_train_fwd_bwd")
         return self._finish()
 
