@@ -5,8 +5,9 @@ process).  Launch one process per GPU:
 
 Every rank holds the full MLP (265 KB), draws its own disjoint pixel / jitter streams, runs the fused
 fwd+bwd kernel on its n_rand rays with the loss normalised by the GLOBAL ray count, and the flat
-gradient (+loss) is summed with ONE NCCL all-reduce; the identical fused Adam step then runs on every
-rank, so parameters never need a broadcast.
+gradient (+loss) is summed AND the Adam step applied by ONE kernel over NVLink peer memory
+(tnerf_allreduce_adam_step; TNERF_COMM=nccl selects all_reduce + tnerf_adam_step).  The sum is formed in
+rank order, so every rank computes bit-identical parameters and they never need a broadcast.
 """
 import os
 from dataclasses import dataclass
