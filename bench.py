@@ -349,6 +349,7 @@ def main():
         g1.record()
         torch.cuda.synchronize()
         kernels_per_call = (E.launch_count() - lk0) / reps
+        tr.gbuf.zero_()
         ms_kernel = g0.elapsed_time(g1) / reps
         units_per_step = rays * S
         flop = FLOP_FWD_BWD

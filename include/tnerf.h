@@ -174,21 +174,34 @@ int tnerf_mse_psnr(const float* pred, const float* target, long long n, float* o
 int tnerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                     int step, float lr, float beta1, float beta2, float eps, float inv_scale,
                     const int* found_inf, void* stream);
+/* a9 + (f) N1: the optimiser step of the training loop as ONE launch: Adam as above (inv_scale = 1) on the flat parameter
+ * vector, the gradient vector cleared for the next step (grads[0 .. n_clear), n_clear >= n so a trailing loss slot is cleared
+ * too; their old values go to tail_out if non-NULL) and -- repack != 0 -- the fp16 operand image of the tensor-core kernels refreshed in place (replaces memset +
+ * tnerf_adam_step + tnerf_pack_weights; needs the handle's parameters bound as views of `params` in state_dict order). */
+int tnerf_optimizer_step(tnerf_handle* h, float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                         long long n_clear, int step, float lr, float beta1, float beta2, float eps, float* tail_out, int repack,
+                         void* stream);
+
 /* (e) multi-GPU exchange step (new work defined by BASELINE config 3; the reference is single-process):
- * one-shot all-reduce(sum) of the ranks' flat [gradient(n) | loss(1)] vectors over NVLink peer memory fused with the Adam
- * step above -- what ddp would do with ncclAllReduce + optimizer.step() (src/train.py:126-127 per rank).
+ * one-shot all-reduce(sum) of the ranks' flat [gradient(n) | loss(1)] vectors over NVLink peer memory fused with the
+ * optimiser step above -- what DDP would do with ncclAllReduce + optimizer.step() (src/train.py:126-127 per rank).
  * peer_grads[r] / peer_flags[r]: HOST arrays of `world` DEVICE pointers, peer-mapped into this process (e.g. CUDA IPC or
  * torch symmetric memory): rank r's vector of n+1 floats for this epoch and rank r's flag array (>= world uint32, zeroed
  * once).  epoch: same strictly increasing value (>= 1) on every rank for the same step; vectors must be double-buffered by
  * epoch parity.  The sum is formed in rank order, so every rank computes bit-identical parameters.  reduced_out (n+1 floats
- * or NULL) receives the reduced vector.  A peer that never arrives traps after ~3 s instead of hanging the device. */
-int tnerf_allreduce_adam_step(float* params, float* exp_avg, float* exp_avg_sq, long long n,
+ * or NULL) receives the reduced vector; zero_next (n+1 floats or NULL) = this rank's OTHER-parity vector, cleared here for
+ * the next step; repack as in tnerf_optimizer_step (h may be NULL when 0).  A peer that never arrives traps after ~3 s
+ * instead of hanging the device. */
+int tnerf_allreduce_adam_step(tnerf_handle* h, float* params, float* exp_avg, float* exp_avg_sq, long long n,
                               const float* const* peer_grads, unsigned int* const* peer_flags, int world, int rank,
                               unsigned int epoch, int step, float lr, float beta1, float beta2, float eps,
-                              float* reduced_out, void* stream);
+                              float* reduced_out, float* zero_next, int repack, void* stream);
 /* sets *found_inf (device int) to 1 if any grad is non-finite (device-side GradScaler check) */
 int tnerf_check_finite(const float* grads, long long n, int* found_inf, void* stream);
 
+/* test hook: size in bytes of the packed fp16 operand image (negative on error); if dst is non-NULL the image is also copied
+ * there (device to device) -- used to check the optimiser's in-place refresh against a full tnerf_pack_weights */
+long long tnerf_packed_image_copy(const tnerf_handle* h, void* dst, long long dst_bytes, void* stream);
 /* test hook: D(128xN) = A(128xK) * B(NxK)^T through the same tcgen05 descriptors the fused
  * kernels use.  mode 0: A from shared memory, 1: A from tensor memory, 2: B MN-major. */
 /* developer probe: cycles for `reps` back-to-back 128 x n x 16 MMAs (out2[0] = to completion, out2[1] = issue only) */

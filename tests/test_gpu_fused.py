@@ -226,3 +226,35 @@ def test_trainer_steps_match_oracle_adam(dev):
     assert sorted(sd["state"].keys()) == list(range(12)) and float(sd["state"][0]["step"]) == 3.0
     opt = torch.optim.Adam(model.parameters(), lr=5e-4)
     opt.load_state_dict(sd)                                    # interchangeable with torch.optim.Adam (checkpoints)
+
+
+def test_optimizer_step_refreshes_operand_image_like_a_full_repack(dev):
+    """tnerf_optimizer_step (Adam + clear gradient vector + in-place fp16 image refresh, one launch) against
+    tnerf_adam_step followed by tnerf_pack_weights: same parameters, same moments, byte-identical image, cleared gradients."""
+    import _engine as E
+    import engine
+    from encoding import PositionalEncoding
+    for cfg, L in (((63, 128, 4, 2), 10), ((39, 128, 4, 2), 6)):
+        enc = PositionalEncoding(L, True).to(dev)
+        model, _ = make_model(cfg, 71, dev, 1.5)
+        tr = engine.Trainer(model, enc, n_samples=64)
+        P = tr.P
+        g = torch.Generator().manual_seed(72)
+        grads = (torch.randn(P + 1, generator=g) * 1e-2).to(dev)
+        ref_p, ref_m, ref_v = tr.flat.clone(), tr.exp_avg.clone(), tr.exp_avg_sq.clone()
+        nbytes = E.lib().tnerf_packed_image_copy(tr.h.h, None, 0, None)
+        assert nbytes > 0
+        img_a, img_b = torch.zeros(nbytes, dtype=torch.uint8, device=dev), torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        for step in (1, 2, 3):
+            E.check(E.lib().tnerf_adam_step(E.ptr(ref_p), E.ptr(grads), E.ptr(ref_m), E.ptr(ref_v), P, step, 5e-4, 0.9, 0.999, 1e-8, 1.0, None,
+                                            E.stream(dev)))
+            tr.gbuf.copy_(grads)
+            tr.steps = step - 1
+            loss = tr._finish()
+            assert torch.equal(tr.flat, ref_p) and torch.equal(tr.exp_avg, ref_m) and torch.equal(tr.exp_avg_sq, ref_v)
+            assert float(tr.gbuf.abs().max()) == 0.0 and float(loss) == float(grads[P])
+            assert E.lib().tnerf_packed_image_copy(tr.h.h, E.ptr(img_a), nbytes, E.stream(dev)) == nbytes
+            tr.h.ensure_packed(force=True)                         # full re-pack from the fp32 parameters
+            assert E.lib().tnerf_packed_image_copy(tr.h.h, E.ptr(img_b), nbytes, E.stream(dev)) == nbytes
+            torch.cuda.synchronize()
+            assert torch.equal(img_a, img_b), int((img_a != img_b).sum())

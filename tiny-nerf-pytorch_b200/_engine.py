@@ -59,7 +59,9 @@ _SIGS = {
     "tnerf_mse_psnr": (_i, [_p, _p, _ll, _p, _p]),
     "tnerf_adam_step": (_i, [_p, _p, _p, _p, _ll, _i, _f, _f, _f, _f, _f, _p, _p]),
     "tnerf_check_finite": (_i, [_p, _ll, _p, _p]),
-    "tnerf_allreduce_adam_step": (_i, [_p, _p, _p, _ll, _p, _p, _i, _i, C.c_uint, _i, _f, _f, _f, _f, _p, _p]),
+    "tnerf_packed_image_copy": (_ll, [_p, _p, _ll, _p]),
+    "tnerf_optimizer_step": (_i, [_p, _p, _p, _p, _p, _ll, _ll, _i, _f, _f, _f, _f, _p, _i, _p]),
+    "tnerf_allreduce_adam_step": (_i, [_p, _p, _p, _p, _ll, _p, _p, _i, _i, C.c_uint, _i, _f, _f, _f, _f, _p, _p, _i, _p]),
     "tnerf_umma_rate": (_i, [_i, _i, _i, _p, _p]),
     "tnerf_umma_selftest": (_i, [_p, _p, _i, _i, _i, _p, _p]),
 }

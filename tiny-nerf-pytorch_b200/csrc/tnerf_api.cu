@@ -1,7 +1,7 @@
 // C ABI of libtnerf.so (declared in include/tnerf.h).  Argument checking, the handle, and the fp32
 // composition of the fused entry points out of the stand-alone kernels (TNERF_PREC_F32_SIMT).
 #include "../../include/tnerf.h"
-#include "tnerf_internal.cuh"
+#include "tnerf_fused.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -314,15 +314,47 @@ int tnerf_adam_step(float* params, const float* grads, float* exp_avg, float* ex
     if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || step < 1) return bad("tnerf_adam_step: invalid argument");
     return launch_adam(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, inv_scale, found_inf, (cudaStream_t)stream);
 }
-int tnerf_allreduce_adam_step(float* params, float* exp_avg, float* exp_avg_sq, long long n, const float* const* peer_grads,
+long long tnerf_packed_image_copy(const tnerf_handle* h, void* dst, long long dst_bytes, void* stream) {
+    if (!h || !h->packed) { set_error("tnerf_packed_image_copy: no packed image"); return -1; }
+    FusedPlan pl;
+    if (!build_plan(h, pl)) { set_error("tnerf_packed_image_copy: unsupported shape"); return -2; }
+    if (dst) {
+        if (dst_bytes < (long long)pl.image_bytes) { set_error("tnerf_packed_image_copy: destination too small"); return -3; }
+        cudaMemcpyAsync(dst, h->packed, pl.image_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    }
+    return (long long)pl.image_bytes;
+}
+// the flat vector must be the handle's bound parameters laid out back to back (state_dict order) for the image refresh
+static bool params_are_flat(const tnerf_handle* h, const float* flat) {
+    if (!h || h->params.empty()) return false;
+    for (int t = 0; t < h->n_params; ++t)
+        if (h->params[t] != flat + h->offsets[t]) return false;
+    return true;
+}
+int tnerf_optimizer_step(tnerf_handle* h, float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                         long long n_clear, int step, float lr, float beta1, float beta2, float eps, float* tail_out, int repack, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || n_clear < n || step < 1) return bad("tnerf_optimizer_step: invalid argument");
+    RepackMap mp{};
+    if (repack) {
+        if (!params_are_flat(h, params) || n != h->param_count) return bad("tnerf_optimizer_step: repack needs the handle's parameters bound as one flat vector");
+        if (!build_repack_map(h, mp)) return bad("tnerf_optimizer_step: no packed image to refresh (call tnerf_pack_weights once first)");
+    }
+    return launch_adam_fused(params, grads, exp_avg, exp_avg_sq, n, n_clear, step, lr, beta1, beta2, eps, tail_out, mp, (cudaStream_t)stream);
+}
+int tnerf_allreduce_adam_step(tnerf_handle* h, float* params, float* exp_avg, float* exp_avg_sq, long long n, const float* const* peer_grads,
                               unsigned int* const* peer_flags, int world, int rank, unsigned int epoch, int step, float lr,
-                              float beta1, float beta2, float eps, float* reduced_out, void* stream) {
+                              float beta1, float beta2, float eps, float* reduced_out, float* zero_next, int repack, void* stream) {
     if (!params || !exp_avg || !exp_avg_sq || !peer_grads || !peer_flags || n < 0 || step < 1) return bad("tnerf_allreduce_adam_step: invalid argument");
     if (world < 1 || world > 8 || rank < 0 || rank >= world || epoch == 0) return bad("tnerf_allreduce_adam_step: need 1 <= world <= 8, 0 <= rank < world, epoch >= 1");
     for (int r = 0; r < world; ++r)
         if (!peer_grads[r] || !peer_flags[r]) return bad("tnerf_allreduce_adam_step: NULL peer pointer");
+    RepackMap mp{};
+    if (repack) {
+        if (!params_are_flat(h, params) || n != h->param_count) return bad("tnerf_allreduce_adam_step: repack needs the handle's parameters bound as one flat vector");
+        if (!build_repack_map(h, mp)) return bad("tnerf_allreduce_adam_step: no packed image to refresh (call tnerf_pack_weights once first)");
+    }
     return launch_allreduce_adam(params, exp_avg, exp_avg_sq, n, peer_grads, peer_flags, world, rank, epoch, step, lr, beta1, beta2, eps,
-                                 reduced_out, (cudaStream_t)stream);
+                                 reduced_out, zero_next, mp, (cudaStream_t)stream);
 }
 int tnerf_check_finite(const float* grads, long long n, int* found_inf, void* stream) {
     if (!grads || !found_inf || n < 0) return bad("tnerf_check_finite: invalid argument");

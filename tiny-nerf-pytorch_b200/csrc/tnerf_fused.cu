@@ -565,6 +565,35 @@ bool build_plan(const tnerf_handle* h, FusedPlan& pl) {
     return true;
 }
 
+bool build_repack_map(const tnerf_handle* h, RepackMap& mp) {
+    FusedPlan pl;
+    mp = RepackMap{};
+    if (!build_plan(h, pl) || !h->packed) return false;
+    mp.n_tensors = h->n_params; mp.H = h->hidden; mp.image = reinterpret_cast<__half*>(h->packed);
+    for (int t = 0; t < h->n_params; ++t) mp.off[t] = h->offsets[t];
+    mp.off[h->n_params] = h->param_count;
+    for (int l = 0; l <= h->depth; ++l) {
+        const LayerPlan& lp = pl.layer[l];
+        mp.N[l] = lp.N; mp.img_off[l] = lp.b_off / 2; mp.fan[l] = l < h->depth ? h->layer_in[l] : h->hidden;
+        int k0 = 0;
+        mp.act_len[l] = 0; mp.xstart[l] = 0; mp.bias_k[l] = -1;
+        for (int sgi = 0; sgi < lp.nseg; ++sgi) {
+            const int kind = lp.seg_kind[sgi], len = lp.seg_steps[sgi] * 16;
+            if (kind == SEG_ACT) mp.act_len[l] = h->hidden;
+            else if (kind == SEG_X) { mp.xstart[l] = k0; if (pl.bias_in_x) { mp.bias_k[l] = k0 + pl.Kx - 1; mp.bias_hilo[l] = 0; } }
+            else { mp.bias_k[l] = k0; mp.bias_hilo[l] = 1; }
+            k0 += len;
+        }
+        if (mp.bias_k[l] < 0) return false;
+    }
+    for (int l = 0; l < h->depth; ++l) { mp.kind[2 * l] = RP_W_HID; mp.layer[2 * l] = (uint8_t)l; mp.kind[2 * l + 1] = RP_B_HID; mp.layer[2 * l + 1] = (uint8_t)l; }
+    const int d = h->depth;
+    mp.kind[2 * d] = RP_W_SIG; mp.kind[2 * d + 1] = RP_B_SIG; mp.kind[2 * d + 2] = RP_W_RGB; mp.kind[2 * d + 3] = RP_B_RGB;
+    for (int t = 2 * d; t < 2 * d + 4; ++t) mp.layer[t] = (uint8_t)d;
+    mp.valid = 1;
+    return true;
+}
+
 bool fused_shape_supported(const tnerf_handle* h) { FusedPlan pl; return build_plan(h, pl); }
 
 int fused_pack_weights(tnerf_handle* h, cudaStream_t s) {

@@ -144,6 +144,41 @@ __device__ __forceinline__ void encode_stream(const float p[3], int L, uint32_t 
     else encode_stream_impl<KX, INC, false>(p, L, pk);
 }
 
+// ------------------------------------------------------------------------------------------------
+// In-place refresh of the fp16 operand image by the optimiser: parameter i of the flat fp32 vector (state_dict order)
+// owns one image element (weights, biases carried by the encoding's constant-1 column) or two (biases carried by the
+// "ones" K-step as an fp16 hi/lo pair).  Same conventions as pack_weights_kernel (tnerf_fused.cu); padding never changes.
+enum { RP_W_HID = 0, RP_B_HID = 1, RP_W_SIG = 2, RP_B_SIG = 3, RP_W_RGB = 4, RP_B_RGB = 5 };
+struct RepackMap {
+    int n_tensors, H, valid;
+    long long off[2 * kMaxDepth + 5];          // flat offset of every tensor (+ total)
+    uint8_t kind[2 * kMaxDepth + 4], layer[2 * kMaxDepth + 4];
+    int fan[kMaxDepth + 1], act_len[kMaxDepth + 1], xstart[kMaxDepth + 1], bias_k[kMaxDepth + 1], bias_hilo[kMaxDepth + 1], N[kMaxDepth + 1];
+    uint32_t img_off[kMaxDepth + 1];           // in halfs
+    __half* image;
+};
+__device__ __forceinline__ void repack_param(const RepackMap& mp, long long i, float val) {
+    int t = 0;
+    while (t + 1 < mp.n_tensors && mp.off[t + 1] <= i) ++t;
+    const int loc = (int)(i - mp.off[t]), kind = mp.kind[t], l = mp.layer[t], N = mp.N[l];
+    __half* img = mp.image + mp.img_off[l];
+    int n, kk;
+    bool bias = false;
+    if (kind == RP_W_HID) { n = loc / mp.fan[l]; const int j = loc - n * mp.fan[l]; kk = j < mp.act_len[l] ? j : mp.xstart[l] + (j - mp.act_len[l]); }
+    else if (kind == RP_W_SIG) { n = 0; kk = loc; }
+    else if (kind == RP_W_RGB) { n = 1 + loc / mp.H; kk = loc % mp.H; }
+    else { bias = true; n = (kind == RP_B_HID) ? loc : (kind == RP_B_SIG ? 0 : 1 + loc); kk = mp.bias_k[l]; }
+    const __half hi = __float2half_rn(val);
+    img[img_idx(n, kk, N)] = hi;
+    if (bias && mp.bias_hilo[l]) img[img_idx(n, kk + 1, N)] = __float2half_rn(val - __half2float(hi));
+}
+bool build_repack_map(const tnerf_handle* h, RepackMap& mp);
+int launch_adam_fused(float* p, float* g, float* m, float* v, long long n, long long n_clear, int step, float lr, float b1, float b2,
+                      float eps, float* tail_out, const RepackMap& mp, cudaStream_t s);
+int launch_allreduce_adam(float* p, float* m, float* v, long long n, const float* const* peer_grads, unsigned int* const* peer_flags,
+                          int world, int rank, unsigned int epoch, int step, float lr, float b1, float b2, float eps, float* reduced_out,
+                          float* zero_next, const RepackMap& mp, cudaStream_t s);
+
 bool build_plan(const tnerf_handle* h, FusedPlan& pl);
 int fused_render_fwd_fast(const FwdParams& p, int grid, cudaStream_t s);   // tnerf_fused_fast.cu (n_samples % 32 == 0)
 

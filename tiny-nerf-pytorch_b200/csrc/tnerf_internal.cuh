@@ -64,9 +64,7 @@ int launch_composite_bwd(const float* rgb, const float* sigma, const float* z, l
 int launch_mse_psnr(const float* a, const float* b, long long n, float* out2, cudaStream_t s);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float b1, float b2, float eps, float inv_scale, const int* found_inf, cudaStream_t s);
 int launch_check_finite(const float* g, long long n, int* flag, cudaStream_t s);
-int launch_allreduce_adam(float* p, float* m, float* v, long long n, const float* const* peer_grads, unsigned int* const* peer_flags,
-                          int world, int rank, unsigned int epoch, int step, float lr, float b1, float b2, float eps, float* reduced_out,
-                          cudaStream_t s);
+
 int launch_mse_grad(const float* c, const float* t, long long n3, float inv_denom, float* gC, float* loss, cudaStream_t s);
 
 // fp32 MLP (tnerf_mlp.cu)

@@ -2,7 +2,7 @@
 // get_rays, ray gather, stratified_samples, PositionalEncoding, TinyNeRF (tiled FFMA GEMMs),
 // volume_render forward/backward, MSE/PSNR, Adam.  All are HBM- or FFMA-bound elementwise / scan /
 // SGEMM kernels; the tensor-core fused path lives in tnerf_fused.cu.
-#include "tnerf_internal.cuh"
+#include "tnerf_fused.cuh"
 
 namespace tnerf {
 
@@ -356,6 +356,25 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
     p[i] = p[i] - lr_over_bc1 * (mi / denom);
 }
+// a9 + N1: Adam on the flat parameter vector, the gradient vector cleared for the next step and the fp16 operand image of
+// the tensor-core kernels refreshed in place -- one launch instead of memset + Adam + re-pack.
+__global__ void adam_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                  long long n, long long n_clear, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps,
+                                  float* __restrict__ tail_out, const __grid_constant__ RepackMap mp) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_clear) return;
+    const float gi = g[i];
+    g[i] = 0.f;
+    if (i >= n) { if (tail_out) tail_out[i - n] = gi; return; }      // e.g. the loss slot behind the gradient
+    const float mi = fmaf(1.f - b1, gi - m[i], m[i]);
+    const float vi = fmaf(v[i], b2, (1.f - b2) * gi * gi);
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    const float pn = p[i] - lr_over_bc1 * (mi / denom);
+    p[i] = pn;
+    if (mp.valid) repack_param(mp, i, pn);
+}
+
 // (e) ray-sharded data parallel: one-shot all-reduce of the flat [gradient | loss] vectors over NVLink peer memory, fused with
 // the Adam step (replaces ncclAllReduce + adam_kernel).  Every rank runs this kernel on its own GPU.
 //   1. block 0 publishes "my vector for epoch e is complete" into every peer's flag array (release, system scope);
@@ -376,7 +395,8 @@ __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) 
 
 __global__ void allreduce_adam_kernel(PeerSet ps, int world, int rank, unsigned int epoch, float* __restrict__ p,
                                       float* __restrict__ m, float* __restrict__ v, long long n, float lr_over_bc1,
-                                      float inv_sqrt_bc2, float b1, float b2, float eps, float* __restrict__ reduced_out) {
+                                      float inv_sqrt_bc2, float b1, float b2, float eps, float* __restrict__ reduced_out,
+                                      float* __restrict__ zero_next, const __grid_constant__ RepackMap mp) {
     __shared__ int timed_out;
     if (threadIdx.x == 0) timed_out = 0;
     if (blockIdx.x == 0 && threadIdx.x < world) {
@@ -398,12 +418,16 @@ __global__ void allreduce_adam_kernel(PeerSet ps, int world, int rank, unsigned 
     float g = 0.f;
     for (int r = 0; r < world; ++r) g += __ldcv(ps.grads[r] + i);
     if (reduced_out) reduced_out[i] = g;
+    // every rank is past the barrier, so nobody still reads this rank's OTHER-parity vector: clear it for the next step
+    if (zero_next) zero_next[i] = 0.f;
     if (i == n) return;                                             // the loss element
     const float mi = fmaf(1.f - b1, g - m[i], m[i]);
     const float vi = fmaf(v[i], b2, (1.f - b2) * g * g);
     m[i] = mi; v[i] = vi;
     const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-    p[i] = p[i] - lr_over_bc1 * (mi / denom);
+    const float pn = p[i] - lr_over_bc1 * (mi / denom);
+    p[i] = pn;
+    if (mp.valid) repack_param(mp, i, pn);
 }
 
 __global__ void check_finite_kernel(const float* __restrict__ g, long long n, int* __restrict__ flag) {
@@ -514,15 +538,23 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, int s
                                                     eps, inv_scale, found_inf);
     return count_launch();
 }
+int launch_adam_fused(float* p, float* g, float* m, float* v, long long n, long long n_clear, int step, float lr, float b1, float b2,
+                      float eps, float* tail_out, const RepackMap& mp, cudaStream_t s) {
+    if (n_clear <= 0) return 0;
+    const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+    adam_fused_kernel<<<blocks_for(n_clear, 256), 256, 0, s>>>(p, g, m, v, n, n_clear, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), b1,
+                                                                b2, eps, tail_out, mp);
+    return count_launch();
+}
 int launch_allreduce_adam(float* p, float* m, float* v, long long n, const float* const* peer_grads, unsigned int* const* peer_flags,
                           int world, int rank, unsigned int epoch, int step, float lr, float b1, float b2, float eps, float* reduced_out,
-                          cudaStream_t s) {
+                          float* zero_next, const RepackMap& mp, cudaStream_t s) {
     if (n <= 0) return 0;
     PeerSet ps{};
     for (int r = 0; r < world; ++r) { ps.grads[r] = peer_grads[r]; ps.flags[r] = peer_flags[r]; }
     const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
     allreduce_adam_kernel<<<blocks_for(n + 1, 256), 256, 0, s>>>(ps, world, rank, epoch, p, m, v, n, (float)((double)lr / bc1),
-                                                                 (float)(1.0 / sqrt(bc2)), b1, b2, eps, reduced_out);
+                                                                 (float)(1.0 / sqrt(bc2)), b1, b2, eps, reduced_out, zero_next, mp);
     return count_launch();
 }
 int launch_check_finite(const float* g, long long n, int* flag, cudaStream_t s) {

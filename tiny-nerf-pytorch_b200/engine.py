@@ -167,6 +167,7 @@ class Trainer:
             off += n
         self.gbuf = torch.zeros(self.P + 1, dtype=torch.float32, device=dev)   # [gradient | loss]
         self.loss_view = self.gbuf[self.P:]
+        self.loss_out = torch.zeros(1, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(self.P, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(self.P, dtype=torch.float32, device=dev)
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
@@ -218,29 +219,30 @@ class Trainer:
 
     # ---- one optimisation step ------------------------------------------------------------------
     def _finish(self):
+        """optimiser step: ONE launch (Adam + clearing of the next step's gradient vector + in-place refresh of the fp16
+        operand image); with several ranks the same launch first all-reduces the gradient over NVLink peer memory"""
         self.steps += 1
         st = E.stream(self.device)
+        repack = 1 if self.prec == E.PREC_F16_TC else 0
         if self.comm == "p2p":
             k = self.steps & 1
-            E.check(E.lib().tnerf_allreduce_adam_step(E.ptr(self.flat), E.ptr(self.exp_avg), E.ptr(self.exp_avg_sq), self.P,
+            E.check(E.lib().tnerf_allreduce_adam_step(self.h.h, E.ptr(self.flat), E.ptr(self.exp_avg), E.ptr(self.exp_avg_sq), self.P,
                                                       self._peer_grads[k], self._peer_flags, self.world, self.rank, self.steps, self.steps,
-                                                      self.lr, self.betas[0], self.betas[1], self.eps, E.ptr(self.reduced), st),
-                    "tnerf_allreduce_adam_step")
-            loss = self.reduced[self.P:]
-        else:
-            if self.world > 1:
-                torch.distributed.all_reduce(self.gbuf, group=self.pg)
-            E.check(E.lib().tnerf_adam_step(E.ptr(self.flat), E.ptr(self.gbuf), E.ptr(self.exp_avg), E.ptr(self.exp_avg_sq), self.P,
-                                            self.steps, self.lr, self.betas[0], self.betas[1], self.eps, 1.0, None, st), "tnerf_adam_step")
-            loss = self.loss_view
-        if self.prec == E.PREC_F16_TC:
-            self.h.ensure_packed(force=True)
-        return loss
+                                                      self.lr, self.betas[0], self.betas[1], self.eps, E.ptr(self.reduced),
+                                                      E.ptr(self._gviews[k ^ 1]), repack, st), "tnerf_allreduce_adam_step")
+            return self.reduced[self.P:]
+        if self.world > 1:
+            torch.distributed.all_reduce(self.gbuf, group=self.pg)
+        # the gradient vector and its loss slot are cleared by the optimiser launch; the loss is handed out through loss_out
+        E.check(E.lib().tnerf_optimizer_step(self.h.h, E.ptr(self.flat), E.ptr(self.gbuf), E.ptr(self.exp_avg), E.ptr(self.exp_avg_sq), self.P,
+                                             self.P + 1, self.steps, self.lr, self.betas[0], self.betas[1], self.eps, E.ptr(self.loss_out),
+                                             repack, st),
+                "tnerf_optimizer_step")
+        return self.loss_out
 
     def _launch(self, rs, target, n, jitter, global_rays):
         st = E.stream(self.device)
-        gbuf = self._gviews[(self.steps + 1) & 1] if self.comm == "p2p" else self.gbuf      # [gradient | loss] of this step
-        gbuf.zero_()
+        gbuf = self._gviews[(self.steps + 1) & 1] if self.comm == "p2p" else self.gbuf      # [gradient | loss] of this step, zero on entry
         denom = 3.0 * float(global_rays if global_rays else n * self.world)
         E.check(E.lib().tnerf_train_fwd_bwd(self.h.h, C.byref(rs), E.ptr(target), n, self.near, self.far, self.S, E.ptr(jitter),
                                             int(self.white), self.prec, denom, None, E.ptr(gbuf[self.P:]), E.ptr(gbuf), st),
