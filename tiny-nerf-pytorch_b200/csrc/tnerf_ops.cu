@@ -7,15 +7,46 @@
 namespace tnerf {
 
 // ------------------------------------------------------------------------------------------------
-// a1 get_rays (src/rays.py:3-33): one thread per ray, 24 B written per ray.
+// a1 get_rays (src/rays.py:3-33): 24 B written per ray.  One thread = 4 consecutive rays = three 16-byte stores per output
+// (a thread per ray would issue stride-12 scalar stores); the pixel row/column are divided out once and stepped.
 __global__ void get_rays_kernel(int H, int W, float focal, const float* __restrict__ c2w, long long first,
                                 long long n, float* __restrict__ ro, float* __restrict__ rd) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float dx, dy, dz;
-    pixel_ray(first + i, H, W, focal, c2w, dx, dy, dz);
-    rd[3 * i] = dx; rd[3 * i + 1] = dy; rd[3 * i + 2] = dz;
-    if (ro) { ro[3 * i] = c2w[3]; ro[3 * i + 1] = c2w[7]; ro[3 * i + 2] = c2w[11]; }
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long i0 = 4 * q;
+    if (i0 >= n) return;
+    const float ox = c2w[3], oy = c2w[7], oz = c2w[11];
+    const long long k0 = first + i0;
+    int row = (int)(k0 / W), col = (int)(k0 - (long long)row * W);
+    float d[12];
+    const int cnt = (n - i0 < 4) ? (int)(n - i0) : 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        d[3 * j] = d[3 * j + 1] = d[3 * j + 2] = 0.f;
+        if (j < cnt) {
+            const float cx = __fdiv_rn((float)col - (float)W * 0.5f, focal);
+            const float cy = -__fdiv_rn((float)row - (float)H * 0.5f, focal);
+            const float wx = fmaf(-1.f, c2w[2], fmaf(cy, c2w[1], cx * c2w[0]));
+            const float wy = fmaf(-1.f, c2w[6], fmaf(cy, c2w[5], cx * c2w[4]));
+            const float wz = fmaf(-1.f, c2w[10], fmaf(cy, c2w[9], cx * c2w[8]));
+            const float nn = fmaxf(sqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx))), 1e-12f);
+            d[3 * j] = __fdiv_rn(wx, nn); d[3 * j + 1] = __fdiv_rn(wy, nn); d[3 * j + 2] = __fdiv_rn(wz, nn);
+            if (++col == W) { col = 0; ++row; }
+        }
+    }
+    const bool vec = cnt == 4 && ((reinterpret_cast<uintptr_t>(rd) & 15) == 0) && (!ro || (reinterpret_cast<uintptr_t>(ro) & 15) == 0);
+    if (vec) {
+        float4* pd = reinterpret_cast<float4*>(rd + 3 * i0);
+        pd[0] = make_float4(d[0], d[1], d[2], d[3]); pd[1] = make_float4(d[4], d[5], d[6], d[7]); pd[2] = make_float4(d[8], d[9], d[10], d[11]);
+        if (ro) {
+            float4* po = reinterpret_cast<float4*>(ro + 3 * i0);
+            po[0] = make_float4(ox, oy, oz, ox); po[1] = make_float4(oy, oz, ox, oy); po[2] = make_float4(oz, ox, oy, oz);
+        }
+    } else {
+        for (int j = 0; j < cnt; ++j) {
+            rd[3 * (i0 + j)] = d[3 * j]; rd[3 * (i0 + j) + 1] = d[3 * j + 1]; rd[3 * (i0 + j) + 2] = d[3 * j + 2];
+            if (ro) { ro[3 * (i0 + j)] = ox; ro[3 * (i0 + j) + 1] = oy; ro[3 * (i0 + j) + 2] = oz; }
+        }
+    }
 }
 
 // a2 gather (src/train.py:110-112)
@@ -51,22 +82,68 @@ __global__ void stratified_kernel(const float* __restrict__ ro, long long o_stri
     }
 }
 
-// a4 PositionalEncoding (src/encoding.py:26-33): one thread per OUTPUT element -> coalesced stores.
-__global__ void posenc_kernel(const float* __restrict__ x, long long n, int L, int inc, float* __restrict__ out) {
-    const int D = 6 * L + (inc ? 3 : 0);
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= n * D) return;
-    const long long p = t / D; int c = (int)(t % D);
-    float v;
-    if (inc && c < 3) {
-        v = x[3 * p + c];
-    } else {
-        if (inc) c -= 3;
-        const int k = c / 6, r = c % 6, axis = r % 3;
-        const float arg = x[3 * p + axis] * (float)(1 << k);   // exact power-of-two scaling
-        v = (r < 3) ? sinf(arg) : cosf(arg);
+// vector variant for n_samples % 4 == 0: one thread = 4 consecutive samples of one ray: 16-byte jitter load and depth store,
+// three 16-byte point stores (the scalar kernel writes points with stride-12 scalar stores)
+__global__ void stratified4_kernel(const float* __restrict__ ro, long long o_stride, const float* __restrict__ rd,
+                                   long long n, int S, float near_, float far_, const float* __restrict__ near_ray,
+                                   const float* __restrict__ far_ray, const float* __restrict__ jitter,
+                                   float* __restrict__ z_out, float* __restrict__ pts) {
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int S4 = S >> 2;
+    if (q >= n * S4) return;
+    const long long r = q / S4;
+    const int i0 = (int)(q - r * S4) * 4;
+    const float nr = near_ray ? near_ray[r] : near_, fr = far_ray ? far_ray[r] : far_;
+    const bool jit = jitter != nullptr;
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (jit) u = *reinterpret_cast<const float4*>(jitter + r * S + i0);
+    const float uu[4] = {u.x, u.y, u.z, u.w};
+    // bins i0-1 .. i0+4 once (src/sampling.py:16-17), then the jittered depths (:21-25); same roundings as depth_sample()
+    float bins[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { const int i = i0 - 1 + j; bins[j] = (i >= 0 && i < S) ? depth_bin(i, S, nr, fr) : 0.f; }
+    float z[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j;
+        const float zc = bins[j + 1];
+        if (!jit) { z[j] = zc; continue; }
+        const float lo = (i == 0) ? zc : __fmul_rn(0.5f, __fadd_rn(bins[j], zc));
+        const float hi = (i == S - 1) ? zc : __fmul_rn(0.5f, __fadd_rn(zc, bins[j + 2]));
+        z[j] = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), uu[j]));
     }
-    out[t] = v;
+    if (z_out) *reinterpret_cast<float4*>(z_out + r * S + i0) = make_float4(z[0], z[1], z[2], z[3]);
+    if (pts) {
+        const float* o = ro + r * o_stride;
+        const float ox = o[0], oy = o[1], oz = o[2], dx = rd[3 * r], dy = rd[3 * r + 1], dz = rd[3 * r + 2];
+        float pv[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            pv[3 * j] = __fadd_rn(ox, __fmul_rn(dx, z[j])); pv[3 * j + 1] = __fadd_rn(oy, __fmul_rn(dy, z[j])); pv[3 * j + 2] = __fadd_rn(oz, __fmul_rn(dz, z[j]));
+        }
+        float4* pp = reinterpret_cast<float4*>(pts + 3 * (r * S + i0));
+        pp[0] = make_float4(pv[0], pv[1], pv[2], pv[3]); pp[1] = make_float4(pv[4], pv[5], pv[6], pv[7]); pp[2] = make_float4(pv[8], pv[9], pv[10], pv[11]);
+    }
+}
+
+// a4 PositionalEncoding (src/encoding.py:26-33): 12 B in + 4 D B out per point.  One thread per (point, octave, axis): ONE
+// sincosf serves the sine and the cosine column (a thread per output element evaluated every argument twice and paid two
+// 64-bit divisions); a warp covers one point's row, so its stores fall into the same few 128-byte lines.
+template <typename IDX>
+__global__ void posenc_kernel(const float* __restrict__ x, long long n, int L, int inc, float* __restrict__ out) {
+    const int D = 6 * L + (inc ? 3 : 0), items = 3 * L + (inc ? 3 : 0), base = inc ? 3 : 0;
+    const IDX t = (IDX)blockIdx.x * (IDX)blockDim.x + (IDX)threadIdx.x;
+    if ((long long)t >= n * items) return;
+    const IDX p = t / (IDX)items;
+    int c = (int)(t - p * (IDX)items);
+    float* o = out + (long long)p * D;
+    if (inc && c < 3) { o[c] = x[3 * (long long)p + c]; return; }
+    c -= base;
+    const int k = c / 3, axis = c - 3 * k;
+    float sv, cv;
+    sincosf(x[3 * (long long)p + axis] * (float)(1 << k), &sv, &cv);   // exact power-of-two scaling
+    o[base + 6 * k + axis] = sv;
+    o[base + 6 * k + 3 + axis] = cv;
 }
 
 __global__ void posenc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, long long n, int L,
@@ -457,7 +534,7 @@ static inline unsigned blocks_for(long long n, int per) { return (unsigned)((n +
 int launch_get_rays(int H, int W, float focal, const float* c2w, long long first, long long n, float* ro, float* rd,
                     cudaStream_t s) {
     if (n <= 0) return 0;
-    get_rays_kernel<<<blocks_for(n, 256), 256, 0, s>>>(H, W, focal, c2w, first, n, ro, rd);
+    get_rays_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, s>>>(H, W, focal, c2w, first, n, ro, rd);
     return count_launch();
 }
 int launch_gather3(const long long* idx, long long n, long long n_src, const float* sa, float* da, const float* sb,
@@ -469,13 +546,18 @@ int launch_gather3(const long long* idx, long long n, long long n_src, const flo
 int launch_stratified(const float* ro, long long os, const float* rd, long long n, int S, float nr, float fr,
                       const float* nray, const float* fray, const float* jit, float* z, float* pts, cudaStream_t s) {
     if (n <= 0) return 0;
-    stratified_kernel<<<blocks_for(n * S, 256), 256, 0, s>>>(ro, os, rd, n, S, nr, fr, nray, fray, jit, z, pts);
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (S % 4 == 0 && al16(jit) && al16(z) && al16(pts))
+        stratified4_kernel<<<blocks_for(n * (S / 4), 256), 256, 0, s>>>(ro, os, rd, n, S, nr, fr, nray, fray, jit, z, pts);
+    else
+        stratified_kernel<<<blocks_for(n * S, 256), 256, 0, s>>>(ro, os, rd, n, S, nr, fr, nray, fray, jit, z, pts);
     return count_launch();
 }
 int launch_posenc(const float* x, long long n, int L, int inc, float* out, cudaStream_t s) {
     if (n <= 0) return 0;
-    const long long tot = n * (6 * L + (inc ? 3 : 0));
-    posenc_kernel<<<blocks_for(tot, 256), 256, 0, s>>>(x, n, L, inc, out);
+    const long long tot = n * (3 * L + (inc ? 3 : 0));
+    if (tot < (1LL << 31)) posenc_kernel<unsigned><<<blocks_for(tot, 256), 256, 0, s>>>(x, n, L, inc, out);
+    else posenc_kernel<long long><<<blocks_for(tot, 256), 256, 0, s>>>(x, n, L, inc, out);
     return count_launch();
 }
 int launch_posenc_bwd(const float* x, const float* g, long long n, int L, int inc, float* gx, cudaStream_t s) {
