@@ -513,9 +513,10 @@ int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, flo
     p.slabs = reinterpret_cast<float*>(h->slabs);
     long long grid;
     static const bool force_v1 = getenv("TNERF_TRAIN_V1") != nullptr;
-    if (64 % S == 0 && !force_v1) {
-        // two-stream kernel (tnerf_train2.cu): 64-sample tiles
-        p.R = 64 / S; p.n_tiles = (n + p.R - 1) / p.R;
+    if ((64 % S == 0 || S == 128) && !force_v1) {
+        // two-stream kernel (tnerf_train2.cu): 64-sample tiles; at 128 samples the two streams of a CTA carry the two halves of one ray
+        if (S == 128) { p.R = 1; p.n_tiles = 2 * n; }
+        else { p.R = 64 / S; p.n_tiles = (n + p.R - 1) / p.R; }
         grid = (p.n_tiles + 1) / 2 < h->sm_count ? (p.n_tiles + 1) / 2 : h->sm_count;
         if (int rc = fused_train2(h, fp, p, Kx, (int)grid, s)) return rc;
     } else {

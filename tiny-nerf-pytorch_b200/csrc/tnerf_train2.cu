@@ -28,8 +28,8 @@ constexpr uint32_t S_P0 = 135168, S_Q0 = 151552, S_P1 = 167936, S_Q1 = 184320;  
 constexpr uint32_t S_X0 = 200704, S_X1 = 208896, S_DZH0 = 217088, S_DZH1 = 219136, S_MISC = 221184;
 
 struct Misc {
-    float xch[2][24];          // per stream: cross-warp carries of the compositing scans (one ray spanning two warps)
-    uint64_t bar_w, bar_x[2], bar_in[2], bar_d[2], bar_head[2], bar_dzh[2], bar_g[2][2], bar_gfree[2], bar_xfree[2], bar_wg[2], bar_dread[2];
+    float xch[2][48];          // cross-warp carries of the compositing scans (a ray spans 2 warps at 64 samples, all 4 at 128)
+    uint64_t bar_w, bar_x[2], bar_in[2], bar_d[2], bar_head[2], bar_dzh[2], bar_g[2][2], bar_gfree[2], bar_xfree[2], bar_wg[2], bar_dread[2], bar_in2[2];
     uint32_t tmem_slot;
 };
 
@@ -153,13 +153,13 @@ __device__ __forceinline__ void issuer_loop(Misc& ms, uint32_t sbase, uint32_t t
     const uint32_t bar_x = smem_u32(&ms.bar_x[s]), bar_in = smem_u32(&ms.bar_in[s]), bar_d = smem_u32(&ms.bar_d[s]);
     const uint32_t bar_head = smem_u32(&ms.bar_head[s]), bar_dzh = smem_u32(&ms.bar_dzh[s]), bar_gfree = smem_u32(&ms.bar_gfree[s]);
     const uint32_t bar_g0 = smem_u32(&ms.bar_g[s][0]), bar_g1 = smem_u32(&ms.bar_g[s][1]), bar_xfree = smem_u32(&ms.bar_xfree[s]);
-    const uint32_t bar_wg = smem_u32(&ms.bar_wg[s]), bar_dread = smem_u32(&ms.bar_dread[s]);
+    const uint32_t bar_wg = smem_u32(&ms.bar_wg[s]), bar_dread = smem_u32(&ms.bar_dread[s]), bar_in2 = smem_u32(&ms.bar_in2[s]);
     const uint32_t P = s ? S_P1 : S_P0, Q = s ? S_Q1 : S_Q0, X = s ? S_X1 : S_X0, DZH = s ? S_DZH1 : S_DZH0;   // byte offsets
     const uint32_t D = tmem + C_D + 64 * s;
     const uint32_t i64kk = make_idesc_f16(128, 64, 0, 0), i64kt = make_idesc_f16(128, 64, 0, 1), i64tk = make_idesc_f16(128, 64, 1, 0),
                    i64tt = make_idesc_f16(128, 64, 1, 1), i16tk = make_idesc_f16(128, 16, 1, 0), i16kt = make_idesc_f16(128, 16, 0, 1),
                    i128kk = make_idesc_f16(128, 128, 0, 0), iXkt = make_idesc_f16(128, KX, 0, 1);
-    uint32_t ph_x = 0, ph_in = 0, ph_dzh = 0, ph_gf = 0, ph_dr = 0;
+    uint32_t ph_x = 0, ph_in = 0, ph_dzh = 0, ph_gf = 0, ph_dr = 0, ph_in2 = 0;
 #define T2_WAIT(bar, ph) do { T2_STAMP(); mbar_wait(bar, ph); ph ^= 1; tc_fence_after(); T2_STAMP(); } while (0)
     // the whole warp runs this loop with warp-uniform values; one elected lane issues (operands stay in uniform registers)
 #define T2_ISSUE(...) do { if (elect_one()) { __VA_ARGS__ } __syncwarp(); } while (0)
@@ -207,7 +207,9 @@ __device__ __forceinline__ void issuer_loop(Misc& ms, uint32_t sbase, uint32_t t
                  gemm<4>(tmem + C_DW2 + 128, aP, bXt, iXkt, 1); tc_commit(bar_wg););                    // dW2[:, 128:] += dZ2 . X^T
         T2_WAIT(bar_dread, ph_dr);                                                                      // dH1 has been read out
         T2_ISSUE(gemm<XS>(D, aW0, bXk, i64kk, 0); tc_commit(bar_d););                                   // recompute H0 under the dZ1 drain
-        T2_WAIT(bar_in, ph_in);                                                                         // dZ1 stored
+        // "dZ1 stored" has its own barrier: with the H0 recompute already in flight the drain threads can complete this phase AND
+        // the next one (H0 stored) before this warp looks -- two unobserved phases of ONE mbarrier alias to "not complete" (deadlock)
+        T2_WAIT(bar_in2, ph_in2);                                                                       // dZ1 stored
         T2_WAIT(bar_in, ph_in);
         T2_ISSUE(gemm<4>(D, aQ, bP_lo, i64kk, 0); tc_commit(bar_g0););                                  // dW1[:, :64] partial
         T2_WAIT(bar_gfree, ph_gf);
@@ -242,6 +244,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             mbar_init(smem_u32(&ms.bar_xfree[s]), 1);
             mbar_init(smem_u32(&ms.bar_wg[s]), 1);
             mbar_init(smem_u32(&ms.bar_dread[s]), 128);
+            mbar_init(smem_u32(&ms.bar_in2[s]), 128);
         }
         fence_barrier_init();
     }
@@ -301,15 +304,20 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         uint8_t* DZH = smem + (s ? S_DZH1 : S_DZH0);
         const uint32_t bar_x = smem_u32(&ms.bar_x[s]), bar_head = smem_u32(&ms.bar_head[s]), bar_dzh = smem_u32(&ms.bar_dzh[s]),
                        bar_xfree = smem_u32(&ms.bar_xfree[s]);
-        float* xch = ms.xch[s];
+        // n_samples = 128 ("in-phase" mode): the two streams of the CTA carry the two halves of ONE ray, the four sample warps
+        // composite it together (chain of four 32-sample chunks); otherwise a ray lives inside one stream's tile
+        const bool inphase = p.S == 128;
+        const int nchain = inphase ? 4 : (p.S == 64 ? 2 : 1);          // warps a ray spans
+        const int cw = inphase ? 2 * s + wp : wp;                       // this warp's position in the chain
+        const int cbar = inphase ? 1 : 1 + s, cthreads = inphase ? 128 : 64;
+        float* xch = inphase ? ms.xch[0] : ms.xch[s];
         *reinterpret_cast<uint4*>(DZH + ((size_t)(64 + i) << 4)) = make_uint4(0u, 0u, 0u, 0u);   // head columns 8..15 stay zero
         const bool jit = p.jitter != nullptr;
         const float gscale = p.scale_dev ? *p.scale_dev : p.scale;
         const float bs = p.b_sigma[0], br = p.b_rgb[0], bg = p.b_rgb[1], bb = p.b_rgb[2];
         float hb[4] = {0.f, 0.f, 0.f, 0.f}, loss_acc = 0.f;
         const long long j0 = 2LL * blockIdx.x + s;
-        const int S = p.S, W = S < 32 ? S : 32, sl = lane & (W - 1), si = i % S;
-        const bool two = S == 64;                    // one ray spans both warps of the pair
+        const int S = p.S, W = S < 32 ? S : 32, sl = lane & (W - 1);
         const bool camera = p.rs.rays_d == nullptr;
         float cam[12];
 #pragma unroll
@@ -331,7 +339,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         uint32_t pk[KX / 2];
         // rays (src/rays.py:21-31), depth (sampling.py), Fourier features of sample i of `tile`; returns z and delta*|d| (volume.py:18-23)
         auto encode = [&](long long tile, float& z_out, float& gap_out) {
-            const long long ray = tile * p.R + i / S;
+            const long long ray = inphase ? (tile >> 1) : tile * p.R + i / S;
+            const int si = inphase ? (int)(tile & 1) * 64 + i : i % S;
             float pt[3] = {0.f, 0.f, 0.f};
             float z = 0.f, gd = 0.f;
             if (ray < p.n_rays) {
@@ -387,7 +396,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             if (more) encode(tile + nstreams, z_next, gap_next);          // under the forward GEMMs of this tile
             T2_STAMP();
             // per-ray inputs of the loss are fetched before the heads are ready
-            const long long ray = tile * p.R + i / S;
+            const long long ray = inphase ? (tile >> 1) : tile * p.R + i / S;
             const bool valid = ray < p.n_rays;
             float t0 = 0.f, t1 = 0.f, t2 = 0.f, gd = 0.f, ga = 0.f;
             if (valid) {
@@ -426,19 +435,24 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             const float wl = alpha * excl;
             float c0 = segsum(wl * own.y), c1 = segsum(wl * own.z), c2 = segsum(wl * own.w), asum = segsum(wl);
             float Tc = 1.f;
-            if (two) {
+            if (nchain > 1) {       // stitch the chunks of the ray: chunk c enters with T = prod of the earlier chunks' transmittances
                 const float Pw = __shfl_sync(0xffffffffu, incl, 31);
-                if (lane == 0) { float* x = xch + wp * 8; x[0] = Pw; x[1] = c0; x[2] = c1; x[3] = c2; x[4] = asum; }
-                bar_sync(1 + s, 64);
-                const float P0 = xch[0];
-                c0 = fmaf(P0, xch[9], xch[1]); c1 = fmaf(P0, xch[10], xch[2]); c2 = fmaf(P0, xch[11], xch[3]); asum = fmaf(P0, xch[12], xch[4]);
-                if (wp == 1) Tc = P0;
+                if (lane == 0) { float* x = xch + cw * 8; x[0] = Pw; x[1] = c0; x[2] = c1; x[3] = c2; x[4] = asum; }
+                bar_sync(cbar, cthreads);
+                float T = 1.f;
+                c0 = c1 = c2 = asum = 0.f;
+                for (int c = 0; c < nchain; ++c) {
+                    const float* x = xch + c * 8;
+                    if (c == cw) Tc = T;
+                    c0 = fmaf(T, x[1], c0); c1 = fmaf(T, x[2], c1); c2 = fmaf(T, x[3], c2); asum = fmaf(T, x[4], asum);
+                    T *= x[0];
+                }
             }
             const float Ti = Tc * excl, w = alpha * Ti;
             const float bgc = p.white ? 1.f - asum : 0.f;
             const float C0 = c0 + bgc, C1 = c1 + bgc, C2 = c2 + bgc;
             float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-            const bool leader = sl == 0 && !(two && wp == 1);
+            const bool leader = sl == 0 && cw == 0;
             if (valid) {
                 if (p.target) {
                     const float e0 = C0 - t0, e1 = C1 - t1, e2 = C2 - t2;
@@ -456,10 +470,10 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                 if (sl + off < W) { Aa = fmaf(Qq, An, Aa); Qq *= Qn; }
             }
             float Rc = 0.f;
-            if (two) {
-                if (wp == 1 && lane == 0) xch[16] = Aa;
-                bar_sync(1 + s, 64);
-                if (wp == 0) Rc = xch[16];
+            if (nchain > 1) {       // R entering this chunk from behind = the later chunks' affine maps applied to 0, last chunk first
+                if (lane == 0) { xch[32 + 2 * cw] = Aa; xch[33 + 2 * cw] = Qq; }
+                bar_sync(cbar, cthreads);
+                for (int c = nchain - 1; c > cw; --c) Rc = fmaf(xch[33 + 2 * c], Rc, xch[32 + 2 * c]);
             }
             const float Rprev = fmaf(Qq, Rc, Aa);
             float Ri = __shfl_down_sync(0xffffffffu, Rprev, 1, W);
@@ -500,7 +514,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         const uint32_t D_own = tl + C_D + 64 * s, D_oth = tl + C_D + 64 * (1 - s);
         uint8_t* P = smem + (s ? S_P1 : S_P0);
         uint8_t* Q = smem + (s ? S_Q1 : S_Q0);
-        const uint32_t bar_in = smem_u32(&ms.bar_in[s]), bar_d = smem_u32(&ms.bar_d[s]), bar_wg = smem_u32(&ms.bar_wg[s]), bar_dread = smem_u32(&ms.bar_dread[s]);
+        const uint32_t bar_in = smem_u32(&ms.bar_in[s]), bar_d = smem_u32(&ms.bar_d[s]), bar_wg = smem_u32(&ms.bar_wg[s]), bar_dread = smem_u32(&ms.bar_dread[s]), bar_in2 = smem_u32(&ms.bar_in2[s]);
         const uint32_t bar_g_own = smem_u32(&ms.bar_g[s][s]), bar_g_oth = smem_u32(&ms.bar_g[1 - s][s]);
         const uint32_t bar_gfree_own = smem_u32(&ms.bar_gfree[s]), bar_gfree_oth = smem_u32(&ms.bar_gfree[1 - s]);
         float dw1[64];                  // dW1[f][64 s + j]: this warpgroup's half of the columns, BOTH streams
@@ -513,6 +527,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         const float b1 = p.b1[f], b3 = p.b3[f];
         uint32_t ph_d = 0, ph_g_own = 0, ph_g_oth = 0, ph_wg = 0;
         long long g_oth_left = n_my[1 - s];
+        const bool inphase = p.S == 128;
         long long* dbg = (p.debug && blockIdx.x == 0 && (warp & 3) == 0 && lane == 0) ? p.debug + (s ? 768 : 0) : nullptr;
         int dbg_n = 0;
         if (dbg) dbg[251] = gtimer();
@@ -555,7 +570,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             wait_poll(bar_d, ph_d); drain_fwd<true>(D_own, Q, f, b1, stash); T2_SIGNAL();        // H1 -> Q (+ registers)
             wait_poll(bar_d, ph_d); drain_fwd<false>(D_own, P, f, 0.f, stash); T2_SIGNAL();      // H2 -> P
             wait_poll(bar_d, ph_d); drain_fwd<false>(D_own, Q, f, b3, stash); T2_SIGNAL();       // H3 -> Q
-            if ((s == 1 || t >= 1) && g_oth_left > 0) service();                                 // stream 1: tile t of stream 0; stream 0: tile t-1 of stream 1
+            if (!inphase && (s == 1 || t >= 1) && g_oth_left > 0) service();                     // stream 1: tile t of stream 0; stream 0: tile t-1 of stream 1
             wait_poll(bar_d, ph_d);                                                              // head wgrad
             {
                 uint32_t v[4];
@@ -576,10 +591,14 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                 wait_poll(bar_d, ph_d); db1 += drain_bwd_compute<true>(D_own, Q, f, o, bar_dread);   // dZ1 = dH1 * (H1 > 0)
                 wait_poll(bar_wg, ph_wg);                                                            // dW2 GEMMs no longer read H1 / dZ2
                 drain_store(Q, f, o);                                                                // dZ1 over H1 (Q)
-                T2_SIGNAL();
+                fence_proxy_async(); tc_fence_before(); mbar_arrive(bar_in2);
             }
             wait_poll(bar_d, ph_d); drain_fwd<false>(D_own, P, f, 0.f, stash); T2_SIGNAL();      // H0 -> P (dZ2 is dead)
+            // in-phase mode (n_samples = 128, both streams in the same tile phase): the dW1 halves are drained where they are
+            // produced, in the order stream 0 first half (WG0), stream 0 second half (WG1) | stream 1 first half (WG0), stream 1 second half (WG1)
+            if (inphase && s == 1 && g_oth_left > 0) service();
             wait_poll(bar_g_own, ph_g_own); drain_g(D_own, bar_gfree_own);
+            if (inphase && s == 0 && g_oth_left > 0) service();
             wait_poll(bar_d, ph_d); drain_bwd<false>(D_own, P, f); T2_SIGNAL();                  // dZ0 over H0 (P)
         }
         while (g_oth_left > 0) service();
