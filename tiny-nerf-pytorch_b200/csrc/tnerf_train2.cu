@@ -379,10 +379,6 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             fence_proxy_async();
             mbar_arrive(bar_x);
         };
-        auto segsum = [&](float v) -> float {      // sum over the W lanes of this thread's ray segment
-            for (int o = W >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            return v;
-        };
         uint32_t ph_head = 0, ph_xfree = 0;
         float z_cur = 0.f, gap_cur = 0.f;
         long long* dbg = (p.debug && blockIdx.x == 0 && warp == 8 && lane == 0) ? p.debug + 512 : nullptr;
@@ -426,14 +422,24 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             const float alpha = valid ? 1.f - e : 0.f;
             const float q = valid ? 1.f - alpha + kEpsT : 1.f;
             float incl = q;
-            for (int off = 1; off < W; off <<= 1) {
-                const float up = __shfl_up_sync(0xffffffffu, incl, off, W);
-                if (sl >= off) incl *= up;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                if (off < W) {
+                    const float up = __shfl_up_sync(0xffffffffu, incl, off, W);
+                    if (sl >= off) incl *= up;
+                }
             }
             float excl = __shfl_up_sync(0xffffffffu, incl, 1, W);
             if (sl == 0) excl = 1.f;
             const float wl = alpha * excl;
-            float c0 = segsum(wl * own.y), c1 = segsum(wl * own.z), c2 = segsum(wl * own.w), asum = segsum(wl);
+            float c0 = wl * own.y, c1 = wl * own.z, c2 = wl * own.w, asum = wl;     // four sums over the ray segment, reduced together
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                if (o < W) {
+                    c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+                    c2 += __shfl_xor_sync(0xffffffffu, c2, o); asum += __shfl_xor_sync(0xffffffffu, asum, o);
+                }
+            }
             float Tc = 1.f;
             if (nchain > 1) {       // stitch the chunks of the ray: chunk c enters with T = prod of the earlier chunks' transmittances
                 const float Pw = __shfl_sync(0xffffffffu, incl, 31);
@@ -464,10 +470,13 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             const float gconst = ga - (p.white ? (g0 + g1 + g2) : 0.f);
             const float g = valid ? (g0 * own.y + g1 * own.z + g2 * own.w + gd * z_cur + gconst) : 0.f;
             float Aa = g * alpha, Qq = q;        // suffix composition of the maps R -> g a + q R
-            for (int off = 1; off < W; off <<= 1) {
-                const float An = __shfl_down_sync(0xffffffffu, Aa, off, W);
-                const float Qn = __shfl_down_sync(0xffffffffu, Qq, off, W);
-                if (sl + off < W) { Aa = fmaf(Qq, An, Aa); Qq *= Qn; }
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                if (off < W) {
+                    const float An = __shfl_down_sync(0xffffffffu, Aa, off, W);
+                    const float Qn = __shfl_down_sync(0xffffffffu, Qq, off, W);
+                    if (sl + off < W) { Aa = fmaf(Qq, An, Aa); Qq *= Qn; }
+                }
             }
             float Rc = 0.f;
             if (nchain > 1) {       // R entering this chunk from behind = the later chunks' affine maps applied to 0, last chunk first
