@@ -86,7 +86,7 @@ long long tnerf_param_count(const tnerf_handle* h);
 /* The fused entry points generate the Fourier features themselves.  By default the encoding is
  * inferred from in_dim (6L+3 -> include_input); call this to state it explicitly. */
 int  tnerf_set_encoding(tnerf_handle* h, int num_freqs, int include_input);
-/* Developer hook: a device buffer of 1024 int64 that receives clock64() phase stamps of CTA 0 of the fused
+/* Developer hook: a device buffer of 2048 int64 that receives clock64() phase stamps of CTA 0 of the fused
  * forward kernel (tools/trace_fwd.py); NULL disables it. */
 int  tnerf_set_debug_buffer(tnerf_handle* h, void* buf);
 /* 1 when the tcgen05 fused kernels support this handle's (in_dim, hidden, depth, skip_at) */

@@ -57,75 +57,24 @@ __device__ __forceinline__ void gemm(uint32_t d, const Op a, const Op b, uint32_
 }
 
 // ---- drains (thread <-> feature row f; accumulator columns = the 64 samples of the tile) ------------
-// forward: + bias, relu, fp16, image row f of the slot (16 B = 8 consecutive samples)
-template <bool STASH>
-__device__ __forceinline__ void drain_fwd(uint32_t D, uint8_t* slot, int f, float bias, uint32_t (&stash)[32]) {
-    uint32_t va[2][32];
-    tmem_ld32(D, va[0]);
-    tc_wait_ld();
-    tmem_ld32(D + 32, va[1]);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        if (c == 1) tc_wait_ld();
-        const uint32_t (&v)[32] = va[c];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_relu_h2(__uint_as_float(v[8 * j + 0]) + bias, __uint_as_float(v[8 * j + 1]) + bias);
-            o.y = pack_relu_h2(__uint_as_float(v[8 * j + 2]) + bias, __uint_as_float(v[8 * j + 3]) + bias);
-            o.z = pack_relu_h2(__uint_as_float(v[8 * j + 4]) + bias, __uint_as_float(v[8 * j + 5]) + bias);
-            o.w = pack_relu_h2(__uint_as_float(v[8 * j + 6]) + bias, __uint_as_float(v[8 * j + 7]) + bias);
-            *reinterpret_cast<uint4*>(slot + ((size_t)((c * 4 + j) * 128 + f) << 4)) = o;
-            if (STASH) { stash[(c * 4 + j) * 4 + 0] = o.x; stash[(c * 4 + j) * 4 + 1] = o.y; stash[(c * 4 + j) * 4 + 2] = o.z; stash[(c * 4 + j) * 4 + 3] = o.w; }
-        }
-    }
-}
 __device__ __forceinline__ float h2sum(uint32_t h) {
     const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h));
     return a.x + a.y;
 }
-// backward: dZ = dH * (H > 0) over H in place; optionally returns the row sum (bias gradient of this feature)
-template <bool SUM>
-__device__ __forceinline__ float drain_bwd(uint32_t D, uint8_t* slot, int f) {
-    float sum = 0.f;
-    uint32_t va[2][32];
-    tmem_ld32(D, va[0]);
-    tc_wait_ld();
-    tmem_ld32(D + 32, va[1]);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        if (c == 1) tc_wait_ld();
-        const uint32_t (&v)[32] = va[c];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint4* p = reinterpret_cast<uint4*>(slot + ((size_t)((c * 4 + j) * 128 + f) << 4));
-            const uint4 h = *p;
-            uint4 o;
-            o.x = pack_sat_h2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])) & relu_mask(h.x);
-            o.y = pack_sat_h2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])) & relu_mask(h.y);
-            o.z = pack_sat_h2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])) & relu_mask(h.z);
-            o.w = pack_sat_h2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])) & relu_mask(h.w);
-            *p = o;
-            if (SUM) sum += (h2sum(o.x) + h2sum(o.y)) + (h2sum(o.z) + h2sum(o.w));
-        }
-    }
-    return sum;
-}
-
-// ---- MMA issuer of stream S (one thread).  S is a template parameter so that every shared-memory offset folds into
-// an immediate: the issuer runs with 40 registers.
-// two-phase variant: the masked, packed dZ row is computed into registers while the wgrad GEMM that still reads the slot
+// backward drain, two-phase: dZ = dH * (H > 0); the masked, packed dZ row is computed into registers while the wgrad GEMM that still reads the slot
 // (H as its operand) runs; drain_store() writes it once that GEMM has committed.  `dread_bar` (optional) is arrived on as
 // soon as the accumulator has been read, so a GEMM that only needs the accumulator may be issued under the rest of the drain.
 template <bool SUM>
 __device__ __forceinline__ float drain_bwd_compute(uint32_t D, const uint8_t* slot, int f, uint32_t (&o)[32], uint32_t dread_bar) {
     float sum = 0.f;
+    uint32_t va[2][32];
+    tmem_ld32(D, va[0]);
+    tc_wait_ld();
+    tmem_ld32(D + 32, va[1]);                 // second half in flight while the first is processed
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(D + c * 32, v);
-        tc_wait_ld();
-        if (c == 1 && dread_bar) { tc_fence_before(); mbar_arrive(dread_bar); }
+        if (c == 1) { tc_wait_ld(); if (dread_bar) { tc_fence_before(); mbar_arrive(dread_bar); } }
+        const uint32_t (&v)[32] = va[c];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint4 h = *reinterpret_cast<const uint4*>(slot + ((size_t)((c * 4 + j) * 128 + f) << 4));
@@ -145,16 +94,19 @@ __device__ __forceinline__ void drain_store(uint8_t* slot, int f, const uint32_t
         *reinterpret_cast<uint4*>(slot + ((size_t)(c * 128 + f) << 4)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
 }
 
-template <int KX, int S>
-__device__ __forceinline__ void issuer_loop(Misc& ms, uint32_t sbase, uint32_t tmem, long long n_tiles_mine, long long* dbg) {
+template <int KX, int SS>
+__device__ __forceinline__ void issuer_loop(Misc& ms, uint32_t sbase, uint32_t tmem, int s_rt, long long n_tiles_mine, long long* dbg) {
+    const int s = SS >= 0 ? SS : s_rt;
     int dbg_n = 0;
-    constexpr int s = S;
     constexpr int XS = KX / 16;
     const uint32_t bar_x = smem_u32(&ms.bar_x[s]), bar_in = smem_u32(&ms.bar_in[s]), bar_d = smem_u32(&ms.bar_d[s]);
     const uint32_t bar_head = smem_u32(&ms.bar_head[s]), bar_dzh = smem_u32(&ms.bar_dzh[s]), bar_gfree = smem_u32(&ms.bar_gfree[s]);
     const uint32_t bar_g0 = smem_u32(&ms.bar_g[s][0]), bar_g1 = smem_u32(&ms.bar_g[s][1]), bar_xfree = smem_u32(&ms.bar_xfree[s]);
     const uint32_t bar_wg = smem_u32(&ms.bar_wg[s]), bar_dread = smem_u32(&ms.bar_dread[s]), bar_in2 = smem_u32(&ms.bar_in2[s]);
-    const uint32_t P = s ? S_P1 : S_P0, Q = s ? S_Q1 : S_Q0, X = s ? S_X1 : S_X0, DZH = s ? S_DZH1 : S_DZH0;   // byte offsets
+    // ONE body serves both streams (the kernel's hot code must stay close to the instruction-cache size): the stream only enters
+    // through four per-stream bases, everything else is an immediate
+    constexpr uint32_t P = S_P0, Q = S_Q0, X = S_X0, DZH = S_DZH0;   // byte offsets of stream 0
+    static_assert(S_P1 - S_P0 == 32768 && S_Q1 - S_Q0 == 32768 && S_X1 - S_X0 == 8192 && S_DZH1 - S_DZH0 == 2048, "stream strides");
     const uint32_t D = tmem + C_D + 64 * s;
     const uint32_t i64kk = make_idesc_f16(128, 64, 0, 0), i64kt = make_idesc_f16(128, 64, 0, 1), i64tk = make_idesc_f16(128, 64, 1, 0),
                    i64tt = make_idesc_f16(128, 64, 1, 1), i16tk = make_idesc_f16(128, 16, 1, 0), i16kt = make_idesc_f16(128, 16, 0, 1),
@@ -169,19 +121,20 @@ __device__ __forceinline__ void issuer_loop(Misc& ms, uint32_t sbase, uint32_t t
         // occupy ~100 registers, rebuilt they are one uniform add each
         uint32_t sb = sbase >> 4;
         asm volatile("" : "+r"(sb));
+        const uint32_t sbA = sb + s * (32768u >> 4), sbX = sb + s * (8192u >> 4), sbZ = sb + s * (2048u >> 4), sbH = sb + s * (16384u >> 4);
         // operands (descriptor words); weights are rows = output features
         const Op aW0 = kmaj(sb, S_W0, 128), aW1 = kmaj(sb, S_W1, 128), aW2h = kmaj(sb, S_W2, 128),
                  aW2x = kmaj(sb, S_W2 + 32768, 128), aW3 = kmaj(sb, S_W3, 128);
         const Op aW1t = mnmaj(sb, S_W1, 128), aW2t = mnmaj(sb, S_W2, 128), aW3t = mnmaj(sb, S_W3, 128);
         const Op bWH = kmaj(sb, S_WH, 16), aWHt = mnmaj(sb, S_WH, 16);
-        const Op bXk = kmaj(sb, X, 64), bXt = mnmaj(sb, X, 64);
-        const Op bP = mnmaj(sb, P, 128), bQ = mnmaj(sb, Q, 128);     // [sample x feature] readers (forward / dgrad)
-        const Op aP = kmaj(sb, P, 128), aQ = kmaj(sb, Q, 128);       // [feature x sample] readers (wgrad)
-        const Op bP_lo = kmaj(sb, P, 128), bP_hi = kmaj(sb, P + 1024, 128);
+        const Op bXk = kmaj(sbX, X, 64), bXt = mnmaj(sbX, X, 64);
+        const Op bP = mnmaj(sbA, P, 128), bQ = mnmaj(sbA, Q, 128);   // [sample x feature] readers (forward / dgrad)
+        const Op aP = kmaj(sbA, P, 128), aQ = kmaj(sbA, Q, 128);     // [feature x sample] readers (wgrad)
+        const Op bP_lo = kmaj(sbA, P, 128), bP_hi = kmaj(sbA, P + 1024, 128);
         // head GEMM reads H3 as the M operand with samples on the rows: 128 rows are fetched, the tile's 64 samples
         // land on accumulator lanes 64 s .. 64 s + 63 (stream 1 starts one slot early), the other rows are ignored
-        const Op aQhead = mnmaj(sb, s ? Q - 16384 : Q, 128);
-        const Op bDZHt = mnmaj(sb, DZH, 64), bDZHk = kmaj(sb, DZH, 64);
+        const Op aQhead = mnmaj(sbH, Q, 128);                        // stream 1: Q1 - 16384 = Q0 + 16384
+        const Op bDZHt = mnmaj(sbZ, DZH, 64), bDZHk = kmaj(sbZ, DZH, 64);
         T2_WAIT(bar_x, ph_x);
         T2_ISSUE(gemm<XS>(D, aW0, bXk, i64kk, 0); tc_commit(bar_d););                                   // F0: H0
         T2_WAIT(bar_in, ph_in);
@@ -229,6 +182,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
     Misc& ms = *reinterpret_cast<Misc*>(smem + S_MISC);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wg = warp >> 2;
     const uint32_t sbase = smem_u32(smem);
+    if (p.debug && threadIdx.x == 0) p.debug[1024 + 4 * blockIdx.x] = gtimer();      // per-CTA lifetime (tools/hot_cold.py)
 
     if (warp == 12 && lane == 0) {
         mbar_init(smem_u32(&ms.bar_w), 1);
@@ -276,7 +230,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
     float* slab = p.slabs + (size_t)blockIdx.x * p.sm.total;
 
     if (wg == 3) {
-        TN_SETMAXNREG_DEC(24);
+        TN_SETMAXNREG_DEC(32);
         if (warp == 14 && lane == 0) {
             const uint32_t bar_w = smem_u32(&ms.bar_w);
             uint32_t total = 0;
@@ -291,13 +245,18 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                 }
             }
         }
-        if (warp == 12) issuer_loop<KX, 0>(ms, sbase, tmem, n_my[0], (p.debug && blockIdx.x == 0 && lane == 0) ? p.debug + 256 : nullptr);
-        if (warp == 13) issuer_loop<KX, 1>(ms, sbase, tmem, n_my[1], nullptr);
+#ifndef T2_ISSUER_SHARED        // one issuer body per stream: every offset is an immediate (3 % faster than one shared body)
+        if (warp == 12) issuer_loop<KX, 0>(ms, sbase, tmem, 0, n_my[0], (p.debug && blockIdx.x == 0 && lane == 0) ? p.debug + 256 : nullptr);
+        if (warp == 13) issuer_loop<KX, 1>(ms, sbase, tmem, 1, n_my[1], nullptr);
+#else
+        if (warp <= 13)
+            issuer_loop<KX, -1>(ms, sbase, tmem, warp - 12, n_my[warp - 12], (p.debug && blockIdx.x == 0 && warp == 12 && lane == 0) ? p.debug + 256 : nullptr);
+#endif
         __syncthreads();                                          // (A)
         __syncthreads();                                          // (B)
     } else if (wg == 2) {
         // ------------------------------ sample threads: warps 8-9 stream 0, warps 10-11 stream 1 ------------------------------
-        TN_SETMAXNREG_DEC(104);
+        TN_SETMAXNREG_DEC(96);
         const int s = (warp - 8) >> 1, wp = (warp - 8) & 1, i = wp * 32 + lane;
         const uint32_t Dh = tmem + ((uint32_t)((warp & 3) * 32) << 16) + C_D + 64 * s;
         uint8_t* X = smem + (s ? S_X1 : S_X0);
@@ -383,14 +342,16 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         float z_cur = 0.f, gap_cur = 0.f;
         long long* dbg = (p.debug && blockIdx.x == 0 && warp == 8 && lane == 0) ? p.debug + 512 : nullptr;
         int dbg_n = 0;
-        if (n_my[s] > 0) { encode(j0, z_cur, gap_cur); store_x(); }
-        for (long long t = 0; t < n_my[s]; ++t) {
+        // iteration t = -1 only encodes and stores the first tile: encode() and store_x() have ONE call site each (code size)
+#pragma unroll 1
+        for (long long t = -1; t < n_my[s]; ++t) {
             const long long tile = j0 + t * nstreams;
             const bool more = t + 1 < n_my[s];
             float z_next = 0.f, gap_next = 0.f;
             T2_STAMP();
             if (more) encode(tile + nstreams, z_next, gap_next);          // under the forward GEMMs of this tile
             T2_STAMP();
+            if (t >= 0) {
             // per-ray inputs of the loss are fetched before the heads are ready
             const long long ray = inphase ? (tile >> 1) : tile * p.R + i / S;
             const bool valid = ray < p.n_rays;
@@ -502,6 +463,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             }
             mbar_wait(bar_xfree, ph_xfree); ph_xfree ^= 1;       // last GEMM of the tile has completed: X may be replaced
             T2_STAMP();
+            }
             if (more) { store_x(); z_cur = z_next; gap_cur = gap_next; }
         }
         loss_acc = warp_sum(loss_acc);
@@ -541,82 +503,129 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         int dbg_n = 0;
         if (dbg) dbg[251] = gtimer();
 
-        auto drain_g = [&](uint32_t D, uint32_t free_bar) {     // the accumulator is released as soon as it has been read
-            uint32_t v[2][32];
-            tmem_ld32(D, v[0]);
-            tmem_ld32(D + 32, v[1]);
-            tc_wait_ld();
-            tc_fence_before();
-            mbar_arrive(free_bar);
+        // ---- the tile program of a drain warpgroup, as a rolled step machine: every drain body exists ONCE in the kernel image
+        //      (unrolled per step the kernel's hot code was ~75 KB per tile against a 32 KB instruction cache, and most SMs ran
+        //      20 % slower than the few that happened to hit).  Steps of one tile:
+        //        0-3  forward drains H0->P, H1->Q (+ parked in registers), H2->P, H3->Q
+        //        4    [staggered streams] the other stream's dW1 half: fixed rendezvous where this warpgroup would otherwise sleep
+        //             through its own compositing; keeps the streams half a tile apart, blocking waits only
+        //        5    head weight gradient (4 columns)          6  dZ3 over H3 (Q), bias gradient of layer 3
+        //        7    dZ2 over H2 (P) once dW3 has committed, H1 back into Q
+        //        8    dZ1 over H1 (Q) once dW2 has committed, bias gradient of layer 1; releases the accumulator early (H0 recompute)
+        //        9    recomputed H0 -> P                         10  dW1 halves (own; in-phase mode also the other stream's, see below)
+        //        11   dZ0 over H0 (P)
+        //      after the last tile: the other stream's remaining dW1 halves.
+        // In-phase mode (n_samples = 128, both streams in the same tile phase): the dW1 halves are drained where they are produced,
+        // in the order stream 0 first half (WG0), stream 0 second half (WG1) | stream 1 first half (WG0), stream 1 second half (WG1).
+        enum { K_FWD = 0, K_G = 1, K_SMALL = 2, K_BWD = 3 };
+#define T2_SIGNAL(bar) do { fence_proxy_async(); tc_fence_before(); mbar_arrive(bar); } while (0)
+#pragma unroll 1
+        for (long long t = 0; t <= n_my[s]; ++t) {
+            const bool tail = t == n_my[s];
+#pragma unroll 1
+            for (int step = tail ? 10 : 0; step < 12; ++step) {
+                const int kind = (step == 4 || step == 10) ? K_G : (step == 5) ? K_SMALL : (step <= 3 || step == 9) ? K_FWD : K_BWD;
+                uint8_t* slot = ((0x14A >> step) & 1) ? Q : P;          // Q for steps 1, 3, 6, 8
+                if (tail && step == 11) break;
+                if (kind == K_G) {
+                    // job list: bit j of `own_mask` = job j drains this stream's accumulator, else the other stream's
+                    int njobs = 0, own_mask = 0;
+                    if (tail) njobs = (int)(g_oth_left > 2 ? 2 : g_oth_left);                       // (re-entered below until none are left)
+                    else if (step == 4) njobs = (!inphase && (s == 1 || t >= 1) && g_oth_left > 0) ? 1 : 0;
+                    else if (!inphase) { njobs = 1; own_mask = 1; }
+                    else { njobs = g_oth_left > 0 ? 2 : 1; own_mask = (njobs == 1) ? 1 : (s == 0 ? 1 : 2); }
+#pragma unroll 1
+                    for (int j = 0; j < njobs; ++j) {
+                        const bool own = (own_mask >> j) & 1;
+                        const uint32_t bar = own ? bar_g_own : bar_g_oth;
+                        uint32_t& ph = own ? ph_g_own : ph_g_oth;
+                        T2_STAMP();
+                        mbar_wait(bar, ph);
+                        ph ^= 1;
+                        tc_fence_after();
+                        T2_STAMP();
+                        const uint32_t D = own ? D_own : D_oth;
+                        uint32_t v[2][32];
+                        tmem_ld32(D, v[0]);
+                        tmem_ld32(D + 32, v[1]);
+                        tc_wait_ld();
+                        tc_fence_before();
+                        mbar_arrive(own ? bar_gfree_own : bar_gfree_oth);     // the accumulator is released as soon as it has been read
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
+                        for (int c = 0; c < 2; ++c)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) dw1[c * 32 + j] += __uint_as_float(v[c][j]);
-        };
-        // The other stream's dW1 half is drained at a fixed point of this stream's tile: right after the layer-3 drain, where
-        // this warpgroup would otherwise sleep through its own compositing.  The rendezvous keeps the two streams about
-        // half a tile apart (one stream's backward GEMMs run under the other's compositing); blocking waits only.
-        auto service = [&]() {
-            T2_STAMP();
-            mbar_wait(bar_g_oth, ph_g_oth);
-            tc_fence_after();
-            T2_STAMP();
-            drain_g(D_oth, bar_gfree_oth);
-            ph_g_oth ^= 1;
-            --g_oth_left;
-        };
-        auto wait_poll = [&](uint32_t bar, uint32_t& ph) {
-            T2_STAMP();
-            mbar_wait(bar, ph);
-            ph ^= 1;
-            tc_fence_after();
-            T2_STAMP();
-        };
-#define T2_SIGNAL() do { fence_proxy_async(); tc_fence_before(); mbar_arrive(bar_in); } while (0)
-
-        for (long long t = 0; t < n_my[s]; ++t) {
-            wait_poll(bar_d, ph_d); drain_fwd<false>(D_own, P, f, 0.f, stash); T2_SIGNAL();      // H0 -> P
-            wait_poll(bar_d, ph_d); drain_fwd<true>(D_own, Q, f, b1, stash); T2_SIGNAL();        // H1 -> Q (+ registers)
-            wait_poll(bar_d, ph_d); drain_fwd<false>(D_own, P, f, 0.f, stash); T2_SIGNAL();      // H2 -> P
-            wait_poll(bar_d, ph_d); drain_fwd<false>(D_own, Q, f, b3, stash); T2_SIGNAL();       // H3 -> Q
-            if (!inphase && (s == 1 || t >= 1) && g_oth_left > 0) service();                     // stream 1: tile t of stream 0; stream 0: tile t-1 of stream 1
-            wait_poll(bar_d, ph_d);                                                              // head wgrad
-            {
-                uint32_t v[4];
-                tmem_ld4(D_own + 16, v);
-                tc_wait_ld();
+                            for (int i = 0; i < 32; ++i) dw1[c * 32 + i] += __uint_as_float(v[c][i]);
+                        if (!own) --g_oth_left;
+                    }
+                    if (tail && g_oth_left > 0) --step;                                              // stay in the tail step
+                    continue;
+                }
+                T2_STAMP();
+                mbar_wait(bar_d, ph_d);
+                ph_d ^= 1;
+                tc_fence_after();
+                T2_STAMP();
+                if (kind == K_FWD) {
+                    const bool biased = step == 1 || step == 3;       // layers 1 / 3: fp32 bias added here (uniform branch: no cost elsewhere)
+                    const float bias = (step == 1) ? b1 : b3;
+                    const bool park = step == 1;
+                    uint32_t va[2][32];
+                    tmem_ld32(D_own, va[0]);
+                    tc_wait_ld();
+                    tmem_ld32(D_own + 32, va[1]);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) dwh[k] += __uint_as_float(v[k]);
+                    for (int c = 0; c < 2; ++c) {
+                        if (c == 1) tc_wait_ld();
+                        uint32_t (&v)[32] = va[c];
+                        if (biased) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + bias);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 o;
+                            o.x = pack_relu_h2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                            o.y = pack_relu_h2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                            o.z = pack_relu_h2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                            o.w = pack_relu_h2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                            *reinterpret_cast<uint4*>(slot + ((size_t)((c * 4 + j) * 128 + f) << 4)) = o;
+                            if (park) { stash[(c * 4 + j) * 4 + 0] = o.x; stash[(c * 4 + j) * 4 + 1] = o.y; stash[(c * 4 + j) * 4 + 2] = o.z; stash[(c * 4 + j) * 4 + 3] = o.w; }
+                        }
+                    }
+                    T2_SIGNAL(bar_in);
+                } else if (kind == K_SMALL) {
+                    uint32_t v[4];
+                    tmem_ld4(D_own + 16, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) dwh[k] += __uint_as_float(v[k]);
+                    T2_SIGNAL(bar_in);
+                } else {
+                    // dZ = dH * (H > 0): computed into registers while the weight-gradient GEMM that still reads the slot runs,
+                    // stored once that GEMM has committed (steps 7, 8); steps 6 and 11 store at once
+                    uint32_t o[32];
+                    drain_bwd_compute<false>(D_own, slot, f, o, step == 8 ? bar_dread : 0u);
+                    if (step == 6 || step == 8) {                     // bias gradient of layer 3 / 1 = row sum of dZ3 / dZ1
+                        float sum = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) sum += (h2sum(o[i]) + h2sum(o[i + 1])) + (h2sum(o[i + 2]) + h2sum(o[i + 3]));
+                        if (step == 6) db3 += sum; else db1 += sum;
+                    }
+                    if (step == 7 || step == 8) { T2_STAMP(); mbar_wait(bar_wg, ph_wg); ph_wg ^= 1; T2_STAMP(); }
+                    drain_store(slot, f, o);
+                    if (step == 7) drain_store(Q, f, stash);                                         // H1 back into Q (dZ3 is dead)
+                    T2_SIGNAL(step == 8 ? bar_in2 : bar_in);
+                }
             }
-            T2_SIGNAL();
-            wait_poll(bar_d, ph_d); db3 += drain_bwd<true>(D_own, Q, f); T2_SIGNAL();            // dZ3 over H3 (Q)
-            {
-                uint32_t o[32];
-                wait_poll(bar_d, ph_d); drain_bwd_compute<false>(D_own, P, f, o, 0u);                // dZ2 = dH2 * (H2 > 0), in registers
-                wait_poll(bar_wg, ph_wg);                                                            // dW3 GEMM no longer reads H2 / dZ3
-                drain_store(P, f, o);                                                                // dZ2 over H2 (P)
-                drain_store(Q, f, stash);                                                            // H1 back into Q (dZ3 is dead)
-                T2_SIGNAL();
-                wait_poll(bar_d, ph_d); db1 += drain_bwd_compute<true>(D_own, Q, f, o, bar_dread);   // dZ1 = dH1 * (H1 > 0)
-                wait_poll(bar_wg, ph_wg);                                                            // dW2 GEMMs no longer read H1 / dZ2
-                drain_store(Q, f, o);                                                                // dZ1 over H1 (Q)
-                fence_proxy_async(); tc_fence_before(); mbar_arrive(bar_in2);
-            }
-            wait_poll(bar_d, ph_d); drain_fwd<false>(D_own, P, f, 0.f, stash); T2_SIGNAL();      // H0 -> P (dZ2 is dead)
-            // in-phase mode (n_samples = 128, both streams in the same tile phase): the dW1 halves are drained where they are
-            // produced, in the order stream 0 first half (WG0), stream 0 second half (WG1) | stream 1 first half (WG0), stream 1 second half (WG1)
-            if (inphase && s == 1 && g_oth_left > 0) service();
-            wait_poll(bar_g_own, ph_g_own); drain_g(D_own, bar_gfree_own);
-            if (inphase && s == 0 && g_oth_left > 0) service();
-            wait_poll(bar_d, ph_d); drain_bwd<false>(D_own, P, f); T2_SIGNAL();                  // dZ0 over H0 (P)
         }
-        while (g_oth_left > 0) service();
 #undef T2_SIGNAL
         if (dbg) dbg[253] = clock64();
+        if (p.debug && threadIdx.x == 0) p.debug[1025 + 4 * blockIdx.x] = gtimer();
         tc_fence_before();
         __syncthreads();                                          // (A)
         tc_fence_after();
         if (dbg) dbg[254] = clock64();
+        if (p.debug && threadIdx.x == 0) p.debug[1026 + 4 * blockIdx.x] = gtimer();
         // ---- flush this CTA's weight-gradient slab (coalesced: consecutive rows) ----
         auto flush_tmem = [&](int tcol, int ncols, int off) {
             for (int c0 = 0; c0 < ncols; c0 += 16) {
@@ -649,6 +658,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
     }
     __syncthreads();                                              // (C)
     if (warp == 0) tmem_dealloc(tmem, 512);
+    if (p.debug && threadIdx.x == 0) p.debug[1027 + 4 * blockIdx.x] = gtimer();
 }
 
 }  // namespace t2

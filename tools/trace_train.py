@@ -23,7 +23,7 @@ pose = torch.eye(4, device=dev); pose[2, 3] = 4.0
 pix = torch.randint(0, 10000, (n,), device=dev)
 target = torch.rand(n, 3, device=dev)
 u = torch.rand(n, S, device=dev)
-dbg = torch.zeros(1024, dtype=torch.int64, device=dev)
+dbg = torch.zeros(2048, dtype=torch.int64, device=dev)
 h = E.handle_for(model, dev)
 for it in range(3):
     dbg.zero_()
