@@ -14,7 +14,7 @@ from typing import List, Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtnerf.so")
+LIB_PATH = os.environ.get("TNERF_LIB") or os.path.join(_HERE, "libtnerf.so")      # TNERF_LIB: developer override (A/B builds)
 
 PREC_F16_TC = 0
 PREC_F32_SIMT = 1
