@@ -44,6 +44,7 @@ struct tnerf_handle {
     // tensor-core path
     void* packed = nullptr; size_t packed_bytes = 0;   // fp16 operand image (device)
     void* slabs = nullptr;  size_t slab_bytes = 0;     // per-CTA partial weight gradients
+    bool slab0_zero = false;                           // slab 0 is all zeros (it is the accumulation target of the bulk-reduction mode)
     int sm_count = 0;
     bool fused_ok = false;
     int num_freqs = 0;                    // (in_dim-3)/6 when in_dim = 3+6L

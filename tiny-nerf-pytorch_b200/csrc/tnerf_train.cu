@@ -332,6 +332,7 @@ __global__ void reduce_slabs_kernel(ReduceArgs a) {
     if (e >= a.sm.total) return;
     float s = 0.f;
     for (int i = 0; i < a.n_slabs; ++i) s += a.slabs[(size_t)i * a.sm.total + e];
+    if (a.zero_after) const_cast<float*>(a.slabs)[e] = 0.f;
     s *= a.scale_dev ? 1.f / *a.scale_dev : a.inv_scale;
     long long dst = -1;
     const int fan2 = 128 + a.D;
@@ -509,15 +510,22 @@ int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, flo
         cudaError_t e = cudaMalloc(&h->slabs, need);
         if (e != cudaSuccess) { set_error("cudaMalloc(gradient slabs) failed"); h->slabs = nullptr; h->slab_bytes = 0; return (int)e; }
         h->slab_bytes = need;
+        cudaMemsetAsync(h->slabs, 0, need, s);      // slab 0 doubles as the bulk-reduction target: zero on entry, cleared by the scatter kernel
+        h->slab0_zero = true;
     }
     p.slabs = reinterpret_cast<float*>(h->slabs);
     long long grid;
     static const bool force_v1 = getenv("TNERF_TRAIN_V1") != nullptr;
+    static const bool bulk = getenv("TNERF_BULK_REDUCE") != nullptr && atoi(getenv("TNERF_BULK_REDUCE")) != 0;
+    bool used_bulk = false;
     if ((64 % S == 0 || S == 128) && !force_v1) {
         // two-stream kernel (tnerf_train2.cu): 64-sample tiles; at 128 samples the two streams of a CTA carry the two halves of one ray
         if (S == 128) { p.R = 1; p.n_tiles = 2 * n; }
         else { p.R = 64 / S; p.n_tiles = (n + p.R - 1) / p.R; }
         grid = (p.n_tiles + 1) / 2 < h->sm_count ? (p.n_tiles + 1) / 2 : h->sm_count;
+        p.bulk_reduce = bulk ? 1 : 0;
+        used_bulk = bulk;
+        if (bulk && !h->slab0_zero) cudaMemsetAsync(h->slabs, 0, (size_t)sm.total * sizeof(float), s);
         if (int rc = fused_train2(h, fp, p, Kx, (int)grid, s)) return rc;
     } else {
         grid = p.n_tiles < h->sm_count ? p.n_tiles : h->sm_count;
@@ -528,8 +536,9 @@ int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, flo
         kern<<<(unsigned)grid, TR_THREADS, smem, s>>>(p, tp);
         if (int rc = count_launch()) return rc;
     }
+    h->slab0_zero = used_bulk;          // the scatter kernel leaves slab 0 cleared in bulk mode; otherwise it holds a CTA's partial sums
     ReduceArgs ra{};
-    ra.slabs = p.slabs; ra.n_slabs = (int)grid; ra.sm = sm; ra.D = fp.D; ra.Kx = Kx; ra.inv_scale = 1.f / p.scale; ra.scale_dev = p.scale_dev; ra.grads = grads;
+    ra.slabs = p.slabs; ra.n_slabs = used_bulk ? 1 : (int)grid; ra.zero_after = used_bulk ? 1 : 0; ra.sm = sm; ra.D = fp.D; ra.Kx = Kx; ra.inv_scale = 1.f / p.scale; ra.scale_dev = p.scale_dev; ra.grads = grads;
     for (int l = 0; l < 4; ++l) { ra.off_w[l] = h->offsets[2 * l]; ra.off_b[l] = h->offsets[2 * l + 1]; }
     ra.off_ws = h->offsets[8]; ra.off_bs = h->offsets[9]; ra.off_wc = h->offsets[10]; ra.off_bc = h->offsets[11];
     reduce_slabs_kernel<<<(sm.total + 255) / 256, 256, 0, s>>>(ra);

@@ -25,6 +25,7 @@ struct TrainParams {
     // two-stream kernel only: fp32 biases added in the accumulator drains (layers 1, 3) and by the compositing warps (heads)
     const float *b1, *b3, *b_sigma, *b_rgb;
     long long* debug;          // optional clock64 phase stamps of CTA 0 (tools/trace_train.py)
+    int bulk_reduce;           // two-stream kernel: add the CTA's gradients into ONE vector (slabs[0 .. sm.total)) with bulk async reductions
 };
 
 __device__ __forceinline__ uint32_t pack_sat_h2(float a, float b) {
@@ -157,6 +158,7 @@ struct ReduceArgs {
     float inv_scale;
     const float* scale_dev;
     float* grads;
+    int zero_after;            // clear the (single) slab after reading: it is the accumulation target of the next launch
 };
 int fused_train2(tnerf_handle* h, const FusedPlan& fp, const TrainParams& p, int Kx, int grid, cudaStream_t s);   // tnerf_train2.cu
 

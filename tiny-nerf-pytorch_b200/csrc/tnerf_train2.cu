@@ -473,7 +473,10 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         __syncthreads();                                          // (A) every GEMM of both streams has completed
         if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) slab[p.sm.hb + (warp - 8) * 4 + k] = hb[k];
+            for (int k = 0; k < 4; ++k) {
+                if (p.bulk_reduce) atomicAdd(p.slabs + p.sm.hb + (warp - 8) * 4 + k, hb[k]);
+                else slab[p.sm.hb + (warp - 8) * 4 + k] = hb[k];
+            }
             if (p.loss_sum && loss_acc != 0.f) atomicAdd(p.loss_sum, loss_acc);
         }
         __syncthreads();                                          // (B)
@@ -626,6 +629,57 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         tc_fence_after();
         if (dbg) dbg[254] = clock64();
         if (p.debug && threadIdx.x == 0) p.debug[1026 + 4 * blockIdx.x] = gtimer();
+        if (p.bulk_reduce) {
+            // ---- add this CTA's weight gradients into the ONE global vector: 32-column chunks (16 KB) are staged in the now idle
+            //      activation slots and handed to the bulk-copy engine as reductions (cp.reduce.async.bulk .add.f32: the adds run
+            //      in L2, no 39 MB of slabs, no reduce kernel).  Two staging halves per warpgroup; the issuing thread waits for
+            //      the engine to have READ a half before it is refilled. ----
+            float* G = p.slabs;
+            float* stage = reinterpret_cast<float*>(smem + (s ? S_P1 : S_P0));       // P and Q slot of this stream: 2 x 16 KB
+            const bool issuer_thread = (warp & 3) == 0 && lane == 0;
+            int nchunk = 0;
+            auto begin_chunk = [&]() -> float* {
+                if (nchunk >= 2) { if (issuer_thread) bulk_wait_group_read<1>(); bar_sync(4 + s, 128); }
+                return stage + (nchunk & 1) * 4096;
+            };
+            auto end_chunk = [&](int off, int ncols) {
+                fence_proxy_async();
+                bar_sync(4 + s, 128);
+                if (issuer_thread) { bulk_reduce_add_f32(G + off, smem_u32(stage + (nchunk & 1) * 4096), (uint32_t)ncols * 512u); bulk_commit_group(); }
+                ++nchunk;
+            };
+            auto push_tmem = [&](int tcol, int ncols, int off) {           // ncols is a multiple of 16
+                for (int c0 = 0; c0 < ncols; c0 += 32) {
+                    const int nc = ncols - c0 < 32 ? ncols - c0 : 32;
+                    float* st = begin_chunk();
+                    for (int c1 = 0; c1 < nc; c1 += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(tl + tcol + c0 + c1, v);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) st[(c1 + k) * 128 + f] = __uint_as_float(v[k]);
+                    }
+                    end_chunk(off + c0 * 128, nc);
+                }
+            };
+            if (s == 0) { push_tmem(C_DW3, 128, p.sm.dw3); push_tmem(C_DW0, KX, p.sm.dw0); }
+            else push_tmem(C_DW2, 128 + KX, p.sm.dw2);
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                float* st = begin_chunk();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) st[j * 128 + f] = dw1[h2 * 32 + j];
+                end_chunk(p.sm.dw1 + (64 * s + 32 * h2) * 128, 32);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) atomicAdd(G + p.sm.dwh + k * 128 + f, dwh[k]);
+            atomicAdd(G + p.sm.db1 + f, db1);
+            atomicAdd(G + p.sm.db3 + f, db3);
+            if (issuer_thread) bulk_wait_group<0>();
+            __syncthreads();                                      // (B)
+            if (dbg) { dbg[255] = clock64(); dbg[252] = gtimer(); }
+            tc_fence_before();
+        } else {
         // ---- flush this CTA's weight-gradient slab (coalesced: consecutive rows) ----
         auto flush_tmem = [&](int tcol, int ncols, int off) {
             for (int c0 = 0; c0 < ncols; c0 += 16) {
@@ -655,6 +709,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         }
         if (dbg) { dbg[255] = clock64(); dbg[252] = gtimer(); }
         tc_fence_before();
+        }
     }
     __syncthreads();                                              // (C)
     if (warp == 0) tmem_dealloc(tmem, 512);
