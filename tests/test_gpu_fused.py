@@ -69,6 +69,11 @@ def test_umma_selftest(dev, mode, NK):
     dict(cfg=(63, 128, 3, 1), S=128, n=65, jitter=True, scale=2.0),
     dict(cfg=(63, 128, 5, 0), S=96, n=50, jitter=True, scale=1.5),
     dict(cfg=(60, 128, 2, 1), S=16, n=200, jitter=True, scale=2.0),
+    # wide model of BASELINE config 4 (hidden 256): CTA-pair tcgen05 kernel on the f16 path
+    dict(cfg=(63, 256, 4, 2), S=192, n=301, jitter=False, scale=1.5),
+    dict(cfg=(63, 256, 4, 2), S=64, n=1000, jitter=True, scale=1.5),
+    dict(cfg=(39, 256, 4, 2), S=32, n=3, jitter=True, scale=1.5),
+    dict(cfg=(63, 256, 4, 2), S=96, n=1, jitter=True, scale=1.0),
 ])
 def test_fused_render_vs_oracle(dev, prec, case):
     import engine

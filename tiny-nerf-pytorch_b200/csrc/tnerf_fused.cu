@@ -594,9 +594,10 @@ bool build_repack_map(const tnerf_handle* h, RepackMap& mp) {
     return true;
 }
 
-bool fused_shape_supported(const tnerf_handle* h) { FusedPlan pl; return build_plan(h, pl); }
+bool fused_shape_supported(const tnerf_handle* h) { FusedPlan pl; return build_plan(h, pl) || wide_shape_supported(h); }
 
 int fused_pack_weights(tnerf_handle* h, cudaStream_t s) {
+    if (wide_shape_supported(h)) return wide_pack_weights(h, s);
     FusedPlan pl;
     if (!build_plan(h, pl)) { set_error("fused path: unsupported MLP shape (need hidden=128, in_dim=6L(+3)<=63, depth<=8)"); return -2; }
     if (h->params.empty()) { set_error("pack_weights: parameters not bound"); return -3; }
@@ -621,6 +622,7 @@ static long long gcd_ll(long long a, long long b) { while (b) { long long t = a 
 int fused_render_fwd(tnerf_handle* h, const RaySource& rs, long long n, float nr, float fr, int S, const float* jitter, int white,
                      float* comp, float* depth, float* acc, float* weights, float* rays_d_out, cudaStream_t s) {
     if (n <= 0) return 0;
+    if (wide_shape_supported(h)) return fused_render_fwd_wide(h, rs, n, nr, fr, S, jitter, white, comp, depth, acc, weights, rays_d_out, s);
     FwdParams p{};
     if (!build_plan(h, p.plan)) { set_error("fused path: unsupported MLP shape"); return -2; }
     if (!h->packed) { set_error("fused path: tnerf_pack_weights has not been called"); return -3; }

@@ -82,6 +82,11 @@ int fused_render_fwd(tnerf_handle* h, const RaySource& rs, long long n, float nr
 int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, float fr, int S, const float* jitter, int white,
                 const float* target, float loss_denom, const float* gC, const float* gD, const float* gA, const float* gW,
                 float grad_scale, const float* grad_scale_dev, float* comp, float* loss_sum, float* grads, cudaStream_t s);
+// wide MLP (hidden = 256) on CTA pairs (tnerf_fused_wide.cu)
+bool wide_shape_supported(const tnerf_handle* h);
+int wide_pack_weights(tnerf_handle* h, cudaStream_t s);
+int fused_render_fwd_wide(tnerf_handle* h, const RaySource& rs, long long n, float nr, float fr, int S, const float* jitter, int white,
+                          float* comp, float* depth, float* acc, float* weights, float* rays_d_out, cudaStream_t s);
 int umma_rate(int n, int reps, int variant, long long* out, cudaStream_t s);
 int umma_selftest(const float* a, const float* b, int n, int k, int mode, float* d, cudaStream_t s);
 }  // namespace tnerf

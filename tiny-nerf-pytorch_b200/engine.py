@@ -90,13 +90,15 @@ def fused_supported(module, encoder, S: int, device) -> bool:
         except RuntimeError:
             return False
     g = math.gcd(int(S), 128)
+    if module.hidden == 256:          # wide model (BASELINE config 4): CTA-pair kernel, whole 32-sample chunks per warp
+        return h.fused_ok and S % 32 == 0 and S // g <= 8
     return h.fused_ok and module.hidden == 128 and S // g <= 8
 
 
 def train_supported(module, encoder, S: int, device) -> bool:
     """the tensor-core fused backward covers the reference MLP (depth 4, skip after layer 1, hidden 128) and
     ray tiles of whole rays (n_samples divides 128); everything else takes the fp32 path"""
-    return (fused_supported(module, encoder, S, device) and module.depth == 4 and module.skip_at == 2
+    return (fused_supported(module, encoder, S, device) and module.hidden == 128 and module.depth == 4 and module.skip_at == 2
             and 1 <= int(S) <= 128 and 128 % int(S) == 0)
 
 
@@ -129,6 +131,8 @@ def render_weights(model, ro, o_stride, rd, n, S, near, far, jitter, white, prec
     """The (N,S) compositing weights of a fused render (the 4th value of volume_render), recomputed on demand."""
     dev = rd.device
     h = E.handle_for(model, dev)
+    if prec == E.PREC_F16_TC and model.hidden != 128:
+        prec = E.PREC_F32_SIMT        # the wide kernel does not write per-sample weights
     if prec == E.PREC_F16_TC:
         h.ensure_packed()
     comp = torch.empty((n, 3), dtype=torch.float32, device=dev)
