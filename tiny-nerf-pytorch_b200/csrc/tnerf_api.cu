@@ -193,6 +193,7 @@ int tnerf_create(tnerf_handle** out, int device, int in_dim, int hidden, int dep
 }
 void tnerf_destroy(tnerf_handle* h) {
     if (!h) return;
+    wide_release(h);
     h->ws.release();
     if (h->packed) cudaFree(h->packed);
     if (h->slabs) cudaFree(h->slabs);

@@ -15,22 +15,35 @@
 //     the first twelve K-steps of a layer's first quarter only need quarters 0-2 of the previous layer and are issued while
 //     quarter 3 is still in its epilogue: the tensor pipe never waits for a whole layer to drain;
 //   * biases of layers 0/2 ride on the encoding's constant-1 column, those of layers 1/3 are added in fp32 by the epilogue;
-//   * the two heads (sigma, rgb: 4 x 256) are evaluated in fp32 FMAs by the epilogue of layer 3 straight from its registers
-//     (no fp16 rounding of the last activations, no head GEMM, no shared memory for head weights);
+//   * the two heads (sigma, rgb: 4 x 256) are one more pair-MMA (N = 32, 4 useful columns).  Only 3 KB of shared memory are
+//     left beside the weights, so the head operand is stored with OVERLAPPING core matrices: 4 rows of 16 B per K-octet
+//     (64 B apart instead of 128), the 8-row-group stride is 0.  Rows 4-7 / 8-15 of the operand then alias real head weights
+//     of other K-octets (finite garbage in accumulator columns nobody reads); 2.1 KB instead of 8 KB;
+//   * the biases of layers 1/3 and of the heads sit in the CONSTANT bank (uniform-register operands of the epilogue's adds);
 //   * rays, depths, Fourier features and compositing run in a separate sample warpgroup, as in tnerf_fused_fast.cu.
 //
-// Tensor memory per CTA (columns): ACC0 0-63, ACC1 64-127, P 128-255, Q 256-383, X 384-415, HEAD 416-419.
-// Warps per CTA: 0-3 epilogue, 4-7 samples, 8 weight loader + (leader CTA only) MMA issuer (9-11 idle: setmaxnreg is per warpgroup).
+// Tensor memory per CTA (columns): ACC0 0-63, ACC1 64-127, P 128-255, Q 256-383, X 384-415, HEAD 416-447.
+// Warps per CTA: 0-7 epilogue (warp w: lanes 32(w%4).., columns 32(w/4).. of each 64-column quarter), 8-11 samples,
+// 12 weight loader + (leader CTA only) MMA issuer (13-15 idle: setmaxnreg is per warpgroup).
 // Cross-CTA signalling: "operand ready" barriers live in the leader CTA and collect one arrival per warp of BOTH CTAs
 // (remote mbarrier arrive); MMA completion is multicast to the same barrier in both CTAs by tcgen05.commit.
+#include <mutex>
+#include <type_traits>
 #include "tnerf_fused.cuh"
 
 namespace tnerf {
 namespace wide {
 
-constexpr int THREADS = 384;      // warps 9-11 exist only so that warp 8's warpgroup can take part in the register re-distribution
+constexpr int THREADS = 512;      // warps 13-15 exist only so that warp 12's warpgroup can take part in the register re-distribution
 constexpr int C_ACC = 0, C_P = 128, C_Q = 256, C_X = 384, C_HEAD = 416;
-constexpr int MAX_CHUNKS = 32;
+constexpr uint32_t HEAD_BYTES = 2112;   // 32 K-octets x 64 B + the 64 B the last overlapping core matrix reaches into
+constexpr int TAIL_FLOATS = 1540;
+// b1[256], b3[256], head weights [256][4] (sigma, r, g, b), head biases [4] of the model whose kernel runs next on this device:
+// compile-time offsets, so every bias / head weight is a constant-bank OPERAND of an FADD / FFMA (no load instruction at all).
+// The host re-uploads the table (stream ordered, behind an event of the last kernel that used it) when another handle or a
+// re-packed model comes along.
+__constant__ float c_tail[TAIL_FLOATS];
+constexpr int MAX_CHUNKS = 16;
 
 struct Params {
     RaySource rs;
@@ -40,7 +53,6 @@ struct Params {
     const float* jitter;
     float *comp, *depth, *acc, *rays_d_out;
     const uint8_t* image;      // [2 CTA ranks][image_bytes] fp16 operand slices, then the fp32 tail
-    const float* tail;         // b1[256], b3[256], head weights [256][4] (sigma, r, g, b), head biases [4]
     uint32_t image_bytes;
     int L, include_input;
     long long* debug;
@@ -59,7 +71,9 @@ __host__ __device__ constexpr uint32_t w_off(int l, int q) {
     return l == 0 ? q * s0 : l == 1 ? 4 * s0 + q * s1 : l == 2 ? 4 * (s0 + s1) + q * s2 : 4 * (s0 + s1 + s2) + q * s1;
 }
 template <int KX>
-__host__ __device__ constexpr uint32_t image_bytes_of() { return 4u * (KX * 64u + 16384u + (256u + KX) * 64u + 16384u); }
+__host__ __device__ constexpr uint32_t main_bytes_of() { return 4u * (KX * 64u + 16384u + (256u + KX) * 64u + 16384u); }
+template <int KX>
+__host__ __device__ constexpr uint32_t image_bytes_of() { return main_bytes_of<KX>() + HEAD_BYTES; }
 
 // ---- pair / cluster primitives ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -90,7 +104,7 @@ __device__ __forceinline__ void tc_commit2(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t rank) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
         "r"(rank)
         : "memory");
 }
@@ -98,10 +112,14 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0,%1,%2,%3};" ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(taddr) : "memory");
@@ -111,6 +129,7 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4])
 // Per CTA rank r, layer l, quarter q: B slice [K x 32] of features 64q + 32r + n, K-major canonical (R = 32 rows):
 // element (n, k) at ((k/8)*32 + n)*8 + k%8.  K order: layer 0 = encoding (constant-1 column KX-1 carries the bias);
 // layer 2 = 256 activations, then the encoding (same bias convention); layers 1, 3 = 256 activations.
+// Then the head operand: element (n < 4, k) at byte (k/8)*64 + n*16 + (k%8)*2 (n = 0 sigma, 1..3 rgb).
 struct PackArgs {
     const float* W[4]; const float* b[4];
     const float *Wsig, *bsig, *Wrgb, *brgb;
@@ -125,6 +144,14 @@ __global__ void pack_wide_kernel(PackArgs a, uint8_t* __restrict__ out) {
         long long loc = e - r * halfs;
         const int KX = a.KX;
         const long long s0 = KX * 32, s1 = 8192, s2 = (256 + KX) * 32;
+        const long long main_halfs = 4 * (s0 + s1 + s2 + s1);
+        if (loc >= main_halfs) {
+            const int byte = (int)(loc - main_halfs) * 2, ko = byte / 64, n = (byte % 64) / 16, k = ko * 8 + (byte % 16) / 2;
+            float v = 0.f;
+            if (ko < 32) v = n == 0 ? a.Wsig[k] : a.Wrgb[(n - 1) * 256 + k];
+            reinterpret_cast<__half*>(out)[e] = __float2half_rn(v);
+            return;
+        }
         int l, q;
         if (loc < 4 * s0) { l = 0; q = (int)(loc / s0); loc -= q * s0; }
         else if ((loc -= 4 * s0) < 4 * s1) { l = 1; q = (int)(loc / s1); loc -= q * s1; }
@@ -151,7 +178,6 @@ __global__ void pack_wide_kernel(PackArgs a, uint8_t* __restrict__ out) {
         else if (t < 1540) { const int c = (int)(t - 1536); tail[t] = c == 0 ? a.bsig[0] : a.brgb[c - 1]; }
     }
 }
-constexpr int TAIL_FLOATS = 1540;
 
 // -DWIDE_DEBUG_WAITS: every barrier wait is bounded; a wait that times out records (site, parity) of the first failure of its
 // warp at debug[512 + (blockIdx.x*9 + warp)*2] and FALLS THROUGH, so a protocol bug yields a finished kernel and a trace
@@ -167,7 +193,7 @@ __device__ __forceinline__ void dbg_wait(uint32_t bar, uint32_t parity, long lon
         if (++n > budget) break;
     }
     if (debug && (threadIdx.x & 31) == 0 && blockIdx.x < 16) {
-        long long* slot = debug + 512 + (blockIdx.x * 9 + min((int)(threadIdx.x >> 5), 8)) * 2;
+        long long* slot = debug + 512 + (blockIdx.x * 13 + min((int)(threadIdx.x >> 5), 12)) * 2;
         if (slot[0] == 0) { slot[0] = site; slot[1] = parity; }
     }
     budget = 64;
@@ -203,13 +229,13 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128) fused_fwd_wide_kernel
     const uint32_t bar_e0 = smem_u32(&sm.bar_e[0]), bar_e1 = smem_u32(&sm.bar_e[1]);
     const uint32_t bar_acc0 = smem_u32(&sm.bar_acc[0]), bar_acc1 = smem_u32(&sm.bar_acc[1]);
 
-    if (warp == 8 && lane == 0) {
+    if (warp == 12 && lane == 0) {
         mbar_init(bar_w, 1);
         mbar_init(bar_x, 8);            // one arrival per sample warp of both CTAs (leader's copy is the one waited on)
-        mbar_init(bar_e0, 8); mbar_init(bar_e1, 8);
+        mbar_init(bar_e0, 16); mbar_init(bar_e1, 16);       // one per epilogue warp of both CTAs
         mbar_init(bar_acc0, 1); mbar_init(bar_acc1, 1);
         mbar_init(bar_xfree, 1);
-        mbar_init(bar_head, 4); mbar_init(bar_hfree, 4);
+        mbar_init(bar_head, 1); mbar_init(bar_hfree, 8);    // head MMA commit; one arrival per sample warp of both CTAs
         fence_barrier_init();
     }
     if (warp == 0) { tmem_alloc2(smem_u32(&sm.tmem_slot), 512); tmem_relinquish2(); }
@@ -224,10 +250,10 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128) fused_fwd_wide_kernel
     // number of tiles (a CTA whose unit does not exist processes empty rows)
     const long long u_first = 2 * pair, u_stride = 2 * n_pairs;
 
-    if (warp >= 8) {
-        // ------------------------------ weight loader (both CTAs) + MMA issuer (leader): warp 8 ------------------------------
-        TN_SETMAXNREG_DEC(56);           // executed by the whole warpgroup (warps 8-11)
-        if (warp == 8) {
+    if (warp >= 12) {
+        // ------------------------------ weight loader (both CTAs) + MMA issuer (leader): warp 12 ------------------------------
+        TN_SETMAXNREG_DEC(56);           // executed by the whole warpgroup (warps 12-15)
+        if (warp == 12) {
         if (lane == 0) {
             mbar_expect_tx(bar_w, IMG);
             const uint8_t* src = p.image + (size_t)rank * IMG;
@@ -243,8 +269,11 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128) fused_fwd_wide_kernel
             const uint32_t hi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
             const uint32_t lbo = (512u >> 4) << 16;                       // LBO = 32 rows * 16 B
             const uint32_t tP = tmem + C_P, tQ = tmem + C_Q, tX = tmem + C_X;
-            uint32_t ph_x = 0, ph_e0 = 0, ph_e1 = 0;
-            bool first = true;
+            const uint32_t idesc_h = make_idesc_f16(256, 32, 0, 0);
+            const uint32_t hi_h = 0u | (1u << 14);                        // SBO = 0: rows 8-15 of each CTA's head slice alias rows 0-7
+            const uint32_t lbo_h = (64u >> 4) << 16;                      // LBO = 64 B: overlapping core matrices, 4 real rows each
+            uint32_t ph_x = 0, ph_e0 = 0, ph_e1 = 0, ph_hf = 0;
+            bool first_head = true;
 #define W_TS(STEPS, d, a, blo, accum) do { _Pragma("unroll") for (int j_ = 0; j_ < (STEPS); ++j_) \
         mma_ts2(d, (a) + 8 * j_, ((uint64_t)hi << 32) | ((blo) + j_ * 64u), idesc, (j_ == 0) ? (accum) : 1u); } while (0)
 #define WAIT_E0() do { WWAITC(bar_e0, ph_e0, 3); ph_e0 ^= 1; tc_fence_after(); } while (0)
@@ -257,11 +286,8 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128) fused_fwd_wide_kernel
                     const uint32_t A0 = tmem + C_ACC, A1 = tmem + C_ACC + 64;
                     // ---- layer 0: X -> P ----
                     WWAITC(bar_x, ph_x, 2); ph_x ^= 1; tc_fence_after();
-                    if (!first) WAIT_E0();
                     if (elect_one()) { W_TS(XS, A0, tX, wb + (w_off<KX>(0, 0) >> 4), 0u); tc_commit2(bar_acc0); }
                     __syncwarp();
-                    if (!first) WAIT_E1();
-                    first = false;
                     if (elect_one()) { W_TS(XS, A1, tX, wb + (w_off<KX>(0, 1) >> 4), 0u); tc_commit2(bar_acc1); }
                     __syncwarp();
                     WAIT_E0();
@@ -306,6 +332,19 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128) fused_fwd_wide_kernel
                         }
                         __syncwarp();
                     }
+                    // ---- heads: Q (layer 3 activations) x [256 x 4] -> HEAD ----
+                    WAIT_E0();
+                    WAIT_E1();
+                    if (!first_head) { WWAITC(bar_hfree, ph_hf, 5); ph_hf ^= 1; tc_fence_after(); }
+                    first_head = false;
+                    if (elect_one()) {
+                        const uint32_t hb = sb + (main_bytes_of<KX>() >> 4) + lbo_h;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            mma_ts2(tmem + C_HEAD, tQ + 8 * j, ((uint64_t)hi_h << 32) | (hb + j * 8u), idesc_h, j ? 1u : 0u);
+                        tc_commit2(bar_head);
+                    }
+                    __syncwarp();
                 }
             }
 #undef W_TS
@@ -313,95 +352,53 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128) fused_fwd_wide_kernel
 #undef WAIT_E1
         }
         }
-    } else if (warp < 4) {
-        // ------------------------------ epilogue warpgroup ------------------------------
-        TN_SETMAXNREG_INC(168);      // register pool = 128 x 384 threads: 4 x (168 + 152 + 56) <= 12 x 128
+    } else if (warp < 8) {
+        // ------------------------------ epilogue warps: lanes 32(w%4).., columns 32(w/4).. of every 64-column quarter ------------------------------
+        TN_SETMAXNREG_DEC(112);      // register pool = 128 x 512 threads: 8 x 112 + 4 x 168 + 4 x 56 <= 16 x 128
+        auto epilogue = [&](auto CHC) {
+        constexpr int ch = decltype(CHC)::value;       // column half: compile time, so the constant-bank offsets are immediates
         const int q4 = warp & 3;
         const uint32_t tw = tmem + ((uint32_t)(q4 * 32) << 16);
-        uint32_t ph_acc0 = 0, ph_acc1 = 0, ph_hf = 0;
-        bool first_head = true;
-        const float4* __restrict__ b1v = reinterpret_cast<const float4*>(p.tail);
-        const float4* __restrict__ b3v = reinterpret_cast<const float4*>(p.tail + 256);
-        const float4* __restrict__ whv = reinterpret_cast<const float4*>(p.tail + 512);
-        const float4 bh = *reinterpret_cast<const float4*>(p.tail + 1536);
+        uint32_t ph_acc0 = 0, ph_acc1 = 0;
+        const float* ct = c_tail;
         long long* dbg = (p.debug && blockIdx.x == 0 && warp == 0 && lane == 0) ? p.debug + 256 : nullptr;
         int dbg_n = 0;
         for (long long u = u_first; u < p.n_units; u += u_stride) {
             for (int g = 0; g < p.G; ++g) {
-                float hs0 = bh.x, hs1 = bh.y, hs2 = bh.z, hs3 = bh.w;
-#pragma unroll 1
+#pragma unroll
                 for (int l = 0; l < 4; ++l) {
-                    const uint32_t dst = tw + ((l == 1) ? C_Q : C_P);
+                    const uint32_t dst = tw + ((l & 1) ? C_Q : C_P) + ch * 16;
+                    const float* bias = ct + (l == 3 ? 256 : 0) + ch * 32;          // b1 / b3 (layers 0, 2: bias inside the GEMM)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         WSTAMP();
                         if (q & 1) { WWAIT(bar_acc1, ph_acc1, 10 + l * 4 + q); ph_acc1 ^= 1; } else { WWAIT(bar_acc0, ph_acc0, 10 + l * 4 + q); ph_acc0 ^= 1; }
                         tc_fence_after();
                         WSTAMP();
-                        uint32_t v[2][32];
-                        tmem_ld32(tw + C_ACC + (q & 1) * 64, v[0]);
-                        tmem_ld32(tw + C_ACC + (q & 1) * 64 + 32, v[1]);
+                        uint32_t v[32];
+                        tmem_ld32(tw + C_ACC + (q & 1) * 64 + ch * 32, v);
                         tc_wait_ld();
-                        if (l == 3) {
-                            // last hidden layer: bias + relu in fp32, then the four head dot products straight from registers
+                        if (l & 1) {
 #pragma unroll
-                            for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float4 bb = __ldg(b3v + q * 16 + hh * 8 + i);
-                                    const float a0 = fmaxf(__uint_as_float(v[hh][4 * i]) + bb.x, 0.f), a1 = fmaxf(__uint_as_float(v[hh][4 * i + 1]) + bb.y, 0.f),
-                                                a2 = fmaxf(__uint_as_float(v[hh][4 * i + 2]) + bb.z, 0.f), a3 = fmaxf(__uint_as_float(v[hh][4 * i + 3]) + bb.w, 0.f);
-                                    const int k = q * 64 + hh * 32 + 4 * i;
-                                    const float4 w0 = __ldg(whv + k), w1 = __ldg(whv + k + 1), w2 = __ldg(whv + k + 2), w3 = __ldg(whv + k + 3);
-                                    hs0 = fmaf(a0, w0.x, hs0); hs1 = fmaf(a0, w0.y, hs1); hs2 = fmaf(a0, w0.z, hs2); hs3 = fmaf(a0, w0.w, hs3);
-                                    hs0 = fmaf(a1, w1.x, hs0); hs1 = fmaf(a1, w1.y, hs1); hs2 = fmaf(a1, w1.z, hs2); hs3 = fmaf(a1, w1.w, hs3);
-                                    hs0 = fmaf(a2, w2.x, hs0); hs1 = fmaf(a2, w2.y, hs1); hs2 = fmaf(a2, w2.z, hs2); hs3 = fmaf(a2, w2.w, hs3);
-                                    hs0 = fmaf(a3, w3.x, hs0); hs1 = fmaf(a3, w3.y, hs1); hs2 = fmaf(a3, w3.z, hs2); hs3 = fmaf(a3, w3.w, hs3);
-                                }
-                            }
-                            tc_fence_before();
-                        } else {
-                            if (l == 1) {
-#pragma unroll
-                                for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) {
-                                        const float4 bb = __ldg(b1v + q * 16 + hh * 8 + i);
-                                        v[hh][4 * i] = __float_as_uint(__uint_as_float(v[hh][4 * i]) + bb.x);
-                                        v[hh][4 * i + 1] = __float_as_uint(__uint_as_float(v[hh][4 * i + 1]) + bb.y);
-                                        v[hh][4 * i + 2] = __float_as_uint(__uint_as_float(v[hh][4 * i + 2]) + bb.z);
-                                        v[hh][4 * i + 3] = __float_as_uint(__uint_as_float(v[hh][4 * i + 3]) + bb.w);
-                                    }
-                                }
-                            }
-#pragma unroll
-                            for (int hh = 0; hh < 2; ++hh) {
-                                uint32_t h[16];
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) h[i] = pack_relu_h2(__uint_as_float(v[hh][2 * i]), __uint_as_float(v[hh][2 * i + 1]));
-                                tmem_st16(dst + q * 32 + hh * 16, h);
-                            }
-                            tc_wait_st();
-                            tc_fence_before();
+                            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + bias[q * 64 + i]);
                         }
+                        uint32_t h[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) h[i] = pack_relu_h2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                        tmem_st16(dst + q * 32, h);
+                        tc_wait_st();
+                        tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cta((q & 1) ? bar_e1 : bar_e0, 0);     // accumulator buffer drained (+ activations stored)
+                        if (lane == 0) mbar_arrive_cta((q & 1) ? bar_e1 : bar_e0, 0);     // accumulator buffer drained + activations stored
                     }
                 }
-                // hand (sigma, r, g, b) pre-activations of this tile's samples to the sample warps through tensor memory
-                if (!first_head) { WWAIT(bar_hfree, ph_hf, 30); ph_hf ^= 1; tc_fence_after(); }
-                first_head = false;
-                uint32_t hv[4] = {__float_as_uint(hs0), __float_as_uint(hs1), __float_as_uint(hs2), __float_as_uint(hs3)};
-                tmem_st4(tw + C_HEAD, hv);
-                tc_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_head);
             }
         }
+        };
+        if (warp < 4) epilogue(std::integral_constant<int, 0>{}); else epilogue(std::integral_constant<int, 1>{});
     } else {
         // ------------------------------ sample warpgroup ------------------------------
-        TN_SETMAXNREG_INC(152);
+        TN_SETMAXNREG_INC(168);
         const int q = warp & 3, row = q * 32 + lane;
         const uint32_t tw = tmem + ((uint32_t)(q * 32) << 16);
         const int S = p.S, cpr = S >> 5;                 // chunks (warps) per ray
@@ -413,7 +410,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128) fused_fwd_wide_kernel
         const float lin_step = (S > 1) ? __fdiv_rn(1.f, (float)(S - 1)) : 0.f;
         const float inv_focal = camera ? __frcp_rn(p.rs.focal) : 0.f, half_w = (float)p.rs.W * 0.5f, half_h = (float)p.rs.H * 0.5f;
         const float near_ = p.near_, far_ = p.far_;
-        long long* dbg = (p.debug && blockIdx.x == 0 && warp == 4 && lane == 0) ? p.debug : nullptr;
+        long long* dbg = (p.debug && blockIdx.x == 0 && warp == 8 && lane == 0) ? p.debug : nullptr;
         int dbg_n = 0;
 
         auto bin = [&](int i) -> float {      // bit-exact torch.linspace / z formula (src/sampling.py:16-17)
@@ -553,11 +550,11 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128) fused_fwd_wide_kernel
                 tc_wait_ld();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_hfree);
-                const float sigma = fmaxf(__uint_as_float(hv[0]), 0.f);
-                const float cr = __fdividef(1.f, 1.f + __expf(-__uint_as_float(hv[1])));
-                const float cg = __fdividef(1.f, 1.f + __expf(-__uint_as_float(hv[2])));
-                const float cb = __fdividef(1.f, 1.f + __expf(-__uint_as_float(hv[3])));
+                if (lane == 0) mbar_arrive_cta(bar_hfree, 0);
+                const float sigma = fmaxf(__uint_as_float(hv[0]) + c_tail[1536], 0.f);
+                const float cr = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(hv[1]) + c_tail[1537])));
+                const float cg = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(hv[2]) + c_tail[1538])));
+                const float cb = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(hv[3]) + c_tail[1539])));
                 // chunk-local compositing (this warp = 32 consecutive samples of one ray), src/volume.py:26-41
                 const float alpha = cur.valid ? 1.f - __expf(-sigma * cur.gd) : 0.f;
                 const float qv = 1.f - alpha + kEpsT;
@@ -620,12 +617,22 @@ static int kx_of(const tnerf_handle* h, int& L, int& inc) {
 
 }  // namespace wide
 
+// The constant table belongs to one (handle, pack version) at a time per device.  A launch for another owner first waits (on its
+// stream) for the last kernel that read the table, then uploads its own 6 KB: stream ordered, no host synchronisation.
+struct TableState { const tnerf_handle* owner = nullptr; long long version = -1; cudaEvent_t last_use = nullptr; };
+static std::mutex g_table_mu;
+static TableState g_table[64];
+void wide_release(tnerf_handle* h) {
+    std::lock_guard<std::mutex> lk(g_table_mu);
+    for (TableState& t : g_table) if (t.owner == h) { t.owner = nullptr; t.version = -1; }
+}
+
 bool wide_shape_supported(const tnerf_handle* h) {
     int L, inc;
     return h->hidden == 256 && h->depth == 4 && h->skip_at == 2 && wide::kx_of(h, L, inc) > 0;
 }
 
-static uint32_t wide_image_bytes(int kx) { return 4u * ((uint32_t)kx * 64u + 16384u + (256u + (uint32_t)kx) * 64u + 16384u); }
+static uint32_t wide_image_bytes(int kx) { return 4u * ((uint32_t)kx * 64u + 16384u + (256u + (uint32_t)kx) * 64u + 16384u) + wide::HEAD_BYTES; }
 
 int wide_pack_weights(tnerf_handle* h, cudaStream_t s) {
     int L, inc;
@@ -646,6 +653,7 @@ int wide_pack_weights(tnerf_handle* h, cudaStream_t s) {
     a.D = h->in_dim; a.KX = kx; a.image_bytes = img;
     const long long total = (long long)img + wide::TAIL_FLOATS;      // img halfs per rank * 2 ranks = img elements, then the tail
     wide::pack_wide_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, reinterpret_cast<uint8_t*>(h->packed));
+    ++h->wide_version;
     return count_launch();
 }
 
@@ -654,7 +662,7 @@ int fused_render_fwd_wide(tnerf_handle* h, const RaySource& rs, long long n, flo
     int L, inc;
     const int kx = wide::kx_of(h, L, inc);
     if (!wide_shape_supported(h) || !kx) { set_error("wide fused path: unsupported MLP shape"); return -2; }
-    if (!h->packed) { set_error("fused path: tnerf_pack_weights has not been called"); return -3; }
+    if (!h->packed || h->wide_version == 0) { set_error("fused path: tnerf_pack_weights has not been called"); return -3; }
     if (weights) { set_error("wide fused path: per-sample weights output is not available (use the fp32 path)"); return -4; }
     if (S < 32 || S % 32) { set_error("wide fused path: n_samples must be a multiple of 32"); return -4; }
     long long a = S, b = 128;
@@ -666,7 +674,6 @@ int fused_render_fwd_wide(tnerf_handle* h, const RaySource& rs, long long n, flo
     p.jitter = jitter; p.comp = comp; p.depth = depth; p.acc = acc; p.rays_d_out = rays_d_out;
     p.image_bytes = wide_image_bytes(kx);
     p.image = reinterpret_cast<const uint8_t*>(h->packed);
-    p.tail = reinterpret_cast<const float*>(p.image + 2ull * p.image_bytes);
     p.L = L; p.include_input = inc;
     p.debug = reinterpret_cast<long long*>(h->debug);
     const size_t smem = p.image_bytes + sizeof(wide::Smem);
@@ -676,7 +683,17 @@ int fused_render_fwd_wide(tnerf_handle* h, const RaySource& rs, long long n, flo
               : kx == 32 ? wide::fused_fwd_wide_kernel<32> : wide::fused_fwd_wide_kernel<16>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("wide fused fwd: shared memory request rejected"); return (int)e; }
+    std::lock_guard<std::mutex> lk(g_table_mu);
+    TableState& t = g_table[h->device & 63];
+    if (!t.last_use && cudaEventCreateWithFlags(&t.last_use, cudaEventDisableTiming) != cudaSuccess) { set_error("wide fused fwd: cudaEventCreate failed"); return -6; }
+    if (t.owner != h || t.version != h->wide_version) {
+        if (t.owner) cudaStreamWaitEvent(s, t.last_use, 0);
+        e = cudaMemcpyToSymbolAsync(wide::c_tail, p.image + 2ull * p.image_bytes, wide::TAIL_FLOATS * sizeof(float), 0, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) { set_error("wide fused fwd: constant-bank upload failed"); return (int)e; }
+        t.owner = h; t.version = h->wide_version;
+    }
     kern<<<(unsigned)(2 * pairs), wide::THREADS, smem, s>>>(p);
+    cudaEventRecord(t.last_use, s);
     return count_launch();
 }
 

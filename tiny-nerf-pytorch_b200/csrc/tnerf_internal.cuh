@@ -46,6 +46,7 @@ struct tnerf_handle {
     void* slabs = nullptr;  size_t slab_bytes = 0;     // per-CTA partial weight gradients
     bool slab0_zero = false;                           // slab 0 is all zeros (it is the accumulation target of the bulk-reduction mode)
     int sm_count = 0;
+    long long wide_version = 0;           // bumped by every pack of the hidden=256 image (the kernel's constant table follows it)
     bool fused_ok = false;
     int num_freqs = 0;                    // (in_dim-3)/6 when in_dim = 3+6L
     void* debug = nullptr;                // optional device buffer (1024 int64) for kernel phase stamps
@@ -85,6 +86,7 @@ int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, flo
 // wide MLP (hidden = 256) on CTA pairs (tnerf_fused_wide.cu)
 bool wide_shape_supported(const tnerf_handle* h);
 int wide_pack_weights(tnerf_handle* h, cudaStream_t s);
+void wide_release(tnerf_handle* h);
 int fused_render_fwd_wide(tnerf_handle* h, const RaySource& rs, long long n, float nr, float fr, int S, const float* jitter, int white,
                           float* comp, float* depth, float* acc, float* weights, float* rays_d_out, cudaStream_t s);
 int umma_rate(int n, int reps, int variant, long long* out, cudaStream_t s);

@@ -91,7 +91,7 @@ def fused_supported(module, encoder, S: int, device) -> bool:
             return False
     g = math.gcd(int(S), 128)
     if module.hidden == 256:          # wide model (BASELINE config 4): CTA-pair kernel, whole 32-sample chunks per warp
-        return h.fused_ok and S % 32 == 0 and S // g <= 8
+        return h.fused_ok and S % 32 == 0 and S // g <= 4
     return h.fused_ok and module.hidden == 128 and S // g <= 8
 
 
