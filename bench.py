@@ -30,6 +30,7 @@ for _p in (ROOT, PKG):
 import torch  # noqa: E402
 
 FLOP_FWD = 131584          # 2*MAC of the Linear layers, L=10, hidden 128
+FLOP_FWD_256 = 459776      # same, hidden 256
 FLOP_FWD_BWD = 362496
 FOCAL = 138.88888549804688
 
@@ -130,8 +131,9 @@ def reference_arm(args, rank, world):
     from oracle import oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    S = args.samples
-    p = O.init_params(63, 128, 4, 2, seed=0)
+    c4 = args.workload == "c4"
+    S = 192 if c4 else args.samples
+    p = O.init_params(63, 256 if c4 else 128, 4, 2, seed=0)
     poses = [look_at(2 * math.pi * i / 8, 0.5) for i in range(8)]
     if args.workload == "train":
         rays_full = args.rays
@@ -160,14 +162,18 @@ def reference_arm(args, rank, world):
         sample = f"{rays} of {rays_full} rays x {S} samples per step, {args.steps} steps, fp32, torch CPU ({cores} threads)"
         cfg = {"workload": "C3 train.py random-ray batch 4096x64 fwd+bwd+Adam", "rays_per_gpu": rays_full, "samples": S}
     else:
+        RH, RW_, rfocal = (800, 800, 1111.11) if c4 else (100, 100, FOCAL)
+        rays_full = RH * RW_
+
         def one(i, rays):
-            ro, rd = O.get_rays(100, 100, FOCAL, poses[i % 8])
+            ro, rd = O.get_rays(RH, RW_, rfocal, poses[i % 8])
+            lo = (rays_full - rays) // 2              # a slice from the middle of the frame (rays are independent)
             with torch.no_grad():
-                O.render_rays(p, ro[:rays], rd[:rays], 2.0, 6.0, S, None)
-        rays_full, rays = 10000, 10000
-        t0 = time.perf_counter(); one(0, rays_full); t1 = time.perf_counter() - t0
-        while rays > 512 and t1 * (rays / rays_full) * (args.steps + args.warmup) > 150.0:
-            rays //= 2
+                O.render_rays(p, ro[lo:lo + rays], rd[lo:lo + rays], 2.0, 6.0, S, None)
+        rays = 4096 if c4 else rays_full
+        t0 = time.perf_counter(); one(0, rays); t1 = time.perf_counter() - t0
+        while rays > 512 and t1 * (args.steps + args.warmup) > 150.0:
+            rays //= 2; t1 /= 2
         for i in range(args.warmup):
             one(i, rays)
         t0 = time.perf_counter()
@@ -178,8 +184,10 @@ def reference_arm(args, rank, world):
         unit, metric = "rays/s", "render rays/sec (fused forward)"
         sample = f"{rays} of {rays_full} rays x {S} samples per step, {args.steps} steps, fp32, torch CPU ({cores} threads)"
         cfg = {"workload": "C2 full 100x100 view render, 64 samples/ray", "rays": rays_full, "samples": S}
+        if c4:
+            cfg["workload"] = "C4 800x800 frame, 192 samples/ray, L=10 hidden=256"
     line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -191,10 +199,13 @@ def cpu_baseline(args):
     from oracle import oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    S = args.samples
-    p = O.init_params(63, 128, 4, 2, seed=0)
+    c4 = args.workload == "c4"
+    S = 192 if c4 else args.samples
+    p = O.init_params(63, 256 if c4 else 128, 4, 2, seed=0)
     pose = look_at(0.3, 0.5)
-    ro, rd = O.get_rays(100, 100, FOCAL, pose)
+    ro, rd = O.get_rays(800, 800, 1111.11, pose) if c4 else O.get_rays(100, 100, FOCAL, pose)
+    if c4:
+        ro, rd = ro[318000:320048], rd[318000:320048]          # 2048 rays from the middle of the frame
     if args.workload == "train":
         rays = min(args.rays, 4096)
         pix, tgt, jit = make_inputs(1, rays, S, 99)
@@ -206,7 +217,7 @@ def cpu_baseline(args):
             O.adam_step(p, g, m, v, i + 1)
         units, unit, reps = rays * S, "ray-samples/s", 6
     else:
-        rays = 10000
+        rays = int(ro.shape[0])
 
         def one(i):
             with torch.no_grad():
@@ -229,7 +240,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "render"])
+    ap.add_argument("--workload", default="train", choices=["train", "render", "c4"])
     ap.add_argument("--rays", type=int, default=4096, help="rays per GPU per train step")
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--precision", default=None, help="f16 (tcgen05) or f32 (exact FFMA path); default: engine default")
@@ -255,7 +266,10 @@ def main():
 
     torch.manual_seed(0)
     enc = PositionalEncoding(10, True).to(dev)
-    model = TinyNeRF(enc.out_dim, 128, 4, 2).to(dev)
+    c4 = args.workload == "c4"           # BASELINE config 4: 800x800 frame, 192 samples/ray, hidden 256, rows sharded over the ranks
+    model = TinyNeRF(enc.out_dim, 256 if c4 else 128, 4, 2).to(dev)
+    if c4:
+        args.samples = 192
     S, rays = args.samples, args.rays
     poses = torch.stack([look_at(2 * math.pi * i / 106 + 0.01 * i, 0.25 + 0.6 * ((i * 37) % 106) / 106) for i in range(106)]).to(dev)
     pk = peaks()
@@ -365,13 +379,15 @@ def main():
         prec = engine._PREC[args.precision] if args.precision else engine.default_precision()
         if prec == 0:
             h.ensure_packed(force=True)
-        n = 10000
+        RH, RW_, rfocal = (800, 800, 1111.11) if c4 else (100, 100, FOCAL)
+        n = RH * RW_ // world if c4 else RH * RW_            # C4: contiguous row block of the frame per rank; C2: one replica per rank
+        first = rank * n if c4 else 0
         comp, depth, acc = (torch.empty(n, 3, device=dev), torch.empty(n, 1, device=dev), torch.empty(n, 1, device=dev))
         import ctypes as C
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
         def step(i):
-            rs = engine.ray_source(c2w=poses[i % 106], H=100, W=100, focal=FOCAL, first_ray=0)
+            rs = engine.ray_source(c2w=poses[i % 106], H=RH, W=RW_, focal=rfocal, first_ray=first)
             E.check(E.lib().tnerf_render_fwd(h.h, C.byref(rs), n, 2.0, 6.0, S, None, 1, prec, E.ptr(comp), E.ptr(depth), E.ptr(acc), None, None,
                                              E.stream(dev)))
         for i in range(args.warmup):
@@ -398,7 +414,7 @@ def main():
         f0.record()
         for i in range(args.steps):
             sb_pose.copy_(pose_h[i % 106], non_blocking=True)
-            rs = engine.ray_source(c2w=sb_pose, H=100, W=100, focal=FOCAL, first_ray=0)
+            rs = engine.ray_source(c2w=sb_pose, H=RH, W=RW_, focal=rfocal, first_ray=first)
             E.check(E.lib().tnerf_render_fwd(h.h, C.byref(rs), n, 2.0, 6.0, S, None, 1, prec, E.ptr(comp), E.ptr(depth), E.ptr(acc), None, None,
                                              E.stream(dev)))
             img_h.copy_(comp, non_blocking=True)
@@ -408,12 +424,15 @@ def main():
         h2d, d2h = 64, n * 12
         ms_kernel = ms / args.steps
         units_per_step = n
-        flop = FLOP_FWD * S
+        flop = (FLOP_FWD_256 if c4 else FLOP_FWD) * S
         unit, metric = "rays/s", "render rays/sec (fused forward)"
         cfg = {"workload": "C2 full 100x100 view render, 64 samples/ray, fused forward, L=10 hidden=128", "rays": n, "samples": S,
                "parallelism": f"replicas x{world}", "precision": "fp16 operands / fp32 accumulate (tcgen05)" if prec == 0 else "fp32 FFMA",
                "l2": "256 MB flush write between timed iterations"}
-        dominant = "tnerf_render_fwd"
+        if c4:
+            cfg.update({"workload": "C4 800x800 frame, 192 samples/ray, L=10 hidden=256, fused forward on CTA pairs; rows sharded over the ranks",
+                        "rays": RH * RW_, "rays_per_gpu": n, "parallelism": f"row-sharded x{world}"})
+        dominant = "tnerf_render_fwd_wide" if c4 else "tnerf_render_fwd"
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -427,7 +446,7 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(dominant)
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if c4 else "weak", "vs_baseline": None,
             "dtype": "f16" if "fp16" in cfg["precision"] else "f32", "data": "synthetic", "config": cfg,
             "e2e": {"value": value_e2e, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks,

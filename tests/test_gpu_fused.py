@@ -102,6 +102,43 @@ def test_fused_render_vs_oracle(dev, prec, case):
     assert acc.min() >= 0 and comp.shape == (n, 3) and depth.shape == (n, 1)
 
 
+def test_config4_frame_rows_vs_oracle(dev):
+    """BASELINE config 4 shape (800x800 frame, 192 samples/ray, hidden 256) through the C ABI with rays generated in-kernel from the
+    pose: two rows from the middle of the frame against the oracle, and the same rows rendered as part of a larger row block
+    (what a rank of the row-sharded render does) must be bit-identical."""
+    import ctypes as C
+    import _engine as E
+    import engine
+    from encoding import PositionalEncoding
+    PositionalEncoding(10, True).to(dev)
+    model, p = make_model((63, 256, 4, 2), 77, dev, 1.5)
+    H = W = 800
+    focal, S = 1111.11, 192
+    pose = O.look_at_pose(0.4, 0.55)
+    h = E.handle_for(model, dev)
+    h.set_encoding(10, True)
+    h.ensure_packed(force=True)
+    pose_d = pose.to(dev)
+
+    def render(first, n):
+        comp, depth, acc = torch.empty(n, 3, device=dev), torch.empty(n, 1, device=dev), torch.empty(n, 1, device=dev)
+        rs = engine.ray_source(c2w=pose_d, H=H, W=W, focal=focal, first_ray=first)
+        E.check(E.lib().tnerf_render_fwd(h.h, C.byref(rs), n, 2.0, 6.0, S, None, 1, E.PREC_F16_TC, E.ptr(comp), E.ptr(depth), E.ptr(acc),
+                                         None, None, E.stream(dev)))
+        return comp.cpu(), depth.cpu(), acc.cpu()
+
+    first, n = 400 * W, 2 * W
+    comp, depth, acc = render(first, n)
+    ro, rd = O.get_rays(H, W, focal, pose)
+    ro, rd = ro[first:first + n].contiguous(), rd[first:first + n].contiguous()
+    oc, od, oa, _ = O.render_rays(p, ro, rd, 2.0, 6.0, S, None)
+    keep = O.last_sample_sigma_pre(p, ro, rd, 2.0, 6.0, S, None).abs() > 4e-3
+    assert keep.float().mean() > 0.97
+    assert (comp - oc)[keep].abs().max() < 2e-3 and (acc - oa)[keep].abs().max() < 2e-3 and (depth - od)[keep].abs().max() < 1.2e-2
+    big, _, _ = render(390 * W, 20 * W + 37)             # a rank's row block (ragged end): same rays, different tiles / CTAs
+    assert torch.equal(big[10 * W:12 * W], comp)
+
+
 @pytest.mark.parametrize("prec", ["f32", "f16"])
 def test_fused_render_black_background_and_broadcast_origin(dev, prec):
     import engine
