@@ -143,6 +143,15 @@ int tnerf_render_fwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long lo
                      int precision, float* comp_rgb, float* depth, float* acc, float* weights,
                      float* rays_d_out, void* stream);
 
+/* (f) N3  pose-batched rendering: the frame loop of src/make_gif.py:22-27 (render_one per spiral pose) as ONE call.
+ * poses = n_poses row-major 4x4 camera-to-world matrices (device); every pose renders the pixel range
+ * [first_ray, first_ray + rays_per_pose) of an H x W frame (the whole frame: 0, H*W).  Outputs are
+ * (n_poses * rays_per_pose, 3|1|1), pose-major.  One kernel launch for the whole batch on the tensor-core path
+ * when n_samples % 32 == 0 (the kernel indexes the pose per ray), otherwise one launch per pose from inside the call. */
+int tnerf_render_frames(tnerf_handle* h, const float* poses, int n_poses, int H, int W, float focal,
+                        long long first_ray, long long rays_per_pose, float near_, float far_, int n_samples,
+                        int white_bkgd, int precision, float* comp_rgb, float* depth, float* acc, void* stream);
+
 /* Backward of tnerf_render_fwd w.r.t. the MLP parameters with activations recomputed on chip
  * (implicit backward of src/train.py:126).  Upstream grads as in tnerf_composite_bwd.
  * grads (param_count) is ACCUMULATED into.  The tensor-core path carries gradients as fp16 operands:

@@ -2,6 +2,7 @@
 oracle, with a SHARED jitter tensor.  Bars (BASELINE.json north_star): per-ray rgb/depth/acc within
 2e-3 absolute, parameter gradients within 1e-2 relative (per tensor, rel-L2)."""
 import math
+import os
 
 import pytest
 import torch
@@ -100,6 +101,41 @@ def test_fused_render_vs_oracle(dev, prec, case):
     errs = [(comp.cpu() - oc)[keep].abs().max().item(), (depth.cpu() - od)[keep].abs().max().item(), (acc.cpu() - oa)[keep].abs().max().item()]
     assert errs[0] < tol and errs[2] < tol and errs[1] < tol * 6.0, errs    # depth is a sum of w*z with z up to 6
     assert acc.min() >= 0 and comp.shape == (n, 3) and depth.shape == (n, 1)
+
+
+@pytest.mark.parametrize("cfg,S,prec", [((63, 128, 4, 2), 64, "f16"), ((63, 256, 4, 2), 96, "f16"), ((63, 128, 4, 2), 24, "f16"),
+                                        ((39, 128, 3, 1), 32, "f32")])
+def test_pose_batched_frames_equal_per_pose_renders(dev, cfg, S, prec):
+    """(f) N3: tnerf_render_frames (the make_gif.py frame loop as one call) returns exactly what one single-pose render per frame returns --
+    one launch for the batch on the role-split kernels (n_samples % 32 == 0), a loop inside the call otherwise."""
+    import _engine as E
+    import engine
+    from camera import spiral_poses
+    from encoding import PositionalEncoding
+    L = (cfg[0] - 3) // 6
+    enc = PositionalEncoding(L, True).to(dev)
+    model, p = make_model(cfg, 31, dev, 1.5)
+    H, W, focal = 37, 53, 60.0
+    path = spiral_poses(O.look_at_pose(0.2, 0.5).to(dev), n_frames=5, radius=0.4)
+    l0 = E.launch_count()
+    imgs, depth, acc = engine.render_frames(model, enc, H, W, focal, path, n_samples=S, precision=prec, return_aux=True)
+    launches = E.launch_count() - l0
+    assert imgs.shape == (5, H, W, 3) and depth.shape == (5, H, W, 1)
+    if prec == "f16" and S % 32 == 0:
+        assert launches <= 2, launches            # (pack +) ONE render launch for five frames
+    import ctypes as C
+    h = E.handle_for(model, dev)
+    for i in range(5):          # the same frame as a single-pose call (rays generated in-kernel from the pose): bit-identical
+        comp = torch.empty(H * W, 3, device=dev)
+        pose_i = path[i].contiguous()
+        rs = engine.ray_source(c2w=pose_i, H=H, W=W, focal=focal, first_ray=0)
+        E.check(E.lib().tnerf_render_fwd(h.h, C.byref(rs), H * W, 2.0, 6.0, S, None, 1, engine._PREC[prec], E.ptr(comp), None, None, None, None,
+                                         E.stream(dev)))
+        assert torch.equal(comp.reshape(H, W, 3).clamp(0, 1), imgs[i]), i
+    oro, ord_ = O.get_rays(H, W, focal, path[3].cpu())
+    oc, _, _, _ = O.render_rays(p, oro, ord_, 2.0, 6.0, S, None, num_freqs=L, depth=cfg[2], skip_at=cfg[3])
+    err = (imgs[3].reshape(-1, 3).cpu() - oc.clamp(0, 1)).abs().max(dim=1).values
+    assert (err < (2e-5 if prec == "f32" else 2e-3)).float().mean() > 0.97
 
 
 def test_config4_frame_rows_vs_oracle(dev):

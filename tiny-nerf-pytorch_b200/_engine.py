@@ -54,6 +54,7 @@ _SIGS = {
     "tnerf_composite_fwd": (_i, [_p, _p, _p, _ll, _p, _ll, _i, _i, _p, _p, _p, _p, _p]),
     "tnerf_composite_bwd": (_i, [_p, _p, _p, _ll, _p, _ll, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "tnerf_render_fwd": (_i, [_p, C.POINTER(RaySource), _ll, _f, _f, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "tnerf_render_frames": (_i, [_p, _p, _i, _i, _i, _f, _ll, _ll, _f, _f, _i, _i, _i, _p, _p, _p, _p]),
     "tnerf_render_bwd": (_i, [_p, C.POINTER(RaySource), _ll, _f, _f, _i, _p, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p]),
     "tnerf_train_fwd_bwd": (_i, [_p, C.POINTER(RaySource), _p, _ll, _f, _f, _i, _p, _i, _i, _f, _p, _p, _p, _p]),
     "tnerf_mse_psnr": (_i, [_p, _p, _ll, _p, _p]),

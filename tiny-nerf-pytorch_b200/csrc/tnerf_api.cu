@@ -37,7 +37,7 @@ static int bad(const char* msg) { set_error(msg); return -1; }
 static RaySource to_device_source(const tnerf_ray_source* r) {
     RaySource s;
     s.rays_o = r->rays_o; s.o_stride = r->o_stride; s.rays_d = r->rays_d; s.c2w = r->c2w; s.H = r->H; s.W = r->W;
-    s.focal = r->focal; s.pixel_index = r->pixel_index; s.first_ray = r->first_ray;
+    s.focal = r->focal; s.pixel_index = r->pixel_index; s.first_ray = r->first_ray; s.frame_rays = 0;
     return s;
 }
 static int check_source(const tnerf_ray_source* r) {
@@ -273,6 +273,40 @@ int tnerf_render_fwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long lo
     F32Job job{};
     job.mode = 0; job.comp = comp_rgb; job.depth = depth; job.acc = acc; job.weights = weights; job.rays_d_out = rays_d_out;
     return run_f32(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, job, (cudaStream_t)stream);
+}
+
+int tnerf_render_frames(tnerf_handle* h, const float* poses, int n_poses, int H, int W, float focal, long long first_ray,
+                        long long rays_per_pose, float near_, float far_, int n_samples, int white_bkgd, int precision, float* comp_rgb,
+                        float* depth, float* acc, void* stream) {
+    if (n_poses == 0 || rays_per_pose == 0) return 0;
+    if (!h || h->params.empty() || !poses || !comp_rgb || n_poses < 0 || H <= 0 || W <= 0 || !(focal > 0.f) || first_ray < 0 ||
+        rays_per_pose < 0 || first_ray + rays_per_pose > (long long)H * W || n_samples < 1)
+        return bad("tnerf_render_frames: invalid argument / params not bound");
+    const long long total = (long long)n_poses * rays_per_pose;
+    RaySource rs{};
+    rs.c2w = poses; rs.H = H; rs.W = W; rs.focal = focal; rs.first_ray = first_ray; rs.frame_rays = rays_per_pose;
+    // one launch for the whole pose batch where the kernel indexes the pose per ray (role-split render kernels: n_samples % 32 == 0);
+    // other shapes: one launch per pose from here
+    const bool one_launch = precision == TNERF_PREC_F16_TC && n_samples % 32 == 0 && total < (1ll << 31);
+    if (one_launch)
+        return fused_render_fwd(h, rs, total, near_, far_, n_samples, nullptr, white_bkgd, comp_rgb, depth, acc, nullptr, nullptr, (cudaStream_t)stream);
+    rs.frame_rays = 0;
+    for (int f = 0; f < n_poses; ++f) {
+        rs.c2w = poses + 16 * f;
+        float* c = comp_rgb + 3 * f * rays_per_pose;
+        float* d = depth ? depth + f * rays_per_pose : nullptr;
+        float* a = acc ? acc + f * rays_per_pose : nullptr;
+        int e;
+        if (precision == TNERF_PREC_F16_TC)
+            e = fused_render_fwd(h, rs, rays_per_pose, near_, far_, n_samples, nullptr, white_bkgd, c, d, a, nullptr, nullptr, (cudaStream_t)stream);
+        else {
+            F32Job job{};
+            job.mode = 0; job.comp = c; job.depth = d; job.acc = a;
+            e = run_f32(h, rs, rays_per_pose, near_, far_, n_samples, nullptr, white_bkgd, job, (cudaStream_t)stream);
+        }
+        if (e) return e;
+    }
+    return 0;
 }
 
 int tnerf_render_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long long n_rays, float near_, float far_, int n_samples,

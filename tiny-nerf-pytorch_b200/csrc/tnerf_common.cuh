@@ -21,6 +21,7 @@ struct RaySource {          // device-side mirror of tnerf_ray_source
     float focal;
     const long long* pixel_index;
     long long first_ray;
+    long long frame_rays;   // > 0: pose batch -- ray i belongs to pose i / frame_rays (c2w = [n_poses][16]), pixel first_ray + i % frame_rays
 };
 
 // t_i of torch.linspace(0,1,S) in fp32, bit for bit (src/sampling.py:16):
@@ -67,9 +68,11 @@ __device__ __forceinline__ void load_ray(const RaySource& rs, long long i, float
         const float* po = rs.rays_o + rs.o_stride * i;
         o[0] = po[0]; o[1] = po[1]; o[2] = po[2];
     } else {
-        const long long k = rs.pixel_index ? rs.pixel_index[i] : rs.first_ray + i;
-        pixel_ray(k, rs.H, rs.W, rs.focal, rs.c2w, d[0], d[1], d[2]);
-        o[0] = rs.c2w[3]; o[1] = rs.c2w[7]; o[2] = rs.c2w[11];
+        const long long f = rs.frame_rays ? i / rs.frame_rays : 0;
+        const float* cm = rs.c2w + 16 * f;
+        const long long k = rs.pixel_index ? rs.pixel_index[i] : rs.first_ray + (i - f * rs.frame_rays);
+        pixel_ray(k, rs.H, rs.W, rs.focal, cm, d[0], d[1], d[2]);
+        o[0] = cm[3]; o[1] = cm[7]; o[2] = cm[11];
     }
 }
 

@@ -127,6 +127,33 @@ def render_rays(model, encoder, rays_o, rays_d, near: float, far: float, n_sampl
                               bool(white_bkgd), prec, bprec, *model._params())
 
 
+@torch.no_grad()
+def render_frames(model, encoder, H: int, W: int, focal: float, poses: torch.Tensor, n_samples: int = 64, near: float = 2.0,
+                  far: float = 6.0, white_bkgd: bool = True, precision: Optional[str] = None, return_aux: bool = False):
+    """Pose-batched full-frame rendering: the frame loop of src/make_gif.py:22-27 (one ``render_one`` per pose) as ONE
+    tnerf_render_frames call -- a single kernel launch for the whole camera path on the tensor-core path.
+    poses (n,4,4) -> images (n,H,W,3) clamped to [0,1] like ``render_one``; with ``return_aux`` also depth and acc (n,H,W,1)."""
+    dev = E.need_cuda(poses)
+    h = E.handle_for(model, dev)
+    h.set_encoding(encoder.num_freqs, encoder.include_input)
+    prec, _ = pick_precisions(model, encoder, n_samples, dev, precision)
+    if prec == E.PREC_F16_TC:
+        h.ensure_packed()
+    else:
+        h.bind()
+    poses_d = E.f32c(poses.reshape(-1, 4, 4))
+    n, hw = int(poses_d.shape[0]), int(H) * int(W)
+    comp = torch.empty((n * hw, 3), dtype=torch.float32, device=dev)
+    depth = torch.empty((n * hw, 1), dtype=torch.float32, device=dev) if return_aux else None
+    acc = torch.empty((n * hw, 1), dtype=torch.float32, device=dev) if return_aux else None
+    E.check(E.lib().tnerf_render_frames(h.h, E.ptr(poses_d), n, int(H), int(W), float(focal), 0, hw, float(near), float(far), int(n_samples),
+                                        int(white_bkgd), prec, E.ptr(comp), E.ptr(depth), E.ptr(acc), E.stream(dev)), "tnerf_render_frames")
+    img = comp.reshape(n, H, W, 3).clamp(0, 1)
+    if return_aux:
+        return img, depth.reshape(n, H, W, 1), acc.reshape(n, H, W, 1)
+    return img
+
+
 def render_weights(model, ro, o_stride, rd, n, S, near, far, jitter, white, prec):
     """The (N,S) compositing weights of a fused render (the 4th value of volume_render), recomputed on demand."""
     dev = rd.device
