@@ -28,3 +28,9 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden():
     return np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_c4():
+    """BASELINE config 4 vectors (hidden 256, 800x800, 192 samples) from the unmodified reference (tests/golden/make_golden_c4.py)"""
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors_c4.npz"))

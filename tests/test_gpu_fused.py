@@ -138,6 +138,39 @@ def test_pose_batched_frames_equal_per_pose_renders(dev, cfg, S, prec):
     assert (err < (2e-5 if prec == "f32" else 2e-3)).float().mean() > 0.97
 
 
+def test_config4_pair_kernel_against_reference_vectors(dev, golden_c4):
+    """The CTA-pair kernel, through the C ABI with in-kernel ray generation, against pixels the UNMODIFIED reference produced for
+    the config-4 model (tests/golden/make_golden_c4.py): 2e-3 on rgb / acc."""
+    import ctypes as C
+    import importlib.util
+    import _engine as E
+    import engine
+    from nerf import TinyNeRF
+    spec = importlib.util.spec_from_file_location("_make_golden_c4", os.path.join(os.path.dirname(__file__), "golden", "make_golden_c4.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    model = TinyNeRF(63, 256, 4, 2)
+    model.load_state_dict(mod.synthetic_params())
+    model = model.to(dev)
+    h = E.handle_for(model, dev)
+    h.set_encoding(10, True)
+    h.ensure_packed(force=True)
+    g = golden_c4
+    pose = torch.from_numpy(g["c4_c2w"]).to(dev)
+    pick = torch.from_numpy(g["c4_pick"]).to(dev)
+    n = int(pick.numel())
+    comp, depth, acc = torch.empty(n, 3, device=dev), torch.empty(n, 1, device=dev), torch.empty(n, 1, device=dev)
+    rs = engine.ray_source(c2w=pose, H=800, W=800, focal=1111.11, pixel_index=pick)
+    E.check(E.lib().tnerf_render_fwd(h.h, C.byref(rs), n, 2.0, 6.0, 192, None, 1, E.PREC_F16_TC, E.ptr(comp), E.ptr(depth), E.ptr(acc), None,
+                                     None, E.stream(dev)))
+    last_pre = torch.from_numpy(g["c4_sigma"]).reshape(n, 192)[:, -1]      # relu'd: rays whose last density is exactly 0 may sit on the discontinuity
+    keep = last_pre > 4e-3
+    assert keep.sum() >= n - 3
+    assert (comp.cpu() - torch.from_numpy(g["c4_comp"]))[keep].abs().max() < 2e-3
+    assert (acc.cpu() - torch.from_numpy(g["c4_acc"]))[keep].abs().max() < 2e-3
+    assert (depth.cpu() - torch.from_numpy(g["c4_depth"]))[keep].abs().max() < 1.2e-2
+
+
 def test_config4_frame_rows_vs_oracle(dev):
     """BASELINE config 4 shape (800x800 frame, 192 samples/ray, hidden 256) through the C ABI with rays generated in-kernel from the
     pose: two rows from the middle of the frame against the oracle, and the same rows rendered as part of a larger row block

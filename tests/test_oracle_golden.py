@@ -145,3 +145,37 @@ def test_render_image(golden):
 
 def test_spiral(golden):
     close(O.spiral_poses(T(golden["train_c2w"]), 7, 0.3), golden["spiral"], rtol=1e-6, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------ BASELINE config 4 (hidden 256)
+def c4_params():
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("_make_golden_c4", os.path.join(os.path.dirname(__file__), "golden", "make_golden_c4.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.synthetic_params()
+
+
+def test_config4_chain_against_reference(golden_c4):
+    """800x800 frame, 192 deterministic samples, TinyNeRF(63, hidden=256): rays, depths, features, MLP outputs and the
+    composited pixels of twelve rays, as the unmodified reference computes them."""
+    g = golden_c4
+    p = c4_params()
+    ro, rd = O.get_rays(800, 800, 1111.11, T(g["c4_c2w"]))
+    pick = T(g["c4_pick"])
+    close(rd[pick], g["c4_rays_d"], rtol=1e-6, atol=1e-7)
+    close(ro[pick], g["c4_rays_o"])
+    ro_p, rd_p = T(g["c4_rays_o"].copy()), T(g["c4_rays_d"].copy())
+    z, pts = O.stratified(2.0, 6.0, 192, ro_p, rd_p, None)
+    close(z, g["c4_z"])
+    feat = O.posenc(pts.reshape(-1, 3), 10, True)
+    close(feat[::97], g["c4_feat_rows"], rtol=1e-6, atol=1e-6)
+    c, s = O.mlp_forward(p, feat, 4, 2)
+    close(c, g["c4_rgb"], rtol=1e-5, atol=2e-6)
+    close(s, g["c4_sigma"], rtol=1e-5, atol=2e-5)
+    comp, depth, acc, w = O.render_rays(p, ro_p, rd_p, 2.0, 6.0, 192, None)
+    close(comp, g["c4_comp"], atol=2e-5)
+    close(depth, g["c4_depth"], atol=1e-4)
+    close(acc, g["c4_acc"], atol=2e-5)
+    close(w, g["c4_weights"], atol=2e-5)
