@@ -15,7 +15,8 @@ from nerf import TinyNeRF  # noqa: E402
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-model = TinyNeRF(63, 128, 4, 2).to(dev)
+hidden = int(os.environ.get("STRESS_HIDDEN", "128"))          # 256 = the CTA-pair kernel of BASELINE config 4
+model = TinyNeRF(63, hidden, 4, 2).to(dev)
 h = E.handle_for(model, dev); h.set_encoding(10, True); h.ensure_packed(force=True)
 pose = torch.eye(4, device=dev); pose[2, 3] = 4.0
 cases = [(int(a.split("x")[0]), int(a.split("x")[1])) for a in sys.argv[1].split(",")]
