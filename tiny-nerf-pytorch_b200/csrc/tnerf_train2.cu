@@ -73,7 +73,7 @@ __device__ __forceinline__ float drain_bwd_compute(uint32_t D, const uint8_t* sl
     tmem_ld32(D + 32, va[1]);                 // second half in flight while the first is processed
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-        if (c == 1) { tc_wait_ld(); if (dread_bar) { tc_fence_before(); mbar_arrive(dread_bar); } }
+        if (c == 1) { tc_wait_ld(); if (dread_bar) { tc_fence_before(); __syncwarp(); if ((threadIdx.x & 31) == 0) mbar_arrive(dread_bar); } }
         const uint32_t (&v)[32] = va[c];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -187,18 +187,19 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
     if (warp == 12 && lane == 0) {
         mbar_init(smem_u32(&ms.bar_w), 1);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(smem_u32(&ms.bar_x[s]), 64);
-            mbar_init(smem_u32(&ms.bar_in[s]), 128);
+            mbar_init(smem_u32(&ms.bar_x[s]), 2);             // thread groups signal with ONE arrival per warp (after __syncwarp):
+                                                              // 128 arrivals on one barrier serialise for a few hundred cycles
+            mbar_init(smem_u32(&ms.bar_in[s]), 4);
             mbar_init(smem_u32(&ms.bar_d[s]), 1);
             mbar_init(smem_u32(&ms.bar_head[s]), 1);
-            mbar_init(smem_u32(&ms.bar_dzh[s]), 64);
+            mbar_init(smem_u32(&ms.bar_dzh[s]), 2);
             mbar_init(smem_u32(&ms.bar_g[s][0]), 1);
             mbar_init(smem_u32(&ms.bar_g[s][1]), 1);
-            mbar_init(smem_u32(&ms.bar_gfree[s]), 128);
+            mbar_init(smem_u32(&ms.bar_gfree[s]), 4);
             mbar_init(smem_u32(&ms.bar_xfree[s]), 1);
             mbar_init(smem_u32(&ms.bar_wg[s]), 1);
-            mbar_init(smem_u32(&ms.bar_dread[s]), 128);
-            mbar_init(smem_u32(&ms.bar_in2[s]), 128);
+            mbar_init(smem_u32(&ms.bar_dread[s]), 4);
+            mbar_init(smem_u32(&ms.bar_in2[s]), 4);
         }
         fence_barrier_init();
     }
@@ -336,7 +337,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             for (int c = 0; c < KX / 8; ++c)
                 *reinterpret_cast<uint4*>(X + ((size_t)(c * 64 + i) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
             fence_proxy_async();
-            mbar_arrive(bar_x);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_x);
         };
         uint32_t ph_head = 0, ph_xfree = 0;
         float z_cur = 0.f, gap_cur = 0.f;
@@ -457,7 +459,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                 *reinterpret_cast<uint4*>(DZH + ((size_t)i << 4)) = make_uint4(pack_sat_h2(s0, s1), pack_sat_h2(s2, s3), 0u, 0u);
                 fence_proxy_async();
                 tc_fence_before();
-                mbar_arrive(bar_dzh);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_dzh);
                 T2_STAMP();
                 hb[0] += s0; hb[1] += s1; hb[2] += s2; hb[3] += s3;      // head bias gradients: per-thread partials, reduced at the end
             }
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         // In-phase mode (n_samples = 128, both streams in the same tile phase): the dW1 halves are drained where they are produced,
         // in the order stream 0 first half (WG0), stream 0 second half (WG1) | stream 1 first half (WG0), stream 1 second half (WG1).
         enum { K_FWD = 0, K_G = 1, K_SMALL = 2, K_BWD = 3 };
-#define T2_SIGNAL(bar) do { fence_proxy_async(); tc_fence_before(); mbar_arrive(bar); } while (0)
+#define T2_SIGNAL(bar) do { fence_proxy_async(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar); } while (0)
 #pragma unroll 1
         for (long long t = 0; t <= n_my[s]; ++t) {
             const bool tail = t == n_my[s];
@@ -553,7 +556,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                         tmem_ld32(D + 32, v[1]);
                         tc_wait_ld();
                         tc_fence_before();
-                        mbar_arrive(own ? bar_gfree_own : bar_gfree_oth);     // the accumulator is released as soon as it has been read
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(own ? bar_gfree_own : bar_gfree_oth);     // the accumulator is released as soon as it has been read
 #pragma unroll
                         for (int c = 0; c < 2; ++c)
 #pragma unroll
