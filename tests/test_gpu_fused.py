@@ -369,3 +369,91 @@ def test_optimizer_step_refreshes_operand_image_like_a_full_repack(dev):
             assert E.lib().tnerf_packed_image_copy(tr.h.h, E.ptr(img_b), nbytes, E.stream(dev)) == nbytes
             torch.cuda.synchronize()
             assert torch.equal(img_a, img_b), int((img_a != img_b).sum())
+
+
+# ------------------------------------------------------------------------------------------ deferred fusion
+def test_reference_call_sequence_is_fused(dev):
+    """src/train.py:114-121 verbatim call sequence -> one fused forward launch, same numbers."""
+    import _engine as E
+    from encoding import PositionalEncoding
+    from sampling import stratified_samples
+    from volume import volume_render
+    enc = PositionalEncoding(10, True).to(dev)
+    model, p = make_model((63, 128, 4, 2), 31, dev, 2.0)
+    n, S = 512, 64
+    ro, rd = random_rays(n, 32)
+    u = torch.rand(n, S, generator=torch.Generator().manual_seed(33))
+    target = torch.rand(n, 3, generator=torch.Generator().manual_seed(34))
+    ro_d, rd_d = ro.to(dev), rd.to(dev)
+    model.train()
+    z_vals, pts = stratified_samples(2.0, 6.0, S, ro_d, rd_d, randomized=True, t_rand=u.to(dev))
+    before = E.launch_count()
+    with torch.amp.autocast("cuda", enabled=True):
+        xenc = enc(pts.reshape(-1, 3))
+        rgb, sigma = model(xenc)
+        rgb = rgb.reshape(n, S, 3)
+        sigma = sigma.reshape(n, S, 1)
+        comp_rgb, _, _, w = volume_render(rgb, sigma, z_vals, rd_d)
+        loss = torch.mean((comp_rgb - target.to(dev)) ** 2)
+    launches_fwd = E.launch_count() - before
+    assert launches_fwd <= 2, launches_fwd           # (weight pack +) one fused kernel
+    scaler = torch.amp.GradScaler("cuda")
+    scaler.scale(loss).backward()
+    l_ref, g_ref, (oc, _, _) = O.loss_and_grads(p, ro, rd, target, 2.0, 6.0, S, u)
+    keep = O.last_sample_sigma_pre(p, ro, rd, 2.0, 6.0, S, u).abs() > 4e-3
+    assert keep.float().mean() > 0.97 and (comp_rgb.detach().cpu() - oc)[keep].abs().max() < 2e-3
+    for k, v in model.named_parameters():
+        assert rel_l2(v.grad.cpu() / scaler.get_scale(), g_ref[k]) < 1e-2, k
+    assert w.shape == (n, S)
+    ow = O.render_rays(p, ro, rd, 2.0, 6.0, S, u)[3]
+    assert ((w + 0).cpu() - ow)[keep].abs().max() < 2e-3
+
+
+def test_deferred_falls_back_when_chain_is_broken(dev):
+    from encoding import PositionalEncoding
+    from sampling import stratified_samples
+    from volume import volume_render
+    enc = PositionalEncoding(4, True).to(dev)
+    model, p = make_model((27, 32, 3, 1), 41, dev, 2.0)     # hidden 32: no tensor-core path -> fp32 kernels
+    n, S = 33, 24
+    ro, rd = random_rays(n, 42)
+    with torch.no_grad():
+        z, pts = stratified_samples(2.0, 6.0, S, ro.to(dev), rd.to(dev), randomized=False)
+        assert pts.shape == (n, S, 3) and pts.shape[0] == n
+        rgb, sigma = model(enc(pts.reshape(-1, 3)))
+        rgb = rgb.reshape(n, S, 3) * 1.0                   # arithmetic on a deferred tensor materialises it
+        comp, depth, acc, w = volume_render(rgb, sigma.reshape(n, S, 1), z, rd.to(dev))
+    oc, od, oa, ow = O.render_rays(p, ro, rd, 2.0, 6.0, S, None, num_freqs=4, depth=3, skip_at=1)
+    assert (comp.cpu() - oc).abs().max() < 2e-5 and (w.cpu() - ow).abs().max() < 2e-5
+    oz, op = O.stratified(2.0, 6.0, S, ro, rd, None)
+    assert torch.equal(pts[3:5].cpu(), op[3:5])              # indexing a deferred tensor works too
+
+
+def test_reference_call_sequence_with_the_wide_model(dev):
+    """The same five-call sequence with TinyNeRF(hidden=256) (BASELINE config 4 model, 192 deterministic samples): the forward is
+    one launch of the CTA-pair kernel; the per-sample weights (4th output) come from the fp32 path on demand."""
+    import _engine as E
+    from encoding import PositionalEncoding
+    from sampling import stratified_samples
+    from volume import volume_render
+    enc = PositionalEncoding(10, True).to(dev)
+    model, p = make_model((63, 256, 4, 2), 61, dev, 1.5)
+    n, S = 150, 192
+    ro, rd = random_rays(n, 62)
+    ro_d, rd_d = ro.to(dev), rd.to(dev)
+    model.eval()
+    E.handle_for(model, dev).ensure_packed(force=True) if E.handle_for(model, dev).fused_ok else None
+    with torch.no_grad():
+        z_vals, pts = stratified_samples(2.0, 6.0, S, ro_d, rd_d, randomized=False)
+        before = E.launch_count()
+        rgb, sigma = model(enc(pts.reshape(-1, 3)))
+        comp, depth, acc, w = volume_render(rgb.reshape(n, S, 3), sigma.reshape(n, S, 1), z_vals, rd_d)
+        comp = comp + 0
+        launches = E.launch_count() - before
+        assert launches <= 2, launches               # (weight pack +) the pair kernel
+        w = w + 0                                    # materialises the weights: fp32 path
+    oc, od, oa, ow = O.render_rays(p, ro, rd, 2.0, 6.0, S, None)
+    keep = O.last_sample_sigma_pre(p, ro, rd, 2.0, 6.0, S, None).abs() > 4e-3
+    assert keep.float().mean() > 0.97
+    assert (comp.cpu() - oc)[keep].abs().max() < 2e-3 and (acc.cpu() - oa)[keep].abs().max() < 2e-3
+    assert w.shape == (n, S) and (w.cpu() - ow)[keep].abs().max() < 2e-4
