@@ -38,7 +38,8 @@ constexpr int THREADS = 512;      // warps 13-15 exist only so that warp 12's wa
 constexpr int C_ACC = 0, C_P = 128, C_Q = 256, C_X = 384, C_HEAD = 416;
 constexpr uint32_t HEAD_BYTES = 2112;   // 32 K-octets x 64 B + the 64 B the last overlapping core matrix reaches into
 constexpr int TAIL_FLOATS = 1540;
-// b1[256], b3[256], head weights [256][4] (sigma, r, g, b), head biases [4] of the model whose kernel runs next on this device:
+// b1[256], b3[256], head weights [256][4] (sigma, r, g, b; kept for tools, the kernel's heads are an MMA), head biases [4] of the model
+// whose kernel runs next on this device:
 // compile-time offsets, so every bias / head weight is a constant-bank OPERAND of an FADD / FFMA (no load instruction at all).
 // The host re-uploads the table (stream ordered, behind an event of the last kernel that used it) when another handle or a
 // re-packed model comes along.
@@ -116,13 +117,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0,%1,%2,%3};" ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(taddr) : "memory");
 }
 
 // ---- weight image --------------------------------------------------------------------------------------------------------
