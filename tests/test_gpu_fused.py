@@ -300,6 +300,49 @@ def test_train_fwd_bwd_entry_point_vs_oracle(dev, prec, white):
         off += cnt
 
 
+def test_train_kernel_variants_agree_on_a_large_batch(dev):
+    """The training kernel has a rolled tile program (n_samples <= 64: BASELINE config 3) and an unrolled one (n_samples = 128: config 5).
+    Same arithmetic in the same order: on 16 384 rays x 64 samples both must return the same gradient bits (and the same loss up to the order of its atomic sum), and the
+    result must be consistent with the sum of two half batches (which the small-batch variant computes)."""
+    import ctypes as C
+    import _engine as E
+    import engine
+    from encoding import PositionalEncoding
+    PositionalEncoding(10, True).to(dev)
+    model, p = make_model((63, 128, 4, 2), 71, dev, 2.0)
+    H, W, focal, S, n = 200, 200, 260.0, 64, 16384
+    g = torch.Generator().manual_seed(72)
+    pix = torch.randint(0, H * W, (n,), generator=g).to(dev)
+    u, target = torch.rand(n, S, generator=g).to(dev), torch.rand(n, 3, generator=g).to(dev)
+    pose = O.look_at_pose(1.1, 0.4).to(dev)
+    h = E.handle_for(model, dev)
+    h.set_encoding(10, True)
+    h.ensure_packed(force=True)
+
+    def run(lo, cnt, unroll_from):
+        os.environ["TNERF_TRAIN_UNROLL_FROM"] = str(unroll_from)
+        try:
+            grads = torch.zeros(h.param_count, device=dev)
+            loss = torch.zeros(1, device=dev)
+            rs = engine.ray_source(c2w=pose, H=H, W=W, focal=focal, pixel_index=pix[lo:lo + cnt].contiguous())
+            E.check(E.lib().tnerf_train_fwd_bwd(h.h, C.byref(rs), E.ptr(target[lo:lo + cnt].contiguous()), cnt, 2.0, 6.0, S,
+                                                E.ptr(u[lo:lo + cnt].contiguous()), 1, E.PREC_F16_TC, 3.0 * n, None, E.ptr(loss), E.ptr(grads),
+                                                E.stream(dev)))
+            torch.cuda.synchronize()
+            return loss.cpu(), grads.cpu()
+        finally:
+            os.environ.pop("TNERF_TRAIN_UNROLL_FROM", None)
+
+    l_u, g_u = run(0, n, 1)                  # unrolled tile program
+    l_r, g_r = run(0, n, 1 << 30)            # rolled
+    assert torch.equal(g_u, g_r), (g_u - g_r).abs().max().item()
+    assert abs(l_u.item() - l_r.item()) < 1e-6          # the loss is summed with atomics across CTAs: last-bit differences between runs
+    l_a, g_a = run(0, n // 2, 1 << 30)
+    l_b, g_b = run(n // 2, n // 2, 1 << 30)
+    assert abs((l_a + l_b).item() - l_u.item()) < 1e-5
+    assert rel_l2(g_a + g_b, g_u) < 2e-3     # same rays, different tile -> CTA assignment and loss-scale rounding of the fp16 gradients
+
+
 def test_trainer_steps_match_oracle_adam(dev):
     """fused optimisation steps (train kernel + slab reduce + Adam kernel + re-pack) vs oracle loss_and_grads +
     adam_step.  Before every step the engine is re-synchronised to the oracle's parameters and moments: Adam divides

@@ -16,6 +16,7 @@
 // Warp roles (512 threads): warpgroup 0/1 = drain threads of stream 0/1 (thread <-> feature <-> TMEM lane);
 // warps 8-9 / 10-11 = sample threads of stream 0/1 (rays, depths, Fourier features, compositing fwd+bwd);
 // warp 12/13 lane 0 = MMA issuer of stream 0/1; warp 14 loads the weights.
+#include <cstdlib>
 #include "tnerf_train.cuh"
 
 namespace tnerf {
@@ -176,7 +177,7 @@ __device__ __forceinline__ void issuer_loop(Misc& ms, uint32_t sbase, uint32_t t
 #undef T2_WAIT
 }
 
-template <int KX>
+template <int KX, bool UNROLL>
 __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_constant__ TrainParams p, const __grid_constant__ Extra ex) {
     extern __shared__ __align__(1024) uint8_t smem[];
     Misc& ms = *reinterpret_cast<Misc*>(smem + S_MISC);
@@ -525,14 +526,14 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         // in the order stream 0 first half (WG0), stream 0 second half (WG1) | stream 1 first half (WG0), stream 1 second half (WG1).
         enum { K_FWD = 0, K_G = 1, K_SMALL = 2, K_BWD = 3 };
 #define T2_SIGNAL(bar) do { fence_proxy_async(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar); } while (0)
-#pragma unroll 1
-        for (long long t = 0; t <= n_my[s]; ++t) {
-            const bool tail = t == n_my[s];
-#pragma unroll 1
-            for (int step = tail ? 10 : 0; step < 12; ++step) {
+        // one step of the tile program; returns 0 = next step, 1 = stay in this step (tail: more foreign halves), 2 = leave the tile.
+        // ROLLED (default): called from a rolled loop, each drain body exists once (instruction-cache footprint: the two streams of a
+        // CTA are half a tile apart and run different steps at the same time).  UNROLL: the twelve calls of a full tile are unrolled and
+        // specialised per step: 15 % faster when the streams run in phase (n_samples = 128, BASELINE config 5); the host picks.
+        auto do_step = [&](const int step, const bool tail, const long long t) __attribute__((always_inline)) -> int {
                 const int kind = (step == 4 || step == 10) ? K_G : (step == 5) ? K_SMALL : (step <= 3 || step == 9) ? K_FWD : K_BWD;
                 uint8_t* slot = ((0x14A >> step) & 1) ? Q : P;          // Q for steps 1, 3, 6, 8
-                if (tail && step == 11) break;
+                if (tail && step == 11) return 2;
                 if (kind == K_G) {
                     // job list: bit j of `own_mask` = job j drains this stream's accumulator, else the other stream's
                     int njobs = 0, own_mask = 0;
@@ -564,8 +565,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                             for (int i = 0; i < 32; ++i) dw1[c * 32 + i] += __uint_as_float(v[c][i]);
                         if (!own) --g_oth_left;
                     }
-                    if (tail && g_oth_left > 0) --step;                                              // stay in the tail step
-                    continue;
+                    return (tail && g_oth_left > 0) ? 1 : 0;                                         // stay in the tail step
                 }
                 T2_STAMP();
                 mbar_wait(bar_d, ph_d);
@@ -622,6 +622,21 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                     drain_store(slot, f, o);
                     if (step == 7) drain_store(Q, f, stash);                                         // H1 back into Q (dZ3 is dead)
                     T2_SIGNAL(step == 8 ? bar_in2 : bar_in);
+                }
+                return 0;
+        };
+#pragma unroll 1
+        for (long long t = 0; t <= n_my[s]; ++t) {
+            const bool tail = t == n_my[s];
+            if (UNROLL && !tail) {
+#pragma unroll
+                for (int step = 0; step < 12; ++step) do_step(step, false, t);
+            } else {
+#pragma unroll 1
+                for (int step = tail ? 10 : 0; step < 12; ++step) {
+                    const int r = do_step(step, tail, t);
+                    if (r == 2) break;
+                    if (r == 1) --step;
                 }
             }
         }
@@ -733,8 +748,17 @@ int fused_train2(tnerf_handle* h, const FusedPlan& fp, const TrainParams& p, int
     ex.w[3] = {fp.layer[3].b_off, t2::S_W3, 32768u};
     ex.w[4] = {fp.layer[4].b_off, t2::S_WH, 4096u};
     const size_t smem = t2::S_MISC + sizeof(t2::Misc);
-    auto kern = Kx == 64 ? t2::fused_train2_kernel<64> : Kx == 48 ? t2::fused_train2_kernel<48> : Kx == 32 ? t2::fused_train2_kernel<32>
-                                                                                                            : t2::fused_train2_kernel<16>;
+    // Unrolled tile program for n_samples = 128 (BASELINE config 5): there the two streams of a CTA run IN PHASE, both drain
+    // warpgroups execute the same specialised code at the same time and the larger image costs nothing (+15 %, tools/sweep_c5.py).
+    // With n_samples <= 64 the streams are half a tile apart and execute different parts of the program: the rolled variant is
+    // 3-5 % faster at every batch size (tools/variant_crossover.py).  TNERF_TRAIN_UNROLL_FROM = tiles per stream from which the
+    // unrolled variant runs regardless of n_samples (tuning / tests).
+    const char* uf = getenv("TNERF_TRAIN_UNROLL_FROM");
+    const long long per_stream = p.n_tiles / (2ll * grid);
+    const bool unroll = Kx == 64 && (uf ? per_stream >= atoi(uf) : (p.S == 128 && per_stream >= 8));
+    auto kern = unroll ? t2::fused_train2_kernel<64, true>
+              : Kx == 64 ? t2::fused_train2_kernel<64, false> : Kx == 48 ? t2::fused_train2_kernel<48, false>
+              : Kx == 32 ? t2::fused_train2_kernel<32, false> : t2::fused_train2_kernel<16, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("fused train (two-stream): shared memory request rejected"); return (int)e; }
     kern<<<(unsigned)grid, t2::THREADS, smem, s>>>(p, ex);
