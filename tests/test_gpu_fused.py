@@ -301,9 +301,11 @@ def test_train_fwd_bwd_entry_point_vs_oracle(dev, prec, white):
 
 
 def test_train_kernel_variants_agree_on_a_large_batch(dev):
-    """The training kernel has a rolled tile program (n_samples <= 64: BASELINE config 3) and an unrolled one (n_samples = 128: config 5).
-    Same arithmetic in the same order: on 16 384 rays x 64 samples both must return the same gradient bits (and the same loss up to the order of its atomic sum), and the
-    result must be consistent with the sum of two half batches (which the small-batch variant computes)."""
+    """The training kernel has two tile programs (rolled / unrolled per step) and two stream schedules (in phase = default; half a
+    tile apart = TNERF_TRAIN_SYNC=0, the run-to-run reproducible mode: the two streams of a CTA then feed the shared weight-gradient
+    accumulators in a fixed order).  On 16 384 rays x 64 samples: the two programs return the same gradient BITS under the
+    reproducible schedule, the in-phase schedule agrees with it to fp32 summation-order noise, and the sum of two half batches
+    matches the full batch."""
     import ctypes as C
     import _engine as E
     import engine
@@ -319,8 +321,9 @@ def test_train_kernel_variants_agree_on_a_large_batch(dev):
     h.set_encoding(10, True)
     h.ensure_packed(force=True)
 
-    def run(lo, cnt, unroll_from):
+    def run(lo, cnt, unroll_from, sync):
         os.environ["TNERF_TRAIN_UNROLL_FROM"] = str(unroll_from)
+        os.environ["TNERF_TRAIN_SYNC"] = str(sync)
         try:
             grads = torch.zeros(h.param_count, device=dev)
             loss = torch.zeros(1, device=dev)
@@ -332,13 +335,17 @@ def test_train_kernel_variants_agree_on_a_large_batch(dev):
             return loss.cpu(), grads.cpu()
         finally:
             os.environ.pop("TNERF_TRAIN_UNROLL_FROM", None)
+            os.environ.pop("TNERF_TRAIN_SYNC", None)
 
-    l_u, g_u = run(0, n, 1)                  # unrolled tile program
-    l_r, g_r = run(0, n, 1 << 30)            # rolled
-    assert torch.equal(g_u, g_r), (g_u - g_r).abs().max().item()
+    l_u, g_u = run(0, n, 1, 0)               # unrolled tile program, reproducible schedule
+    l_r, g_r = run(0, n, 1 << 30, 0)         # rolled
+    l_r2, g_r2 = run(0, n, 1 << 30, 0)       # ... twice
+    assert torch.equal(g_u, g_r) and torch.equal(g_r, g_r2), (g_u - g_r).abs().max().item()
     assert abs(l_u.item() - l_r.item()) < 1e-6          # the loss is summed with atomics across CTAs: last-bit differences between runs
-    l_a, g_a = run(0, n // 2, 1 << 30)
-    l_b, g_b = run(n // 2, n // 2, 1 << 30)
+    l_s, g_s = run(0, n, 1, 1)               # default: streams in phase
+    assert rel_l2(g_s, g_r) < 1e-5 and abs(l_s.item() - l_r.item()) < 1e-6
+    l_a, g_a = run(0, n // 2, 1 << 30, 0)
+    l_b, g_b = run(n // 2, n // 2, 1 << 30, 0)
     assert abs((l_a + l_b).item() - l_u.item()) < 1e-5
     assert rel_l2(g_a + g_b, g_u) < 2e-3     # same rays, different tile -> CTA assignment and loss-scale rounding of the fp16 gradients
 

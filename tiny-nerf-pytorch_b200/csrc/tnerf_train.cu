@@ -524,6 +524,7 @@ int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, flo
         else { p.R = 64 / S; p.n_tiles = (n + p.R - 1) / p.R; }
         grid = (p.n_tiles + 1) / 2 < h->sm_count ? (p.n_tiles + 1) / 2 : h->sm_count;
         p.bulk_reduce = bulk ? 1 : 0;
+        p.sync_streams = -1;      // decided by fused_train2 (TNERF_TRAIN_SYNC=0/1 overrides)
         used_bulk = bulk;
         if (bulk && !h->slab0_zero) cudaMemsetAsync(h->slabs, 0, (size_t)sm.total * sizeof(float), s);
         if (int rc = fused_train2(h, fp, p, Kx, (int)grid, s)) return rc;

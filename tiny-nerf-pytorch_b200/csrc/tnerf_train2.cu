@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         const float b1 = p.b1[f], b3 = p.b3[f];
         uint32_t ph_d = 0, ph_g_own = 0, ph_g_oth = 0, ph_wg = 0;
         long long g_oth_left = n_my[1 - s];
-        const bool inphase = p.S == 128;
+        const bool inphase = p.S == 128 || p.sync_streams > 0;
         long long* dbg = (p.debug && blockIdx.x == 0 && (warp & 3) == 0 && lane == 0) ? p.debug + (s ? 768 : 0) : nullptr;
         int dbg_n = 0;
         if (dbg) dbg[251] = gtimer();
@@ -748,20 +748,28 @@ int fused_train2(tnerf_handle* h, const FusedPlan& fp, const TrainParams& p, int
     ex.w[3] = {fp.layer[3].b_off, t2::S_W3, 32768u};
     ex.w[4] = {fp.layer[4].b_off, t2::S_WH, 4096u};
     const size_t smem = t2::S_MISC + sizeof(t2::Misc);
-    // Unrolled tile program for n_samples = 128 (BASELINE config 5): there the two streams of a CTA run IN PHASE, both drain
-    // warpgroups execute the same specialised code at the same time and the larger image costs nothing (+15 %, tools/sweep_c5.py).
-    // With n_samples <= 64 the streams are half a tile apart and execute different parts of the program: the rolled variant is
-    // 3-5 % faster at every batch size (tools/variant_crossover.py).  TNERF_TRAIN_UNROLL_FROM = tiles per stream from which the
-    // unrolled variant runs regardless of n_samples (tuning / tests).
+    // Schedule of the two streams of a CTA and tile program (measured: tools/variant_crossover.py, tools/sweep_c5.py):
+    //   * IN PHASE + UNROLLED (default): both streams run the same step of their tiles at the same time (each drain warpgroup drains
+    //     its dW1 half for both streams where the halves are produced), so both warpgroups execute the same per-step specialised code
+    //     and the larger image costs nothing: 5-8 % faster than the alternative from 100 to 65 536 rays at 16-64 samples, 15 % at 128
+    //     (where in-phase is the only mode: the two streams carry the halves of one ray);
+    //   * half a tile apart + ROLLED: the previous default (the foreign dW1 half is drained in the middle of the own tile, each drain
+    //     body exists once because the streams execute different steps at the same time); kept as the comparison arm
+    //     (TNERF_TRAIN_SYNC=0).
+    // TNERF_TRAIN_UNROLL_FROM = tiles per stream from which the unrolled program runs (tuning / tests).
+    TrainParams q = p;
+    const char* sy = getenv("TNERF_TRAIN_SYNC");
     const char* uf = getenv("TNERF_TRAIN_UNROLL_FROM");
-    const long long per_stream = p.n_tiles / (2ll * grid);
-    const bool unroll = Kx == 64 && (uf ? per_stream >= atoi(uf) : (p.S == 128 && per_stream >= 8));
-    auto kern = unroll ? t2::fused_train2_kernel<64, true>
-              : Kx == 64 ? t2::fused_train2_kernel<64, false> : Kx == 48 ? t2::fused_train2_kernel<48, false>
-              : Kx == 32 ? t2::fused_train2_kernel<32, false> : t2::fused_train2_kernel<16, false>;
+    const long long per_stream = q.n_tiles / (2ll * grid);
+    if (q.sync_streams < 0) q.sync_streams = sy ? (sy[0] == '1') : 1;
+    const bool unroll = uf ? per_stream >= atoi(uf) : (q.sync_streams || q.S == 128);
+    auto kern = unroll ? (Kx == 64 ? t2::fused_train2_kernel<64, true> : Kx == 48 ? t2::fused_train2_kernel<48, true>
+                          : Kx == 32 ? t2::fused_train2_kernel<32, true> : t2::fused_train2_kernel<16, true>)
+                       : (Kx == 64 ? t2::fused_train2_kernel<64, false> : Kx == 48 ? t2::fused_train2_kernel<48, false>
+                          : Kx == 32 ? t2::fused_train2_kernel<32, false> : t2::fused_train2_kernel<16, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("fused train (two-stream): shared memory request rejected"); return (int)e; }
-    kern<<<(unsigned)grid, t2::THREADS, smem, s>>>(p, ex);
+    kern<<<(unsigned)grid, t2::THREADS, smem, s>>>(q, ex);
     return count_launch();
 }
 

@@ -17,16 +17,17 @@ dev = torch.device("cuda:0")
 torch.manual_seed(0)
 enc = PositionalEncoding(10, True).to(dev)
 model = TinyNeRF(63, 128, 4, 2).to(dev)
-tr = engine.Trainer(model, enc, n_samples=64)
+tr = engine.Trainer(model, enc, n_samples=int(sys.argv[1]) if len(sys.argv) > 1 else 64)
 pose = torch.eye(4, device=dev); pose[2, 3] = 4.0
-S = 64
-for n in (2048, 4096, 6144, 8192, 12288, 16384, 32768, 65536):
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+for n in (100, 1000, 2048, 4096, 4097, 6144, 8192, 16384, 65536):
     nsets = max(2, int(140e6 / (n * (S * 4 + 20))) + 1)
     pix = torch.randint(0, 10000, (nsets, n), device=dev); tgt = torch.rand(nsets, n, 3, device=dev); jit = torch.rand(nsets, n, S, device=dev)
     rss = [engine.ray_source(c2w=pose, H=100, W=100, focal=138.9, pixel_index=pix[k]) for k in range(nsets)]
     res = []
-    for mode in ("1000000000", "1"):
+    for mode, sync in (("1000000000", "0"), ("1", "1")):
         os.environ["TNERF_TRAIN_UNROLL_FROM"] = mode
+        os.environ["TNERF_TRAIN_SYNC"] = sync
         reps = max(20, 400000 // n)
         for timed in (False, True):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -38,6 +39,6 @@ for n in (2048, 4096, 6144, 8192, 12288, 16384, 32768, 65536):
             b.record()
             torch.cuda.synchronize()
         res.append(a.elapsed_time(b) / reps * 1e3)
-    tiles = n * S // 64 / 296
-    print(f"n={n:6d} ({tiles:6.1f} tiles/stream): rolled {res[0]:8.1f} us, unrolled {res[1]:8.1f} us  ({res[0] / res[1]:.3f}x)", flush=True)
+    tiles = n * S / 64 / 296
+    print(f"n={n:6d} ({tiles:6.1f} tiles/stream): rolled / half a tile apart {res[0]:8.1f} us, unrolled / in phase {res[1]:8.1f} us  ({res[0] / res[1]:.3f}x)", flush=True)
 os.environ.pop("TNERF_TRAIN_UNROLL_FROM", None)
