@@ -516,7 +516,13 @@ int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, flo
     p.slabs = reinterpret_cast<float*>(h->slabs);
     long long grid;
     static const bool force_v1 = getenv("TNERF_TRAIN_V1") != nullptr;
-    static const bool bulk = getenv("TNERF_BULK_REDUCE") != nullptr && atoi(getenv("TNERF_BULK_REDUCE")) != 0;
+    // Default mode: streams in phase + gradients added into ONE vector by bulk async reductions (fastest; fp32 sums differ in the last
+    // bits between runs).  TNERF_TRAIN_SYNC=0 = the run-to-run reproducible mode: streams half a tile apart, per-CTA slabs summed in a
+    // fixed order.  TNERF_BULK_REDUCE=0/1 overrides the flush alone.
+    const char* sy_env = getenv("TNERF_TRAIN_SYNC");
+    const char* bk_env = getenv("TNERF_BULK_REDUCE");
+    const int sync = sy_env ? (sy_env[0] == '1') : 1;
+    const bool bulk = bk_env ? atoi(bk_env) != 0 : (sync != 0);
     bool used_bulk = false;
     if ((64 % S == 0 || S == 128) && !force_v1) {
         // two-stream kernel (tnerf_train2.cu): 64-sample tiles; at 128 samples the two streams of a CTA carry the two halves of one ray
@@ -524,7 +530,7 @@ int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, flo
         else { p.R = 64 / S; p.n_tiles = (n + p.R - 1) / p.R; }
         grid = (p.n_tiles + 1) / 2 < h->sm_count ? (p.n_tiles + 1) / 2 : h->sm_count;
         p.bulk_reduce = bulk ? 1 : 0;
-        p.sync_streams = -1;      // decided by fused_train2 (TNERF_TRAIN_SYNC=0/1 overrides)
+        p.sync_streams = sync;
         used_bulk = bulk;
         if (bulk && !h->slab0_zero) cudaMemsetAsync(h->slabs, 0, (size_t)sm.total * sizeof(float), s);
         if (int rc = fused_train2(h, fp, p, Kx, (int)grid, s)) return rc;

@@ -758,10 +758,9 @@ int fused_train2(tnerf_handle* h, const FusedPlan& fp, const TrainParams& p, int
     //     (TNERF_TRAIN_SYNC=0).
     // TNERF_TRAIN_UNROLL_FROM = tiles per stream from which the unrolled program runs (tuning / tests).
     TrainParams q = p;
-    const char* sy = getenv("TNERF_TRAIN_SYNC");
     const char* uf = getenv("TNERF_TRAIN_UNROLL_FROM");
     const long long per_stream = q.n_tiles / (2ll * grid);
-    if (q.sync_streams < 0) q.sync_streams = sy ? (sy[0] == '1') : 1;
+    if (q.sync_streams < 0) q.sync_streams = 1;
     const bool unroll = uf ? per_stream >= atoi(uf) : (q.sync_streams || q.S == 128);
     auto kern = unroll ? (Kx == 64 ? t2::fused_train2_kernel<64, true> : Kx == 48 ? t2::fused_train2_kernel<48, true>
                           : Kx == 32 ? t2::fused_train2_kernel<32, true> : t2::fused_train2_kernel<16, true>)
