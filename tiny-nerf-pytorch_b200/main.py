@@ -18,9 +18,8 @@ from rays import get_rays
 def test_render_once(model, encoder, H, W, focal, pose, device, n_samples=64, near=2.0, far=6.0, chunk=8192):
     """(H,W,3) image of one pose; one fused launch (`chunk` kept for signature compatibility)."""
     model.eval()
-    rays_o, rays_d = get_rays(H, W, focal, pose.to(device), device=device)
-    rgb = engine.render_rays(model, encoder, rays_o, rays_d, near, far, n_samples)[0]
-    return rgb.reshape(H, W, 3).clamp(0.0, 1.0)
+    # rays are generated inside the render kernel from the pose (a1 fused in)
+    return engine.render_frames(model, encoder, H, W, focal, pose.to(device).reshape(1, 4, 4), n_samples=n_samples, near=near, far=far)[0]
 
 
 def main():

@@ -58,9 +58,8 @@ def render_one(model: nn.Module, encoder: nn.Module, H: int, W: int, focal: floa
     """Full (H,W,3) frame for one pose, clamped to [0,1].  `chunk` is accepted for signature compatibility:
     the fused kernel keeps no per-sample tensors in HBM, so the frame is rendered in one launch."""
     model.eval()
-    rays_o, rays_d = get_rays(H, W, focal, pose.to(device), device=device)
-    rgb, _, _ = engine.render_rays(model, encoder, rays_o, rays_d, near, far, n_samples, t_rand=None)
-    return rgb.reshape(H, W, 3).clamp(0.0, 1.0)
+    # rays are generated inside the render kernel from the pose (a1 fused in): no get_rays launch, no (H*W,3) ray tensors
+    return engine.render_frames(model, encoder, H, W, focal, pose.to(device).reshape(1, 4, 4), n_samples=n_samples, near=near, far=far)[0]
 
 
 def _to_png(img: torch.Tensor) -> np.ndarray:
