@@ -438,6 +438,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 __global__ void adam_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                   long long n, long long n_clear, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps,
                                   float* __restrict__ tail_out, const __grid_constant__ RepackMap mp) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // programmatic stream serialisation: set up under the previous kernel's tail
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n_clear) return;
     const float gi = g[i];
@@ -624,8 +625,12 @@ int launch_adam_fused(float* p, float* g, float* m, float* v, long long n, long 
                       float eps, float* tail_out, const RepackMap& mp, cudaStream_t s) {
     if (n_clear <= 0) return 0;
     const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
-    adam_fused_kernel<<<blocks_for(n_clear, 256), 256, 0, s>>>(p, g, m, v, n, n_clear, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), b1,
-                                                                b2, eps, tail_out, mp);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)blocks_for(n_clear, 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, adam_fused_kernel, p, g, m, v, n, n_clear, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), b1, b2, eps, tail_out, mp);
     return count_launch();
 }
 int launch_allreduce_adam(float* p, float* m, float* v, long long n, const float* const* peer_grads, unsigned int* const* peer_flags,

@@ -328,6 +328,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) fused_train_kernel(const __grid
 // slab reduction: grads[flat] += (sum over CTAs of slab[.]) / scale, scattering the TMEM-native
 // [col][row] slab layout into the state_dict-ordered flat gradient.
 __global__ void reduce_slabs_kernel(ReduceArgs a) {
+    // launched with programmatic stream serialisation: the grid is set up while the training kernel drains; wait for its results here
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= a.sm.total) return;
     float s = 0.f;
@@ -548,7 +550,12 @@ int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, flo
     ra.slabs = p.slabs; ra.n_slabs = used_bulk ? 1 : (int)grid; ra.zero_after = used_bulk ? 1 : 0; ra.sm = sm; ra.D = fp.D; ra.Kx = Kx; ra.inv_scale = 1.f / p.scale; ra.scale_dev = p.scale_dev; ra.grads = grads;
     for (int l = 0; l < 4; ++l) { ra.off_w[l] = h->offsets[2 * l]; ra.off_b[l] = h->offsets[2 * l + 1]; }
     ra.off_ws = h->offsets[8]; ra.off_bs = h->offsets[9]; ra.off_wc = h->offsets[10]; ra.off_bc = h->offsets[11];
-    reduce_slabs_kernel<<<(sm.total + 255) / 256, 256, 0, s>>>(ra);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((sm.total + 255) / 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, reduce_slabs_kernel, ra);
     return count_launch();
 }
 

@@ -220,6 +220,10 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // Launched with programmatic stream serialisation: everything above (barriers, tensor-memory allocation and clearing) ran under the
+    // tail of the previous kernel in the stream (the optimiser); its results -- the refreshed operand image, the cleared loss slot -- are
+    // needed from here on.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // tiles are dealt round-robin over (cta, stream) pairs
     const long long nstreams = 2LL * gridDim.x;
@@ -768,7 +772,12 @@ int fused_train2(tnerf_handle* h, const FusedPlan& fp, const TrainParams& p, int
                           : Kx == 32 ? t2::fused_train2_kernel<32, false> : t2::fused_train2_kernel<16, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("fused train (two-stream): shared memory request rejected"); return (int)e; }
-    kern<<<(unsigned)grid, t2::THREADS, smem, s>>>(q, ex);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(t2::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, q, ex);
     return count_launch();
 }
 
