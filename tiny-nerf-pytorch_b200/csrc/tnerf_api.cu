@@ -5,10 +5,12 @@
 
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 namespace tnerf {
 
 std::atomic<long long> g_launches{0};
+int pdl_mask() { const char* e = getenv("TNERF_PDL"); return e ? atoi(e) : 7; }
 static thread_local std::string t_error;
 void set_error(const std::string& msg) { t_error = msg; }
 int count_launch() {

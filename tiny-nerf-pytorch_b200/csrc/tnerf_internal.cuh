@@ -21,6 +21,8 @@ struct GemmArgs {
 };
 
 extern std::atomic<long long> g_launches;
+// which launches use programmatic stream serialisation: 1 = training kernel, 2 = gradient scatter, 4 = optimiser (TNERF_PDL, default 7)
+int pdl_mask();
 void set_error(const std::string& msg);
 // records a launch, returns the pending cudaError_t (0 if none)
 int count_launch();

@@ -629,7 +629,7 @@ int launch_adam_fused(float* p, float* g, float* m, float* v, long long n, long 
     cfg.gridDim = dim3((unsigned)blocks_for(n_clear, 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 4) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, adam_fused_kernel, p, g, m, v, n, n_clear, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), b1, b2, eps, tail_out, mp);
     return count_launch();
 }

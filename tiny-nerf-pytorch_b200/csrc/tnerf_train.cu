@@ -554,7 +554,7 @@ int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, flo
     cfg.gridDim = dim3((unsigned)((sm.total + 255) / 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 2) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, reduce_slabs_kernel, ra);
     return count_launch();
 }

@@ -776,7 +776,7 @@ int fused_train2(tnerf_handle* h, const FusedPlan& fp, const TrainParams& p, int
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(t2::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 1) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kern, q, ex);
     return count_launch();
 }
