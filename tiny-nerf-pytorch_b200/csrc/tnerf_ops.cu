@@ -477,6 +477,7 @@ __global__ void allreduce_adam_kernel(PeerSet ps, int world, int rank, unsigned 
                                       float* __restrict__ zero_next, const __grid_constant__ RepackMap mp) {
     __shared__ int timed_out;
     if (threadIdx.x == 0) timed_out = 0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // programmatic stream serialisation: this rank's gradient (previous kernel) is complete
     if (blockIdx.x == 0 && threadIdx.x < world) {
         __threadfence_system();
         st_release_sys(ps.flags[threadIdx.x] + rank, epoch);
@@ -640,8 +641,13 @@ int launch_allreduce_adam(float* p, float* m, float* v, long long n, const float
     PeerSet ps{};
     for (int r = 0; r < world; ++r) { ps.grads[r] = peer_grads[r]; ps.flags[r] = peer_flags[r]; }
     const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
-    allreduce_adam_kernel<<<blocks_for(n + 1, 256), 256, 0, s>>>(ps, world, rank, epoch, p, m, v, n, (float)((double)lr / bc1),
-                                                                 (float)(1.0 / sqrt(bc2)), b1, b2, eps, reduced_out, zero_next, mp);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)blocks_for(n + 1, 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 4) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, allreduce_adam_kernel, ps, world, rank, epoch, p, m, v, n, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), b1, b2,
+                       eps, reduced_out, zero_next, mp);
     return count_launch();
 }
 int launch_check_finite(const float* g, long long n, int* flag, cudaStream_t s) {
