@@ -25,8 +25,8 @@ struct TrainParams {
     // two-stream kernel only: fp32 biases added in the accumulator drains (layers 1, 3) and by the compositing warps (heads)
     const float *b1, *b3, *b_sigma, *b_rgb;
     long long* debug;          // optional clock64 phase stamps of CTA 0 (tools/trace_train.py)
-    int bulk_reduce;
-    int sync_streams;      // the two streams of a CTA keep the same tile phase (dW1 halves drained where they are produced); -1 = host default           // two-stream kernel: add the CTA's gradients into ONE vector (slabs[0 .. sm.total)) with bulk async reductions
+    int bulk_reduce;           // two-stream kernel: add the CTA's gradients into ONE vector (slabs[0 .. sm.total)) with bulk async reductions
+    int sync_streams;          // the two streams of a CTA keep the same tile phase (dW1 halves drained where they are produced); -1 = host default
 };
 
 __device__ __forceinline__ uint32_t pack_sat_h2(float a, float b) {
