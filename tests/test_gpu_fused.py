@@ -171,6 +171,39 @@ def test_config4_pair_kernel_against_reference_vectors(dev, golden_c4):
     assert (depth.cpu() - torch.from_numpy(g["c4_depth"]))[keep].abs().max() < 1.2e-2
 
 
+def test_two_wide_models_alternate(dev):
+    """The pair kernel keeps its epilogue biases in a constant-bank table owned by one (model, pack version) at a time: renders of two
+    live hidden-256 models interleaved on two streams, and a re-packed model, must each see their own table."""
+    import engine
+    from encoding import PositionalEncoding
+    enc = PositionalEncoding(10, True).to(dev)
+    ma, pa = make_model((63, 256, 4, 2), 81, dev, 1.5)
+    mb, pb = make_model((63, 256, 4, 2), 82, dev, 1.5)
+    ro, rd = random_rays(500, 83)
+    ro_d, rd_d = ro.to(dev), rd.to(dev)
+    with torch.no_grad():
+        ra = engine.render_rays(ma, enc, ro_d, rd_d, 2.0, 6.0, 64, precision="f16")[0].clone()
+        rb = engine.render_rays(mb, enc, ro_d, rd_d, 2.0, 6.0, 64, precision="f16")[0].clone()
+        assert (ra - rb).abs().max() > 1e-3                      # different models
+        s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        torch.cuda.synchronize()
+        outs = []
+        for k in range(6):
+            with torch.cuda.stream(s1 if k % 2 == 0 else s2):
+                m = ma if k % 2 == 0 else mb
+                outs.append(engine.render_rays(m, enc, ro_d, rd_d, 2.0, 6.0, 64, precision="f16")[0])
+        torch.cuda.synchronize()
+        for k, o in enumerate(outs):
+            assert torch.equal(o, ra if k % 2 == 0 else rb), k
+        # in-place parameter change -> new pack version -> the table follows
+        ma.layers[1].bias.add_(0.05)
+        rc = engine.render_rays(ma, enc, ro_d, rd_d, 2.0, 6.0, 64, precision="f16")[0]
+    pa2 = {k: v.detach().cpu() for k, v in ma.state_dict().items()}
+    oc = O.render_rays(pa2, ro, rd, 2.0, 6.0, 64, None)[0]
+    keep = O.last_sample_sigma_pre(pa2, ro, rd, 2.0, 6.0, 64, None).abs() > 4e-3
+    assert (rc.cpu() - oc)[keep].abs().max() < 2e-3 and (rc - ra).abs().max() > 1e-4
+
+
 def test_config4_frame_rows_vs_oracle(dev):
     """BASELINE config 4 shape (800x800 frame, 192 samples/ray, hidden 256) through the C ABI with rays generated in-kernel from the
     pose: two rows from the middle of the frame against the oracle, and the same rows rendered as part of a larger row block
