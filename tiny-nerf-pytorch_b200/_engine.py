@@ -6,6 +6,7 @@ shared library raises at import of any op that needs it.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 import weakref
@@ -142,11 +143,12 @@ class ModelHandle:
         self.module = weakref.ref(module)
         self.device = device
         h = _p()
-        check(lib().tnerf_create(C.byref(h), device.index or 0, module.in_dim, module.hidden, module.depth,
-                                 module.skip_at), "tnerf_create")
+        check(lib().tnerf_create(C.byref(h), device.index if device.index is not None else torch.cuda.current_device(), module.in_dim,
+                                 module.hidden, module.depth, module.skip_at), "tnerf_create")
         self.h = h
         self._bound = None
         self._packed_versions = None
+        self.generation = 0          # bumped by writers that change the parameters without touching their version counters
         self.param_count = int(lib().tnerf_param_count(h))
         self.fused_ok = bool(lib().tnerf_fused_supported(h))
 
@@ -186,20 +188,35 @@ class ModelHandle:
 
     def ensure_packed(self, force: bool = False) -> None:
         ps = self.bind()
-        ver = tuple(p._version for p in ps)
+        ver = tuple(p._version for p in ps) + (self.generation,)
         if force or ver != self._packed_versions:
             check(lib().tnerf_pack_weights(self.h, stream(self.device)), "tnerf_pack_weights")
             self._packed_versions = ver
 
 
+# handles live OUTSIDE the module (keyed weakly by it): a ctypes pointer inside module.__dict__ would make
+# copy.deepcopy(model) / torch.save(model) fail, which the reference nn.Module supports
+_HANDLES: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
 def handle_for(module, device: torch.device) -> ModelHandle:
-    cache = module.__dict__.setdefault("_tnerf_handles", {})
-    key = (device.type, device.index or 0)
+    cache = _HANDLES.get(module)
+    if cache is None:
+        cache = _HANDLES[module] = {}
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
     h = cache.get(key)
     if h is None:
-        h = ModelHandle(module, device)
+        h = ModelHandle(module, torch.device("cuda", key[1]))
         cache[key] = h
     return h
+
+
+def on_device(dev):
+    """context that makes ``dev`` the current CUDA device for a stand-alone launch (no-op when it already is): the kernels of the
+    pointer-only entry points run on the current device, the reference's torch ops on the tensor's"""
+    if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+        return contextlib.nullcontext()
+    return torch.cuda.device(dev)
 
 
 def flat_grad_views(module, flat: torch.Tensor) -> List[torch.Tensor]:

@@ -36,6 +36,27 @@ int Workspace::reserve(size_t need) {
 void Workspace::release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
 
 static int bad(const char* msg) { set_error(msg); return -1; }
+// Every entry point that takes a handle runs on the handle's device whatever the caller's current device is, and leaves the
+// caller's device selected on return (torch modules work on any device; so must their replacements).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int want) {
+        if (want < 0) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != want && cudaSetDevice(want) == cudaSuccess) prev = cur;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define TN_ON_DEVICE(h) DeviceGuard device_guard_((h) ? (h)->device : -1)
+// pointer-only entry points: the device that owns one of the (required) buffers
+static int device_of(const void* p) {
+    cudaPointerAttributes a{};
+    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
+}
+#define TN_ON_DEVICE_OF(ptr) DeviceGuard device_guard_(device_of(ptr))
 static RaySource to_device_source(const tnerf_ray_source* r) {
     RaySource s;
     s.rays_o = r->rays_o; s.o_stride = r->o_stride; s.rays_d = r->rays_d; s.c2w = r->c2w; s.H = r->H; s.W = r->W;
@@ -134,6 +155,7 @@ long long tnerf_launch_count(void) { return g_launches.load(); }
 
 int tnerf_get_rays(int H, int W, float focal, const float* c2w, long long first_ray, long long n_rays, float* rays_o,
                    float* rays_d, void* stream) {
+    TN_ON_DEVICE_OF(rays_d);
     if (H <= 0 || W <= 0 || !(focal > 0.f) || !c2w || !rays_d || first_ray < 0 || n_rays < 0 || first_ray + n_rays > (long long)H * W)
         return bad("tnerf_get_rays: invalid argument");
     return launch_get_rays(H, W, focal, c2w, first_ray, n_rays, rays_o, rays_d, (cudaStream_t)stream);
@@ -141,6 +163,7 @@ int tnerf_get_rays(int H, int W, float focal, const float* c2w, long long first_
 
 int tnerf_gather3(const long long* index, long long n, long long n_src, const float* sa, float* da, const float* sb, float* db,
                   const float* sc, float* dc, void* stream) {
+    TN_ON_DEVICE_OF(index);
     if (n == 0) return 0;
     if (!index || n < 0 || (sa && !da) || (sb && !db) || (sc && !dc)) return bad("tnerf_gather3: invalid argument");
     return launch_gather3(index, n, n_src, sa, da, sb, db, sc, dc, (cudaStream_t)stream);
@@ -149,6 +172,7 @@ int tnerf_gather3(const long long* index, long long n, long long n_src, const fl
 int tnerf_stratified(const float* rays_o, long long o_stride, const float* rays_d, long long n_rays, int n_samples, float near_,
                      float far_, const float* near_ray, const float* far_ray, const float* jitter, float* z_vals, float* pts,
                      void* stream) {
+    TN_ON_DEVICE_OF(z_vals ? (const void*)z_vals : (const void*)pts);
     if (n_rays == 0) return 0;
     if (n_rays < 0 || n_samples < 1 || (pts && (!rays_o || !rays_d))) return bad("tnerf_stratified: invalid argument");
     return launch_stratified(rays_o, o_stride, rays_d, n_rays, n_samples, near_, far_, near_ray, far_ray, jitter, z_vals, pts,
@@ -156,11 +180,13 @@ int tnerf_stratified(const float* rays_o, long long o_stride, const float* rays_
 }
 
 int tnerf_posenc(const float* x, long long n_pts, int num_freqs, int include_input, float* out, void* stream) {
+    TN_ON_DEVICE_OF(out);
     if (n_pts == 0) return 0;
     if (!x || !out || n_pts < 0 || num_freqs < 0 || num_freqs > 30) return bad("tnerf_posenc: invalid argument");
     return launch_posenc(x, n_pts, num_freqs, include_input, out, (cudaStream_t)stream);
 }
 int tnerf_posenc_bwd(const float* x, const float* g_out, long long n_pts, int num_freqs, int include_input, float* g_x, void* stream) {
+    TN_ON_DEVICE_OF(g_x);
     if (n_pts == 0) return 0;
     if (!x || !g_out || !g_x || n_pts < 0 || num_freqs < 0 || num_freqs > 30) return bad("tnerf_posenc_bwd: invalid argument");
     return launch_posenc_bwd(x, g_out, n_pts, num_freqs, include_input, g_x, (cudaStream_t)stream);
@@ -169,8 +195,9 @@ int tnerf_posenc_bwd(const float* x, const float* g_out, long long n_pts, int nu
 int tnerf_create(tnerf_handle** out, int device, int in_dim, int hidden, int depth, int skip_at) {
     if (!out || in_dim < 1 || hidden < 1 || depth < 1 || depth > kMaxDepth) return bad("tnerf_create: invalid shape (1 <= depth <= 8)");
     if (skip_at == depth) return bad("tnerf_create: skip_at == depth leaves the heads with hidden+in_dim inputs (the reference errors too)");
-    cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) { set_error("cudaSetDevice failed"); return (int)e; }
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) return bad("tnerf_create: no such CUDA device");
+    DeviceGuard device_guard_(device);          // the caller's current device is left as it was
     tnerf_handle* h = new tnerf_handle();
     h->device = device; h->in_dim = in_dim; h->hidden = hidden; h->depth = depth; h->skip_at = skip_at;
     h->n_params = 2 * depth + 4;
@@ -194,6 +221,7 @@ int tnerf_create(tnerf_handle** out, int device, int in_dim, int hidden, int dep
     return 0;
 }
 void tnerf_destroy(tnerf_handle* h) {
+    TN_ON_DEVICE(h);
     if (!h) return;
     wide_release(h);
     h->ws.release();
@@ -221,11 +249,13 @@ int tnerf_bind_params(tnerf_handle* h, const float* const* params_host, int n_pa
 long long tnerf_param_count(const tnerf_handle* h) { return h ? h->param_count : -1; }
 int tnerf_fused_supported(const tnerf_handle* h) { return h && h->fused_ok; }
 int tnerf_pack_weights(tnerf_handle* h, void* stream) {
+    TN_ON_DEVICE(h);
     if (!h) return bad("NULL handle");
     return fused_pack_weights(h, (cudaStream_t)stream);
 }
 
 int tnerf_mlp_fwd(tnerf_handle* h, const float* x, long long n, float* rgb, float* sigma, float* acts, void* stream) {
+    TN_ON_DEVICE(h);
     if (n == 0) return 0;
     if (!h || h->params.empty() || !x || !rgb || !sigma || n < 0) return bad("tnerf_mlp_fwd: invalid argument / params not bound");
     float* tmp = nullptr;
@@ -239,6 +269,7 @@ int tnerf_mlp_fwd(tnerf_handle* h, const float* x, long long n, float* rgb, floa
 long long tnerf_mlp_bwd_scratch_floats(const tnerf_handle* h, long long n) { return h ? mlp_bwd_scratch_floats(h, n) : -1; }
 int tnerf_mlp_bwd(tnerf_handle* h, const float* x, long long n, const float* acts, const float* rgb, const float* sigma,
                   const float* g_rgb, const float* g_sigma, float* grads, float* g_x, float* scratch, void* stream) {
+    TN_ON_DEVICE(h);
     if (n == 0) return 0;
     if (!h || h->params.empty() || !x || !acts || !rgb || !sigma || !grads || !scratch || n < 0) return bad("tnerf_mlp_bwd: invalid argument");
     return mlp_backward_f32(h, x, n, acts, rgb, sigma, g_rgb, g_sigma, grads, g_x, scratch, (cudaStream_t)stream);
@@ -247,6 +278,7 @@ int tnerf_mlp_bwd(tnerf_handle* h, const float* x, long long n, const float* act
 int tnerf_composite_fwd(const float* rgb, const float* sigma, const float* z_vals, long long z_stride, const float* rays_d,
                         long long n_rays, int n_samples, int white_bkgd, float* comp_rgb, float* depth, float* acc, float* weights,
                         void* stream) {
+    TN_ON_DEVICE_OF(comp_rgb);
     if (n_rays == 0) return 0;
     if (!rgb || !sigma || !z_vals || !rays_d || !comp_rgb || n_rays < 0 || n_samples < 1) return bad("tnerf_composite_fwd: invalid argument");
     return launch_composite_fwd(rgb, sigma, z_vals, z_stride, rays_d, n_rays, n_samples, white_bkgd, comp_rgb, depth, acc, weights,
@@ -255,6 +287,7 @@ int tnerf_composite_fwd(const float* rgb, const float* sigma, const float* z_val
 int tnerf_composite_bwd(const float* rgb, const float* sigma, const float* z_vals, long long z_stride, const float* rays_d,
                         long long n_rays, int n_samples, int white_bkgd, const float* g_comp, const float* g_depth,
                         const float* g_acc, const float* g_weights, float* g_rgb, float* g_sigma, void* stream) {
+    TN_ON_DEVICE_OF(rgb);
     if (n_rays == 0) return 0;
     if (!rgb || !sigma || !z_vals || !rays_d || n_rays < 0 || n_samples < 1 || n_samples > 256)
         return bad("tnerf_composite_bwd: invalid argument (n_samples <= 256)");
@@ -265,6 +298,7 @@ int tnerf_composite_bwd(const float* rgb, const float* sigma, const float* z_val
 int tnerf_render_fwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long long n_rays, float near_, float far_, int n_samples,
                      const float* jitter, int white_bkgd, int precision, float* comp_rgb, float* depth, float* acc, float* weights,
                      float* rays_d_out, void* stream) {
+    TN_ON_DEVICE(h);
     if (n_rays == 0) return 0;
     if (!h || h->params.empty() || !comp_rgb || n_rays < 0 || n_samples < 1) return bad("tnerf_render_fwd: invalid argument / params not bound");
     if (int e = check_source(rays_host)) return e;
@@ -280,6 +314,7 @@ int tnerf_render_fwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long lo
 int tnerf_render_frames(tnerf_handle* h, const float* poses, int n_poses, int H, int W, float focal, long long first_ray,
                         long long rays_per_pose, float near_, float far_, int n_samples, int white_bkgd, int precision, float* comp_rgb,
                         float* depth, float* acc, void* stream) {
+    TN_ON_DEVICE(h);
     if (n_poses == 0 || rays_per_pose == 0) return 0;
     if (!h || h->params.empty() || !poses || !comp_rgb || n_poses < 0 || H <= 0 || W <= 0 || !(focal > 0.f) || first_ray < 0 ||
         rays_per_pose < 0 || first_ray + rays_per_pose > (long long)H * W || n_samples < 1)
@@ -314,6 +349,7 @@ int tnerf_render_frames(tnerf_handle* h, const float* poses, int n_poses, int H,
 int tnerf_render_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long long n_rays, float near_, float far_, int n_samples,
                      const float* jitter, int white_bkgd, int precision, const float* g_comp, const float* g_depth, const float* g_acc,
                      const float* g_weights, float grad_scale, const float* grad_scale_dev, float* grads, void* stream) {
+    TN_ON_DEVICE(h);
     if (n_rays == 0) return 0;
     if (!h || h->params.empty() || !grads || n_rays < 0 || n_samples < 1) return bad("tnerf_render_bwd: invalid argument");
     if (int e = check_source(rays_host)) return e;
@@ -329,6 +365,7 @@ int tnerf_render_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long lo
 int tnerf_train_fwd_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, const float* target, long long n_rays, float near_,
                         float far_, int n_samples, const float* jitter, int white_bkgd, int precision, float loss_denom,
                         float* comp_rgb, float* loss_sum, float* grads, void* stream) {
+    TN_ON_DEVICE(h);
     if (n_rays == 0) return 0;
     if (!h || h->params.empty() || !target || !grads || !loss_sum || n_rays < 0 || n_samples < 1 || !(loss_denom > 0.f))
         return bad("tnerf_train_fwd_bwd: invalid argument");
@@ -343,15 +380,18 @@ int tnerf_train_fwd_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, cons
 }
 
 int tnerf_mse_psnr(const float* pred, const float* target, long long n, float* out2, void* stream) {
+    TN_ON_DEVICE_OF(out2);
     if (!pred || !target || !out2 || n < 0) return bad("tnerf_mse_psnr: invalid argument");
     return launch_mse_psnr(pred, target, n, out2, (cudaStream_t)stream);
 }
 int tnerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, int step, float lr, float beta1,
                     float beta2, float eps, float inv_scale, const int* found_inf, void* stream) {
+    TN_ON_DEVICE_OF(params);
     if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || step < 1) return bad("tnerf_adam_step: invalid argument");
     return launch_adam(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, inv_scale, found_inf, (cudaStream_t)stream);
 }
 long long tnerf_packed_image_copy(const tnerf_handle* h, void* dst, long long dst_bytes, void* stream) {
+    TN_ON_DEVICE(h);
     if (!h || !h->packed) { set_error("tnerf_packed_image_copy: no packed image"); return -1; }
     FusedPlan pl;
     if (!build_plan(h, pl)) { set_error("tnerf_packed_image_copy: unsupported shape"); return -2; }
@@ -370,6 +410,7 @@ static bool params_are_flat(const tnerf_handle* h, const float* flat) {
 }
 int tnerf_optimizer_step(tnerf_handle* h, float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                          long long n_clear, int step, float lr, float beta1, float beta2, float eps, float* tail_out, int repack, void* stream) {
+    DeviceGuard device_guard_(h ? h->device : device_of(params));
     if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || n_clear < n || step < 1) return bad("tnerf_optimizer_step: invalid argument");
     RepackMap mp{};
     if (repack) {
@@ -381,6 +422,7 @@ int tnerf_optimizer_step(tnerf_handle* h, float* params, float* grads, float* ex
 int tnerf_allreduce_adam_step(tnerf_handle* h, float* params, float* exp_avg, float* exp_avg_sq, long long n, const float* const* peer_grads,
                               unsigned int* const* peer_flags, int world, int rank, unsigned int epoch, int step, float lr,
                               float beta1, float beta2, float eps, float* reduced_out, float* zero_next, int repack, void* stream) {
+    DeviceGuard device_guard_(h ? h->device : device_of(params));
     if (!params || !exp_avg || !exp_avg_sq || !peer_grads || !peer_flags || n < 0 || step < 1) return bad("tnerf_allreduce_adam_step: invalid argument");
     if (world < 1 || world > 8 || rank < 0 || rank >= world || epoch == 0) return bad("tnerf_allreduce_adam_step: need 1 <= world <= 8, 0 <= rank < world, epoch >= 1");
     for (int r = 0; r < world; ++r)
@@ -394,6 +436,7 @@ int tnerf_allreduce_adam_step(tnerf_handle* h, float* params, float* exp_avg, fl
                                  reduced_out, zero_next, mp, (cudaStream_t)stream);
 }
 int tnerf_check_finite(const float* grads, long long n, int* found_inf, void* stream) {
+    TN_ON_DEVICE_OF(grads);
     if (!grads || !found_inf || n < 0) return bad("tnerf_check_finite: invalid argument");
     return launch_check_finite(grads, n, found_inf, (cudaStream_t)stream);
 }

@@ -17,6 +17,7 @@
 // warps 8-9 / 10-11 = sample threads of stream 0/1 (rays, depths, Fourier features, compositing fwd+bwd);
 // warp 12/13 lane 0 = MMA issuer of stream 0/1; warp 14 loads the weights.
 #include <cstdlib>
+#include <type_traits>
 #include "tnerf_train.cuh"
 
 namespace tnerf {
@@ -62,12 +63,21 @@ __device__ __forceinline__ float h2sum(uint32_t h) {
     const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h));
     return a.x + a.y;
 }
+// ReLU masks.  A drain thread remembers which of its row's 64 activations were positive as two 32-bit words (one per 32-sample
+// half): pair k of a half (samples 2k, 2k+1 = one packed fp16x2 word) owns bits 15-k (low half) and 31-k (high half).  The
+// backward drains expand them again instead of re-reading the activation slot: those 16 KB reads per layer competed with the
+// operand fetches of the weight-gradient GEMMs for the shared-memory pipe (7 % of the step).
+__device__ __forceinline__ uint32_t mask_collect(uint32_t acc, uint32_t h2, int k) {    // h2: two non-negative fp16 values
+    const uint32_t t = h2 + 0x7FFF7FFFu;                 // bit 15 / 31 set iff the low / high half is non-zero (no carry between halves)
+    return acc | ((t >> k) & (0x80008000u >> k));
+}
+__device__ __forceinline__ uint32_t mask_expand(uint32_t m, int k) {                    // 0xFFFF per half whose activation was positive
+    return ((m >> (15 - k)) & 0x00010001u) * 0xFFFFu;
+}
 // backward drain, two-phase: dZ = dH * (H > 0); the masked, packed dZ row is computed into registers while the wgrad GEMM that still reads the slot
 // (H as its operand) runs; drain_store() writes it once that GEMM has committed.  `dread_bar` (optional) is arrived on as
 // soon as the accumulator has been read, so a GEMM that only needs the accumulator may be issued under the rest of the drain.
-template <bool SUM>
-__device__ __forceinline__ float drain_bwd_compute(uint32_t D, const uint8_t* slot, int f, uint32_t (&o)[32], uint32_t dread_bar) {
-    float sum = 0.f;
+__device__ __forceinline__ void drain_bwd_compute(uint32_t D, uint32_t mask_lo, uint32_t mask_hi, uint32_t (&o)[32], uint32_t dread_bar) {
     uint32_t va[2][32];
     tmem_ld32(D, va[0]);
     tc_wait_ld();
@@ -76,18 +86,11 @@ __device__ __forceinline__ float drain_bwd_compute(uint32_t D, const uint8_t* sl
     for (int c = 0; c < 2; ++c) {
         if (c == 1) { tc_wait_ld(); if (dread_bar) { tc_fence_before(); __syncwarp(); if ((threadIdx.x & 31) == 0) mbar_arrive(dread_bar); } }
         const uint32_t (&v)[32] = va[c];
+        const uint32_t m = c ? mask_hi : mask_lo;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint4 h = *reinterpret_cast<const uint4*>(slot + ((size_t)((c * 4 + j) * 128 + f) << 4));
-            uint32_t* oo = &o[(c * 4 + j) * 4];
-            oo[0] = pack_sat_h2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])) & relu_mask(h.x);
-            oo[1] = pack_sat_h2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])) & relu_mask(h.y);
-            oo[2] = pack_sat_h2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])) & relu_mask(h.z);
-            oo[3] = pack_sat_h2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])) & relu_mask(h.w);
-            if (SUM) sum += (h2sum(oo[0]) + h2sum(oo[1])) + (h2sum(oo[2]) + h2sum(oo[3]));
-        }
+        for (int k = 0; k < 16; ++k)
+            o[c * 16 + k] = pack_sat_h2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1])) & mask_expand(m, k);
     }
-    return sum;
 }
 __device__ __forceinline__ void drain_store(uint8_t* slot, int f, const uint32_t (&o)[32]) {
 #pragma unroll
@@ -284,26 +287,28 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         const long long j0 = 2LL * blockIdx.x + s;
         const int S = p.S, W = S < 32 ? S : 32, sl = lane & (W - 1);
         const bool camera = p.rs.rays_d == nullptr;
-        float cam[12];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) cam[k] = camera ? p.rs.c2w[k] : 0.f;
-        const float lin_step = (S > 1) ? __fdiv_rn(1.f, (float)(S - 1)) : 0.f;
-        const float inv_focal = camera ? __frcp_rn(p.rs.focal) : 0.f, half_w = (float)p.rs.W * 0.5f, half_h = (float)p.rs.H * 0.5f;
-        const float near_ = p.near_, far_ = p.far_;
-        auto bin = [&](int k) -> float {      // bit-exact torch.linspace / z formula (src/sampling.py:16-17)
-            const float t = (S <= 1) ? 0.f : ((k < S / 2) ? __fmul_rn(lin_step, (float)k) : __fmaf_rn(-lin_step, (float)(S - 1 - k), 1.f));
-            return __fadd_rn(__fmul_rn(near_, __fsub_rn(1.f, t)), __fmul_rn(far_, t));
-        };
-        auto zsample = [&](int k, float uu) -> float {   // src/sampling.py:21-25
-            const float zc = bin(k);
-            if (!jit) return zc;
-            const float lo = (k == 0) ? zc : __fmul_rn(0.5f, __fadd_rn(bin(k - 1), zc));
-            const float hi = (k == S - 1) ? zc : __fmul_rn(0.5f, __fadd_rn(zc, bin(k + 1)));
-            return __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), uu));
-        };
         uint32_t pk[KX / 2];
         // rays (src/rays.py:21-31), depth (sampling.py), Fourier features of sample i of `tile`; returns z and delta*|d| (volume.py:18-23)
         auto encode = [&](long long tile, float& z_out, float& gap_out) {
+            // everything only this lambda needs (pose, sampling constants) is fetched / derived HERE, once per tile, instead of living
+            // in registers across the compositing: the sample warps run on 96 registers and the scans need room to pipeline
+            float cam[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) cam[k] = camera ? __ldg(p.rs.c2w + k) : 0.f;
+            const float lin_step = (S > 1) ? __fdiv_rn(1.f, (float)(S - 1)) : 0.f;
+            const float inv_focal = camera ? __frcp_rn(p.rs.focal) : 0.f, half_w = (float)p.rs.W * 0.5f, half_h = (float)p.rs.H * 0.5f;
+            const float near_ = p.near_, far_ = p.far_;
+            auto bin = [&](int k) -> float {      // bit-exact torch.linspace / z formula (src/sampling.py:16-17)
+                const float t = (S <= 1) ? 0.f : ((k < S / 2) ? __fmul_rn(lin_step, (float)k) : __fmaf_rn(-lin_step, (float)(S - 1 - k), 1.f));
+                return __fadd_rn(__fmul_rn(near_, __fsub_rn(1.f, t)), __fmul_rn(far_, t));
+            };
+            auto zsample = [&](int k, float uu) -> float {   // src/sampling.py:21-25
+                const float zc = bin(k);
+                if (!jit) return zc;
+                const float lo = (k == 0) ? zc : __fmul_rn(0.5f, __fadd_rn(bin(k - 1), zc));
+                const float hi = (k == S - 1) ? zc : __fmul_rn(0.5f, __fadd_rn(zc, bin(k + 1)));
+                return __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), uu));
+            };
             const long long ray = inphase ? (tile >> 1) : tile * p.R + i / S;
             const int si = inphase ? (int)(tile & 1) * 64 + i : i % S;
             float pt[3] = {0.f, 0.f, 0.f};
@@ -356,8 +361,6 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             const bool more = t + 1 < n_my[s];
             float z_next = 0.f, gap_next = 0.f;
             T2_STAMP();
-            if (more) encode(tile + nstreams, z_next, gap_next);          // under the forward GEMMs of this tile
-            T2_STAMP();
             if (t >= 0) {
             // per-ray inputs of the loss are fetched before the heads are ready
             const long long ray = inphase ? (tile >> 1) : tile * p.R + i / S;
@@ -385,77 +388,95 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                 own.w = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(v[3]) + bb)));
             }
             // ---- compositing forward + loss gradient + reverse scan, one sample per thread, all in registers
-            //      (src/volume.py:18-44 and its backward) ----
-            const float e = valid ? __expf(-own.x * gap_cur) : 1.f;
-            const float alpha = valid ? 1.f - e : 0.f;
-            const float q = valid ? 1.f - alpha + kEpsT : 1.f;
-            float incl = q;
+            //      (src/volume.py:18-44 and its backward).  The body is specialised on the number of
+            //      samples per ray (64 and 128 at compile time: no width tests around the shuffles, unrolled chunk stitching);
+            //      other counts take the generic instance.
+            //      Forward: ONE inclusive scan of the per-sample maps (T, C) -> (T q, C + T alpha c) gives the transmittance in
+            //      front of every sample and, in the segment's last lane, the four ray sums (colour, opacity) -- five shuffle
+            //      levels instead of five for the product scan plus five for the sums.
+            //      Reverse: suffix composition of R -> g alpha + q R (division-free). ----
+            T2_STAMP();                                              // heads read and activated
+            auto composite = [&](auto SC) __attribute__((always_inline)) {
+                constexpr int SCT = decltype(SC)::value;
+                const int Wc = SCT ? (SCT < 32 ? SCT : 32) : W;
+                const int slc = SCT >= 32 ? lane : sl;
+                const int nch = SCT == 128 ? 4 : (SCT == 64 ? 2 : nchain);
+                const float e = valid ? __expf(-own.x * gap_cur) : 1.f;
+                const float alpha = valid ? 1.f - e : 0.f;
+                const float q = valid ? 1.f - alpha + kEpsT : 1.f;
+                float Qi = q, A0 = alpha * own.y, A1 = alpha * own.z, A2 = alpha * own.w, A3 = alpha;
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                if (off < W) {
-                    const float up = __shfl_up_sync(0xffffffffu, incl, off, W);
-                    if (sl >= off) incl *= up;
+                for (int off = 1; off < 32; off <<= 1) {
+                    if (SCT >= 32 || off < Wc) {
+                        const float qu = __shfl_up_sync(0xffffffffu, Qi, off, Wc);
+                        const float a0 = __shfl_up_sync(0xffffffffu, A0, off, Wc), a1 = __shfl_up_sync(0xffffffffu, A1, off, Wc);
+                        const float a2 = __shfl_up_sync(0xffffffffu, A2, off, Wc), a3 = __shfl_up_sync(0xffffffffu, A3, off, Wc);
+                        if (slc >= off) {      // earlier segment (qu, a) followed by this one: (qu Q, a + qu A)
+                            A0 = fmaf(qu, A0, a0); A1 = fmaf(qu, A1, a1); A2 = fmaf(qu, A2, a2); A3 = fmaf(qu, A3, a3);
+                            Qi *= qu;
+                        }
+                    }
                 }
-            }
-            float excl = __shfl_up_sync(0xffffffffu, incl, 1, W);
-            if (sl == 0) excl = 1.f;
-            const float wl = alpha * excl;
-            float c0 = wl * own.y, c1 = wl * own.z, c2 = wl * own.w, asum = wl;     // four sums over the ray segment, reduced together
+                float excl = __shfl_up_sync(0xffffffffu, Qi, 1, Wc);
+                if (slc == 0) excl = 1.f;
+                T2_STAMP();                                          // forward scan done
+                float c0, c1, c2, asum, Tc = 1.f;
+                if (nch > 1) {       // stitch the chunks of the ray: chunk c enters with T = product of the earlier chunks' transmittances
+                    if (lane == 31) { float* x = xch + cw * 8; x[0] = Qi; x[1] = A0; x[2] = A1; x[3] = A2; x[4] = A3; }
+                    bar_sync(cbar, cthreads);
+                    float T = 1.f;
+                    c0 = c1 = c2 = asum = 0.f;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                if (o < W) {
-                    c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o);
-                    c2 += __shfl_xor_sync(0xffffffffu, c2, o); asum += __shfl_xor_sync(0xffffffffu, asum, o);
+                    for (int c = 0; c < 4; ++c) {
+                        if (c < nch) {
+                            const float* x = xch + c * 8;
+                            if (c == cw) Tc = T;
+                            c0 = fmaf(T, x[1], c0); c1 = fmaf(T, x[2], c1); c2 = fmaf(T, x[3], c2); asum = fmaf(T, x[4], asum);
+                            T *= x[0];
+                        }
+                    }
+                } else {             // the segment's last lane holds the ray sums
+                    c0 = __shfl_sync(0xffffffffu, A0, Wc - 1, Wc); c1 = __shfl_sync(0xffffffffu, A1, Wc - 1, Wc);
+                    c2 = __shfl_sync(0xffffffffu, A2, Wc - 1, Wc); asum = __shfl_sync(0xffffffffu, A3, Wc - 1, Wc);
                 }
-            }
-            float Tc = 1.f;
-            if (nchain > 1) {       // stitch the chunks of the ray: chunk c enters with T = prod of the earlier chunks' transmittances
-                const float Pw = __shfl_sync(0xffffffffu, incl, 31);
-                if (lane == 0) { float* x = xch + cw * 8; x[0] = Pw; x[1] = c0; x[2] = c1; x[3] = c2; x[4] = asum; }
-                bar_sync(cbar, cthreads);
-                float T = 1.f;
-                c0 = c1 = c2 = asum = 0.f;
-                for (int c = 0; c < nchain; ++c) {
-                    const float* x = xch + c * 8;
-                    if (c == cw) Tc = T;
-                    c0 = fmaf(T, x[1], c0); c1 = fmaf(T, x[2], c1); c2 = fmaf(T, x[3], c2); asum = fmaf(T, x[4], asum);
-                    T *= x[0];
+                T2_STAMP();                                          // ray sums known
+                const float Ti = Tc * excl, w = alpha * Ti;
+                const float bgc = p.white ? 1.f - asum : 0.f;
+                const float C0 = c0 + bgc, C1 = c1 + bgc, C2 = c2 + bgc;
+                float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+                const bool leader = slc == 0 && cw == 0;
+                if (valid) {
+                    if (p.target) {
+                        const float e0 = C0 - t0, e1 = C1 - t1, e2 = C2 - t2;
+                        g0 = 2.f * e0 * p.inv_denom; g1 = 2.f * e1 * p.inv_denom; g2 = 2.f * e2 * p.inv_denom;
+                        if (leader) loss_acc += (e0 * e0 + e1 * e1 + e2 * e2) * p.inv_denom;
+                    } else { g0 = t0; g1 = t1; g2 = t2; }
+                    if (p.comp && leader) { p.comp[3 * ray] = C0; p.comp[3 * ray + 1] = C1; p.comp[3 * ray + 2] = C2; }
                 }
-            }
-            const float Ti = Tc * excl, w = alpha * Ti;
-            const float bgc = p.white ? 1.f - asum : 0.f;
-            const float C0 = c0 + bgc, C1 = c1 + bgc, C2 = c2 + bgc;
-            float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-            const bool leader = sl == 0 && cw == 0;
-            if (valid) {
-                if (p.target) {
-                    const float e0 = C0 - t0, e1 = C1 - t1, e2 = C2 - t2;
-                    g0 = 2.f * e0 * p.inv_denom; g1 = 2.f * e1 * p.inv_denom; g2 = 2.f * e2 * p.inv_denom;
-                    if (leader) loss_acc += (e0 * e0 + e1 * e1 + e2 * e2) * p.inv_denom;
-                } else { g0 = t0; g1 = t1; g2 = t2; }
-                if (p.comp && leader) { p.comp[3 * ray] = C0; p.comp[3 * ray + 1] = C1; p.comp[3 * ray + 2] = C2; }
-            }
-            const float gconst = ga - (p.white ? (g0 + g1 + g2) : 0.f);
-            const float g = valid ? (g0 * own.y + g1 * own.z + g2 * own.w + gd * z_cur + gconst) : 0.f;
-            float Aa = g * alpha, Qq = q;        // suffix composition of the maps R -> g a + q R
+                const float gconst = ga - (p.white ? (g0 + g1 + g2) : 0.f);
+                const float g = valid ? (g0 * own.y + g1 * own.z + g2 * own.w + gd * z_cur + gconst) : 0.f;
+                float Aa = g * alpha, Qq = q;        // suffix composition of the maps R -> g a + q R
+                float Rc = 0.f;
+                T2_STAMP();                                          // loss gradient ready
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                if (off < W) {
-                    const float An = __shfl_down_sync(0xffffffffu, Aa, off, W);
-                    const float Qn = __shfl_down_sync(0xffffffffu, Qq, off, W);
-                    if (sl + off < W) { Aa = fmaf(Qq, An, Aa); Qq *= Qn; }
+                for (int off = 1; off < 32; off <<= 1) {
+                    if (SCT >= 32 || off < Wc) {
+                        const float An = __shfl_down_sync(0xffffffffu, Aa, off, Wc);
+                        const float Qn = __shfl_down_sync(0xffffffffu, Qq, off, Wc);
+                        if (slc + off < Wc) { Aa = fmaf(Qq, An, Aa); Qq *= Qn; }
+                    }
                 }
-            }
-            float Rc = 0.f;
-            if (nchain > 1) {       // R entering this chunk from behind = the later chunks' affine maps applied to 0, last chunk first
-                if (lane == 0) { xch[32 + 2 * cw] = Aa; xch[33 + 2 * cw] = Qq; }
-                bar_sync(cbar, cthreads);
-                for (int c = nchain - 1; c > cw; --c) Rc = fmaf(xch[33 + 2 * c], Rc, xch[32 + 2 * c]);
-            }
-            const float Rprev = fmaf(Qq, Rc, Aa);
-            float Ri = __shfl_down_sync(0xffffffffu, Rprev, 1, W);
-            if (sl == W - 1) Ri = Rc;
-            {
+                if (nch > 1) {       // R entering this chunk from behind = the later chunks' affine maps applied to 0, last chunk first
+                    if (lane == 0) { xch[32 + 2 * cw] = Aa; xch[33 + 2 * cw] = Qq; }
+                    bar_sync(cbar, cthreads);
+#pragma unroll
+                    for (int c = 3; c > 0; --c)
+                        if (c < nch && c > cw) Rc = fmaf(xch[33 + 2 * c], Rc, xch[32 + 2 * c]);
+                }
+                T2_STAMP();                                          // reverse scan + stitch done
+                const float Rprev = fmaf(Qq, Rc, Aa);
+                float Ri = __shfl_down_sync(0xffffffffu, Rprev, 1, Wc);
+                if (slc == Wc - 1) Ri = Rc;
                 const float dsig = Ti * (g - Ri) * gap_cur * e;
                 const float s0 = (own.x > 0.f) ? dsig * gscale : 0.f;
                 const float s1 = w * g0 * own.y * (1.f - own.y) * gscale;
@@ -468,9 +489,20 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                 if (lane == 0) mbar_arrive(bar_dzh);
                 T2_STAMP();
                 hb[0] += s0; hb[1] += s1; hb[2] += s2; hb[3] += s3;      // head bias gradients: per-thread partials, reduced at the end
+            };
+            if (S == 64) composite(std::integral_constant<int, 64>{});
+            else if (S == 128) composite(std::integral_constant<int, 128>{});
+            else composite(std::integral_constant<int, 0>{});
             }
-            mbar_wait(bar_xfree, ph_xfree); ph_xfree ^= 1;       // last GEMM of the tile has completed: X may be replaced
+            // Fourier features of the NEXT tile, computed under the backward GEMMs of this one.  (Computed before the compositing they
+            // stayed live through it -- 32 registers -- and the compiler, short of registers, funnelled every shuffle of the scans
+            // through one register: five dependent shuffle latencies per level instead of one.)
             T2_STAMP();
+            if (more) encode(tile + nstreams, z_next, gap_next);
+            T2_STAMP();
+            if (t >= 0) {
+                mbar_wait(bar_xfree, ph_xfree); ph_xfree ^= 1;   // last GEMM of the tile has completed: X may be replaced
+                T2_STAMP();
             }
             if (more) { store_x(); z_cur = z_next; gap_cur = gap_next; }
         }
@@ -505,6 +537,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         uint32_t stash[32];             // H1 row of this feature, parked between layer 2 forward and layer 2 wgrad
 #pragma unroll
         for (int j = 0; j < 32; ++j) stash[j] = 0u;
+        uint32_t mk0a = 0u, mk0b = 0u, mk1a = 0u, mk1b = 0u, mk2a = 0u, mk2b = 0u, mk3a = 0u, mk3b = 0u;   // ReLU masks of H0 (recomputed), H1, H2, H3
         float dwh[4] = {0.f, 0.f, 0.f, 0.f}, db1 = 0.f, db3 = 0.f;
         const float b1 = p.b1[f], b3 = p.b3[f];
         uint32_t ph_d = 0, ph_g_own = 0, ph_g_oth = 0, ph_wg = 0;
@@ -581,6 +614,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                     const float bias = (step == 1) ? b1 : b3;
                     const bool park = step == 1;
                     uint32_t va[2][32];
+                    uint32_t mk[2] = {0u, 0u};
                     tmem_ld32(D_own, va[0]);
                     tc_wait_ld();
                     tmem_ld32(D_own + 32, va[1]);
@@ -600,9 +634,13 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                             o.z = pack_relu_h2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
                             o.w = pack_relu_h2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
                             *reinterpret_cast<uint4*>(slot + ((size_t)((c * 4 + j) * 128 + f) << 4)) = o;
+                            if (step != 0)        // the first H0 is recomputed before its mask is needed
+                                mk[c] = mask_collect(mask_collect(mask_collect(mask_collect(mk[c], o.x, 4 * j), o.y, 4 * j + 1), o.z, 4 * j + 2), o.w, 4 * j + 3);
                             if (park) { stash[(c * 4 + j) * 4 + 0] = o.x; stash[(c * 4 + j) * 4 + 1] = o.y; stash[(c * 4 + j) * 4 + 2] = o.z; stash[(c * 4 + j) * 4 + 3] = o.w; }
                         }
                     }
+                    if (step == 1) { mk1a = mk[0]; mk1b = mk[1]; } else if (step == 2) { mk2a = mk[0]; mk2b = mk[1]; }
+                    else if (step == 3) { mk3a = mk[0]; mk3b = mk[1]; } else if (step == 9) { mk0a = mk[0]; mk0b = mk[1]; }
                     T2_SIGNAL(bar_in);
                 } else if (kind == K_SMALL) {
                     uint32_t v[4];
@@ -615,7 +653,9 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                     // dZ = dH * (H > 0): computed into registers while the weight-gradient GEMM that still reads the slot runs,
                     // stored once that GEMM has committed (steps 7, 8); steps 6 and 11 store at once
                     uint32_t o[32];
-                    drain_bwd_compute<false>(D_own, slot, f, o, step == 8 ? bar_dread : 0u);
+                    const uint32_t ma = step == 6 ? mk3a : step == 7 ? mk2a : step == 8 ? mk1a : mk0a;
+                    const uint32_t mb = step == 6 ? mk3b : step == 7 ? mk2b : step == 8 ? mk1b : mk0b;
+                    drain_bwd_compute(D_own, ma, mb, o, step == 8 ? bar_dread : 0u);
                     if (step == 6 || step == 8) {                     // bias gradient of layer 3 / 1 = row sum of dZ3 / dZ1
                         float sum = 0.f;
 #pragma unroll

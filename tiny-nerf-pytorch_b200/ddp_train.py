@@ -87,6 +87,59 @@ def main(cfg: Config):
         dist.destroy_process_group()
 
 
+def exchange_self_check(device, steps: int = 4, n: int = 1024, n_samples: int = 64):
+    """Multi-rank parity of the gradient exchange, callable from any initialised process group (bench.py runs it in the warm-up of
+    every N > 1 line; tools/ddp_check.py and tests/test_gpu_ddp.py wrap it):
+      * N-rank training on N ray shards == 1-rank training on the concatenated batch (up to fp32 summation order): every rank
+        also trains alone on the whole batch and compares parameters and losses;
+      * the parameters are BIT-IDENTICAL on every rank after the sharded steps (rank-ordered sum of the exchange kernel);
+      * the peer-memory exchange and the NCCL exchange agree.
+    Returns a dict with ``ok`` and the measured differences."""
+    from encoding import PositionalEncoding
+    from nerf import TinyNeRF
+    rank, world = dist.get_rank(), dist.get_world_size()
+    pose = torch.eye(4, device=device); pose[2, 3] = 4.0
+    g = torch.Generator().manual_seed(77)
+    pix_all = torch.randint(0, 10000, (steps, world * n), generator=g)
+    tgt_all = torch.rand(steps, world * n, 3, generator=g)
+    jit_all = torch.rand(steps, world * n, n_samples, generator=g)
+
+    def run(comm, shard):
+        torch.manual_seed(0)
+        enc = PositionalEncoding(10, True).to(device)
+        model = TinyNeRF(63, 128, 4, 2).to(device)
+        if shard:
+            tr = engine.Trainer(model, enc, n_samples=n_samples, comm=comm)
+            sl = slice(rank * n, (rank + 1) * n)
+        else:                                   # every rank trains alone on the whole batch (no exchange)
+            tr = engine.Trainer(model, enc, n_samples=n_samples, comm="nccl")
+            tr.world, tr.comm = 1, "none"
+            sl = slice(0, world * n)
+        losses = []
+        for k in range(steps):
+            out = tr.step_pixels(pose, 100, 100, 138.9, pix_all[k, sl].to(device), tgt_all[k, sl].to(device), jit_all[k, sl].to(device),
+                                 global_rays=world * n)
+            losses.append(out.clone())
+        torch.cuda.synchronize(device)
+        return tr.flat.clone(), torch.cat(losses), tr.comm
+
+    p_p2p, l_p2p, used = run(None, True)         # the default exchange (peer memory when available)
+    p_nccl, _, _ = run("nccl", True)
+    p_one, l_one, _ = run("nccl", False)
+    gathered = [torch.empty_like(p_p2p) for _ in range(world)]
+    dist.all_gather(gathered, p_p2p)
+    bit_identical = all(torch.equal(gathered[0], x) for x in gathered)
+    res = {"world": world, "comm": used, "steps": steps, "rays_per_rank": n, "bit_identical_across_ranks": bool(bit_identical),
+           "max_abs_p2p_vs_nccl": float((p_p2p - p_nccl).abs().max()), "max_abs_sharded_vs_single_rank": float((p_p2p - p_one).abs().max()),
+           "max_abs_loss_diff": float((l_p2p - l_one).abs().max()), "loss": float(l_p2p[-1])}
+    ok = (bit_identical and res["max_abs_p2p_vs_nccl"] < 5e-5 and res["max_abs_sharded_vs_single_rank"] < 2e-4 and res["max_abs_loss_diff"] < 1e-5
+          and bool(torch.isfinite(p_p2p).all()))
+    flag = torch.tensor([1.0 if ok else 0.0], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # one verdict for the job
+    res["ok"] = bool(flag.item() > 0.5)
+    return res
+
+
 @torch.no_grad()
 def render_sharded(model, encoder, H, W, focal, pose, device, n_samples=64, near=2.0, far=6.0):
     """full frame with contiguous ray ranges per rank and one all_gather of the (rays/world, 3) shards"""

@@ -255,6 +255,10 @@ class Trainer:
         self.steps += 1
         st = E.stream(self.device)
         repack = 1 if self.prec == E.PREC_F16_TC else 0
+        if not repack:
+            # the optimiser kernel writes the flat parameters without touching their version counters: a later fp16 render
+            # (previews, render_frames) must not reuse an operand image packed from older weights
+            self.h.generation += 1
         if self.comm == "p2p":
             k = self.steps & 1
             E.check(E.lib().tnerf_allreduce_adam_step(self.h.h, E.ptr(self.flat), E.ptr(self.exp_avg), E.ptr(self.exp_avg_sq), self.P,
@@ -285,6 +289,13 @@ class Trainer:
         n = int(pixel_index.shape[0])
         if jitter is None:
             jitter = torch.rand((n, self.S), dtype=torch.float32, device=self.device)
+        # the C ABI takes raw pointers: fp32 pose / targets / jitter, int64 pixel ids, all dense (no copies when they already are)
+        E.need_cuda(c2w, pixel_index, target, jitter)
+        c2w, target, jitter = E.f32c(c2w), E.f32c(target), E.f32c(jitter)
+        if pixel_index.dtype != torch.int64 or not pixel_index.is_contiguous():
+            pixel_index = pixel_index.long().contiguous()
+        if tuple(target.shape) != (n, 3) or tuple(jitter.shape) != (n, self.S) or c2w.numel() < 12:
+            raise ValueError(f"step_pixels: expected target ({n}, 3), jitter ({n}, {self.S}), c2w (4, 4)")
         rs = ray_source(c2w=c2w, H=H, W=W, focal=focal, pixel_index=pixel_index)
         return self._launch(rs, target, n, jitter, global_rays)
 
