@@ -490,7 +490,7 @@ def main():
             if key not in rs_cache:
                 rs_cache[key] = engine.ray_source(c2w=poses[i % 106], H=100, W=100, focal=FOCAL, pixel_index=pix_d[k])
             E.check(E.lib().tnerf_train_fwd_bwd(tr.h.h, C.byref(rs_cache[key]), E.ptr(tgt_d[k]), n_rays, 2.0, 6.0, S, E.ptr(jit_d[k]), 1, tr.prec,
-                                                3.0 * n_rays, None, E.ptr(tr.loss_view), E.ptr(tr.gbuf), E.stream(dev)))
+                                                3.0 * n_rays, None, E.ptr(tr.loss_view), E.ptr(tr.gbuf), None, None, E.stream(dev)))
 
         def step(i):
             k = i % n_sets
@@ -644,7 +644,7 @@ def main():
                 sb[0].copy_(pix_h[0], non_blocking=True); sb[1].copy_(tgt_h[0], non_blocking=True); sb[2].copy_(jit_h[0], non_blocking=True)
                 rs = engine.ray_source(c2w=poses[i % 106], H=100, W=100, focal=FOCAL, pixel_index=sb[0])
                 E.check(E.lib().tnerf_train_fwd_bwd(tr.h.h, C.byref(rs), E.ptr(sb[1]), rays, 2.0, 6.0, S, E.ptr(sb[2]), 1, tr.prec, 3.0 * rays, None,
-                                                    E.ptr(tr.loss_view), E.ptr(tr.gbuf), E.stream(dev)))
+                                                    E.ptr(tr.loss_view), E.ptr(tr.gbuf), None, None, E.stream(dev)))
                 loss_h.copy_(tr.loss_view, non_blocking=True)
             ke = max(1, min(K, 20))
             t_e, _ = timed_rounds(e2e_step, 0, align=1, k=ke, r=3)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TNERF_ABI_VERSION 1
+#define TNERF_ABI_VERSION 2
 
 typedef struct tnerf_handle tnerf_handle;
 
@@ -86,6 +86,13 @@ long long tnerf_param_count(const tnerf_handle* h);
 /* The fused entry points generate the Fourier features themselves.  By default the encoding is
  * inferred from in_dim (6L+3 -> include_input); call this to state it explicitly. */
 int  tnerf_set_encoding(tnerf_handle* h, int num_freqs, int include_input);
+/* Schedule options of the fused training kernel (value -1 = built-in choice; the environment variables TNERF_TRAIN_SYNC,
+ * TNERF_BULK_REDUCE and TNERF_TRAIN_UNROLL_FROM give the defaults when the handle is created):
+ *   "train_sync"  1 = the two tile streams of a CTA run in phase (fastest; fp32 gradient sums differ in the last bits between
+ *                 runs), 0 = half a tile apart, fixed accumulation order: run-to-run REPRODUCIBLE gradients;
+ *   "bulk_reduce" 1 = CTAs add their gradients into one vector with bulk async reductions, 0 = per-CTA slabs summed in order;
+ *   "unroll_from" tiles per stream from which the unrolled tile program is used (tuning / tests). */
+int  tnerf_set_option(tnerf_handle* h, const char* name, int value);
 /* Developer hook: a device buffer of 2048 int64 that receives clock64() phase stamps of CTA 0 of the fused
  * forward kernel (tools/trace_fwd.py); NULL disables it. */
 int  tnerf_set_debug_buffer(tnerf_handle* h, void* buf);
@@ -156,7 +163,8 @@ int tnerf_render_frames(tnerf_handle* h, const float* poses, int n_poses, int H,
  * (implicit backward of src/train.py:126).  Upstream grads as in tnerf_composite_bwd.
  * grads (param_count) is ACCUMULATED into.  The tensor-core path carries gradients as fp16 operands:
  * they are multiplied by a power-of-two loss scale on entry and divided on exit -- grad_scale_dev
- * (1 device float) if non-NULL, else grad_scale (<= 0 means 1). */
+ * (1 device float) if non-NULL, else grad_scale if > 0, else (grad_scale <= 0) a scale chosen ON THE DEVICE
+ * from the largest upstream gradient (2^floor(log2(64/max|g|)), one small launch, no host synchronisation). */
 int tnerf_render_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long long n_rays,
                      float near_, float far_, int n_samples, const float* jitter, int white_bkgd,
                      int precision, const float* g_comp, const float* g_depth, const float* g_acc,
@@ -166,11 +174,15 @@ int tnerf_render_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long lo
 /* Whole training step body: forward, MSE against target (n,3), backward   (src/train.py:114-126)
  * loss_denom: the divisor of the summed squared error (3*n_rays for one process, 3*global rays
  * under ray-sharded data parallel).  Outputs: comp_rgb (n,3) or NULL, loss_sum (1 float,
- * ACCUMULATED: sum of squared errors / loss_denom), grads (param_count) ACCUMULATED. */
+ * ACCUMULATED: sum of squared errors / loss_denom), grads (param_count) ACCUMULATED.
+ * GradScaler semantics of src/train.py:81,126 (scaler.scale(loss).backward()) on the device: loss_scale_dev (1 device float, e.g.
+ * tnerf_scaler.state) replaces the built-in power-of-two loss scale of the tensor-core path (NULL = built-in); found_inf (1 device
+ * float or NULL) is SET TO 1 when the step overflowed -- a scaled head gradient beyond 2^10 (the fp16 operands of the backward chain
+ * would saturate), or a non-finite loss / gradient.  It is never cleared here. */
 int tnerf_train_fwd_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, const float* target,
                         long long n_rays, float near_, float far_, int n_samples, const float* jitter,
                         int white_bkgd, int precision, float loss_denom, float* comp_rgb, float* loss_sum,
-                        float* grads, void* stream);
+                        float* grads, const float* loss_scale_dev, float* found_inf, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a7  loss + PSNR                                    (src/train.py:122-123, src/utils.py:14-15)
@@ -183,28 +195,50 @@ int tnerf_mse_psnr(const float* pred, const float* target, long long n, float* o
 int tnerf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                     int step, float lr, float beta1, float beta2, float eps, float inv_scale,
                     const int* found_inf, void* stream);
+/* a9  torch.amp.GradScaler.step()/update() (src/train.py:81,127-128) as device-resident state consumed by the optimiser entry
+ * points below -- no host synchronisation, no extra launch.  state: 16 floats on the device, 8-byte aligned:
+ *   [0] loss scale            [1] clean steps since the scale last changed      [2] optimiser steps actually applied
+ *   [8..15] four doubles: (beta1^t, beta2^t) for call parity 0 and 1 -- initialise both pairs to beta^t of the restored step
+ *           count (1.0, 1.0 for a fresh optimiser) and [0] to the initial scale.
+ * Per call: if the overflow flag is non-zero the step is SKIPPED (parameters and moments untouched, the step count does not
+ * advance) and the scale is multiplied by backoff_factor; otherwise Adam is applied with the bias corrections of the DEVICE step
+ * count, and after growth_interval clean steps in a row the scale is multiplied by growth_factor. */
+typedef struct tnerf_scaler {
+    float*       state;
+    const float* found_inf;      /* this call's overflow flag (device float; tnerf_train_fwd_bwd sets it).  tnerf_allreduce_adam_step
+                                    ignores it: there the flag is element n+1 of the exchanged vectors                              */
+    float*       clear_next;     /* device float cleared for the NEXT call, or NULL: keep two flags and alternate them by `call`     */
+    float        growth_factor, backoff_factor;   /* torch defaults: 2, 0.5 */
+    int          growth_interval;                 /* torch default: 2000    */
+    unsigned int call;           /* strictly increasing per optimiser call (skipped or not); its parity selects the beta-power pair */
+} tnerf_scaler;
+
 /* a9 + (f) N1: the optimiser step of the training loop as ONE launch: Adam as above (inv_scale = 1) on the flat parameter
  * vector, the gradient vector cleared for the next step (grads[0 .. n_clear), n_clear >= n so a trailing loss slot is cleared
  * too; their old values go to tail_out if non-NULL) and -- repack != 0 -- the fp16 operand image of the tensor-core kernels refreshed in place (replaces memset +
- * tnerf_adam_step + tnerf_pack_weights; needs the handle's parameters bound as views of `params` in state_dict order). */
+ * tnerf_adam_step + tnerf_pack_weights; needs the handle's parameters bound as views of `params` in state_dict order).
+ * scaler_host (HOST struct, may be NULL): GradScaler semantics as described at tnerf_scaler; `step` is then only used when
+ * scaler_host is NULL. */
 int tnerf_optimizer_step(tnerf_handle* h, float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                          long long n_clear, int step, float lr, float beta1, float beta2, float eps, float* tail_out, int repack,
-                         void* stream);
+                         const tnerf_scaler* scaler_host, void* stream);
 
 /* (e) multi-GPU exchange step (new work defined by BASELINE config 3; the reference is single-process):
  * one-shot all-reduce(sum) of the ranks' flat [gradient(n) | loss(1)] vectors over NVLink peer memory fused with the
  * optimiser step above -- what DDP would do with ncclAllReduce + optimizer.step() (src/train.py:126-127 per rank).
  * peer_grads[r] / peer_flags[r]: HOST arrays of `world` DEVICE pointers, peer-mapped into this process (e.g. CUDA IPC or
- * torch symmetric memory): rank r's vector of n+1 floats for this epoch and rank r's flag array (>= world uint32, zeroed
- * once).  epoch: same strictly increasing value (>= 1) on every rank for the same step; vectors must be double-buffered by
- * epoch parity.  The sum is formed in rank order, so every rank computes bit-identical parameters.  reduced_out (n+1 floats
- * or NULL) receives the reduced vector; zero_next (n+1 floats or NULL) = this rank's OTHER-parity vector, cleared here for
- * the next step; repack as in tnerf_optimizer_step (h may be NULL when 0).  A peer that never arrives traps after ~3 s
- * instead of hanging the device. */
+ * torch symmetric memory): rank r's vector for this epoch (16-byte aligned, padded to a multiple of 4 floats) and rank r's flag
+ * array (>= world uint32, zeroed once).  epoch: same strictly increasing value (>= 1) on every rank for the same step; vectors
+ * must be double-buffered by epoch parity.  The sum is formed in rank order, so every rank computes bit-identical parameters.
+ * With scaler_host the vectors are [gradient(n) | loss | overflow flag]: the flags are summed too, so every rank takes the same
+ * skip / apply decision.  reduced_out (vector length or NULL) receives the reduced vector; zero_next (same length or NULL) = this
+ * rank's OTHER-parity vector, cleared here for the next step; repack as in tnerf_optimizer_step (h may be NULL when 0).  A peer
+ * that has not arrived after TNERF_PEER_TIMEOUT_S seconds (environment, default 60, 0 = wait forever) traps instead of hanging
+ * the device. */
 int tnerf_allreduce_adam_step(tnerf_handle* h, float* params, float* exp_avg, float* exp_avg_sq, long long n,
                               const float* const* peer_grads, unsigned int* const* peer_flags, int world, int rank,
                               unsigned int epoch, int step, float lr, float beta1, float beta2, float eps,
-                              float* reduced_out, float* zero_next, int repack, void* stream);
+                              float* reduced_out, float* zero_next, int repack, const tnerf_scaler* scaler_host, void* stream);
 /* sets *found_inf (device int) to 1 if any grad is non-finite (device-side GradScaler check) */
 int tnerf_check_finite(const float* grads, long long n, int* found_inf, void* stream);
 

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/tnerf.h but not exported"
     assert sorted(built.exported_symbols()) == declared, "ctypes table and header disagree"
-    assert lib.tnerf_abi_version() == 1
+    assert lib.tnerf_abi_version() == built.ABI_VERSION == 2
 
 
 def test_sass_is_blackwell_native(built):

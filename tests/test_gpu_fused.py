@@ -317,7 +317,7 @@ def test_train_fwd_bwd_entry_point_vs_oracle(dev, prec, white):
     comp = torch.empty(n, 3, device=dev)
     rs = engine.ray_source(c2w=pose_d, H=H, W=W, focal=focal, pixel_index=pix_d)
     E.check(E.lib().tnerf_train_fwd_bwd(h.h, C.byref(rs), E.ptr(t_d), n, 2.0, 6.0, S, E.ptr(u_d), int(white), engine._PREC[prec],
-                                        3.0 * n, E.ptr(comp), E.ptr(loss), E.ptr(grads), E.stream(dev)))
+                                        3.0 * n, E.ptr(comp), E.ptr(loss), E.ptr(grads), None, None, E.stream(dev)))
     oro, ord_ = O.get_rays(H, W, focal, pose)
     l_ref, g_ref, (oc, _, _) = O.loss_and_grads(p, oro[pix], ord_[pix], target, 2.0, 6.0, S, u, white_bkgd=white)
     keep = O.last_sample_sigma_pre(p, oro[pix], ord_[pix], 2.0, 6.0, S, u).abs() > (1e-5 if prec == "f32" else 4e-3)
@@ -335,7 +335,7 @@ def test_train_fwd_bwd_entry_point_vs_oracle(dev, prec, white):
 
 def test_train_kernel_variants_agree_on_a_large_batch(dev):
     """The training kernel has two tile programs (rolled / unrolled per step) and two stream schedules (in phase = default; half a
-    tile apart = TNERF_TRAIN_SYNC=0, the run-to-run reproducible mode: the two streams of a CTA then feed the shared weight-gradient
+    tile apart = option train_sync 0, the run-to-run reproducible mode: the two streams of a CTA then feed the shared weight-gradient
     accumulators in a fixed order).  On 16 384 rays x 64 samples: the two programs return the same gradient BITS under the
     reproducible schedule, the in-phase schedule agrees with it to fp32 summation-order noise, and the sum of two half batches
     matches the full batch."""
@@ -355,20 +355,20 @@ def test_train_kernel_variants_agree_on_a_large_batch(dev):
     h.ensure_packed(force=True)
 
     def run(lo, cnt, unroll_from, sync):
-        os.environ["TNERF_TRAIN_UNROLL_FROM"] = str(unroll_from)
-        os.environ["TNERF_TRAIN_SYNC"] = str(sync)
+        h.set_option("unroll_from", unroll_from)
+        h.set_option("train_sync", sync)
         try:
             grads = torch.zeros(h.param_count, device=dev)
             loss = torch.zeros(1, device=dev)
             rs = engine.ray_source(c2w=pose, H=H, W=W, focal=focal, pixel_index=pix[lo:lo + cnt].contiguous())
             E.check(E.lib().tnerf_train_fwd_bwd(h.h, C.byref(rs), E.ptr(target[lo:lo + cnt].contiguous()), cnt, 2.0, 6.0, S,
                                                 E.ptr(u[lo:lo + cnt].contiguous()), 1, E.PREC_F16_TC, 3.0 * n, None, E.ptr(loss), E.ptr(grads),
-                                                E.stream(dev)))
+                                                None, None, E.stream(dev)))
             torch.cuda.synchronize()
             return loss.cpu(), grads.cpu()
         finally:
-            os.environ.pop("TNERF_TRAIN_UNROLL_FROM", None)
-            os.environ.pop("TNERF_TRAIN_SYNC", None)
+            h.set_option("unroll_from", -1)
+            h.set_option("train_sync", -1)
 
     l_u, g_u = run(0, n, 1, 0)               # unrolled tile program, reproducible schedule
     l_r, g_r = run(0, n, 1 << 30, 0)         # rolled
@@ -431,7 +431,7 @@ def test_optimizer_step_refreshes_operand_image_like_a_full_repack(dev):
     for cfg, L in (((63, 128, 4, 2), 10), ((39, 128, 4, 2), 6)):
         enc = PositionalEncoding(L, True).to(dev)
         model, _ = make_model(cfg, 71, dev, 1.5)
-        tr = engine.Trainer(model, enc, n_samples=64)
+        tr = engine.Trainer(model, enc, n_samples=64, grad_scaler=False)      # host-side step count: bit-comparable with tnerf_adam_step
         P = tr.P
         g = torch.Generator().manual_seed(72)
         grads = (torch.randn(P + 1, generator=g) * 1e-2).to(dev)
@@ -442,7 +442,7 @@ def test_optimizer_step_refreshes_operand_image_like_a_full_repack(dev):
         for step in (1, 2, 3):
             E.check(E.lib().tnerf_adam_step(E.ptr(ref_p), E.ptr(grads), E.ptr(ref_m), E.ptr(ref_v), P, step, 5e-4, 0.9, 0.999, 1e-8, 1.0, None,
                                             E.stream(dev)))
-            tr.gbuf.copy_(grads)
+            tr.gbuf[:P + 1].copy_(grads)
             tr.steps = step - 1
             loss = tr._finish()
             assert torch.equal(tr.flat, ref_p) and torch.equal(tr.exp_avg, ref_m) and torch.equal(tr.exp_avg_sq, ref_v)
@@ -452,6 +452,73 @@ def test_optimizer_step_refreshes_operand_image_like_a_full_repack(dev):
             assert E.lib().tnerf_packed_image_copy(tr.h.h, E.ptr(img_b), nbytes, E.stream(dev)) == nbytes
             torch.cuda.synchronize()
             assert torch.equal(img_a, img_b), int((img_a != img_b).sum())
+
+
+# ------------------------------------------------------------------------------------------ GradScaler semantics
+@pytest.mark.parametrize("prec", ["f16", "f32"])
+def test_grad_scaler_skips_an_overflowed_step_and_recovers(dev, prec):
+    """src/train.py:81,126-128 (GradScaler.scale / step / update) on the device: a step with a non-finite target must leave
+    parameters, moments and Adam's step count untouched and halve the loss scale -- with no host synchronisation in between --
+    and training must resume afterwards exactly as if the bad batch had never been seen."""
+    import engine
+    from encoding import PositionalEncoding
+    enc = PositionalEncoding(10, True).to(dev)
+    H, W, focal, n, S = 40, 40, 60.0, 1024, 64
+    pose = O.look_at_pose(0.9, 0.4).to(dev)
+    g = torch.Generator().manual_seed(91)
+    batches = [(torch.randint(0, H * W, (n,), generator=g).to(dev), torch.rand(n, 3, generator=g).to(dev), torch.rand(n, S, generator=g).to(dev))
+               for _ in range(4)]
+
+    def run(with_bad_batch):
+        model, _ = make_model((63, 128, 4, 2), 90, dev, 1.5)
+        tr = engine.Trainer(model, enc, n_samples=S, precision=prec, growth_interval=1000)
+        log = []
+        for k, (pix, tgt, jit) in enumerate(batches):
+            if with_bad_batch and k == 2:
+                bad = tgt.clone(); bad[5, 1] = float("inf")
+                before = (tr.flat.clone(), tr.exp_avg.clone(), tr.exp_avg_sq.clone(), float(tr.loss_scale), tr.applied_steps())
+                loss = tr.step_pixels(pose, H, W, focal, pix, bad, jit)
+                assert not math.isfinite(float(loss))
+                assert torch.equal(tr.flat, before[0]) and torch.equal(tr.exp_avg, before[1]) and torch.equal(tr.exp_avg_sq, before[2])
+                assert float(tr.loss_scale) == 0.5 * before[3] and tr.applied_steps() == before[4]
+                assert float(tr.gbuf[:tr.P + 1].abs().max()) == 0.0          # the poisoned gradient vector was cleared all the same
+            loss = tr.step_pixels(pose, H, W, focal, pix, tgt, jit)
+            log.append(float(loss))
+        assert tr.applied_steps() == len(batches) and all(math.isfinite(x) for x in log)
+        sd = tr.state_dict()
+        assert float(sd["state"][0]["step"]) == float(len(batches))
+        return tr.flat.clone(), log, float(tr.loss_scale)
+
+    p_clean, log_clean, scale_clean = run(False)
+    p_bad, log_bad, scale_bad = run(True)
+    assert scale_bad == 0.5 * scale_clean
+    # same trajectory: the halved scale only moves fp16 roundings of the backward operands (nothing at all on the fp32 path)
+    tol = 0.0 if prec == "f32" else 2e-4
+    assert (p_clean - p_bad).abs().max().item() <= tol + (5e-7 if prec == "f32" else 0.0), (p_clean - p_bad).abs().max().item()
+    assert max(abs(a - b) for a, b in zip(log_clean, log_bad)) < 1e-4
+
+
+def test_grad_scaler_backs_off_from_a_too_large_scale_and_grows_again(dev):
+    """a loss scale that pushes the head gradients out of the fp16-safe range is detected in the kernel (no infinities appear:
+    the operands saturate): steps are skipped and the scale halves until the step fits; growth_interval clean steps double it."""
+    import engine
+    from encoding import PositionalEncoding
+    enc = PositionalEncoding(10, True).to(dev)
+    model, _ = make_model((63, 128, 4, 2), 93, dev, 1.5)
+    H, W, focal, n, S = 40, 40, 60.0, 1024, 64
+    pose = O.look_at_pose(0.2, 0.5).to(dev)
+    g = torch.Generator().manual_seed(94)
+    pix, tgt, jit = torch.randint(0, H * W, (n,), generator=g).to(dev), torch.rand(n, 3, generator=g).to(dev), torch.rand(n, S, generator=g).to(dev)
+    tr = engine.Trainer(model, enc, n_samples=S, init_scale=2.0 ** 36, growth_interval=3)
+    p0 = tr.flat.clone()
+    scales = []
+    for _ in range(40):
+        tr.step_pixels(pose, H, W, focal, pix, tgt, jit)
+        scales.append(float(tr.loss_scale))
+    applied = tr.applied_steps()
+    assert scales[0] == 2.0 ** 35 and 0 < applied < 40                # the first steps were skipped ...
+    assert not torch.equal(tr.flat, p0) and bool(torch.isfinite(tr.flat).all())
+    assert min(scales) < 2.0 ** 30 and any(b > a for a, b in zip(scales, scales[1:]))    # ... and the scale grows back after clean runs
 
 
 # ------------------------------------------------------------------------------------------ deferred fusion

@@ -32,6 +32,14 @@ class RaySource(C.Structure):
                 ("focal", _f), ("pixel_index", _p), ("first_ray", _ll)]
 
 
+class Scaler(C.Structure):
+    """mirror of tnerf_scaler (include/tnerf.h): device-resident GradScaler state consumed by the optimiser entry points"""
+    _fields_ = [("state", _p), ("found_inf", _p), ("clear_next", _p), ("growth_factor", _f), ("backoff_factor", _f),
+                ("growth_interval", _i), ("call", C.c_uint)]
+
+
+ABI_VERSION = 2
+
 _SIGS = {
     "tnerf_abi_version": (_i, []),
     "tnerf_last_error": (C.c_char_p, []),
@@ -46,6 +54,7 @@ _SIGS = {
     "tnerf_bind_params": (_i, [_p, C.POINTER(_p), _i]),
     "tnerf_param_count": (_ll, [_p]),
     "tnerf_set_encoding": (_i, [_p, _i, _i]),
+    "tnerf_set_option": (_i, [_p, C.c_char_p, _i]),
     "tnerf_set_debug_buffer": (_i, [_p, _p]),
     "tnerf_fused_supported": (_i, [_p]),
     "tnerf_pack_weights": (_i, [_p, _p]),
@@ -57,13 +66,13 @@ _SIGS = {
     "tnerf_render_fwd": (_i, [_p, C.POINTER(RaySource), _ll, _f, _f, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
     "tnerf_render_frames": (_i, [_p, _p, _i, _i, _i, _f, _ll, _ll, _f, _f, _i, _i, _i, _p, _p, _p, _p]),
     "tnerf_render_bwd": (_i, [_p, C.POINTER(RaySource), _ll, _f, _f, _i, _p, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p]),
-    "tnerf_train_fwd_bwd": (_i, [_p, C.POINTER(RaySource), _p, _ll, _f, _f, _i, _p, _i, _i, _f, _p, _p, _p, _p]),
+    "tnerf_train_fwd_bwd": (_i, [_p, C.POINTER(RaySource), _p, _ll, _f, _f, _i, _p, _i, _i, _f, _p, _p, _p, _p, _p, _p]),
     "tnerf_mse_psnr": (_i, [_p, _p, _ll, _p, _p]),
     "tnerf_adam_step": (_i, [_p, _p, _p, _p, _ll, _i, _f, _f, _f, _f, _f, _p, _p]),
     "tnerf_check_finite": (_i, [_p, _ll, _p, _p]),
     "tnerf_packed_image_copy": (_ll, [_p, _p, _ll, _p]),
-    "tnerf_optimizer_step": (_i, [_p, _p, _p, _p, _p, _ll, _ll, _i, _f, _f, _f, _f, _p, _i, _p]),
-    "tnerf_allreduce_adam_step": (_i, [_p, _p, _p, _p, _ll, _p, _p, _i, _i, C.c_uint, _i, _f, _f, _f, _f, _p, _p, _i, _p]),
+    "tnerf_optimizer_step": (_i, [_p, _p, _p, _p, _p, _ll, _ll, _i, _f, _f, _f, _f, _p, _i, C.POINTER(Scaler), _p]),
+    "tnerf_allreduce_adam_step": (_i, [_p, _p, _p, _p, _ll, _p, _p, _i, _i, C.c_uint, _i, _f, _f, _f, _f, _p, _p, _i, C.POINTER(Scaler), _p]),
     "tnerf_umma_rate": (_i, [_i, _i, _i, _p, _p]),
     "tnerf_umma_selftest": (_i, [_p, _p, _i, _i, _i, _p, _p]),
 }
@@ -84,7 +93,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.tnerf_abi_version() != 1:
+        if L.tnerf_abi_version() != ABI_VERSION:
             raise RuntimeError("libtnerf.so ABI version mismatch")
         _lib = L
     return _lib
@@ -185,6 +194,10 @@ class ModelHandle:
     def set_encoding(self, num_freqs: int, include_input: bool) -> None:
         check(lib().tnerf_set_encoding(self.h, int(num_freqs), int(bool(include_input))), "tnerf_set_encoding")
         self.fused_ok = bool(lib().tnerf_fused_supported(self.h))
+
+    def set_option(self, name: str, value: int) -> None:
+        """schedule options of the fused training kernel (include/tnerf.h, tnerf_set_option); -1 = built-in choice"""
+        check(lib().tnerf_set_option(self.h, name.encode(), int(value)), "tnerf_set_option")
 
     def ensure_packed(self, force: bool = False) -> None:
         ps = self.bind()

@@ -5,12 +5,13 @@
 
 #include <cstdio>
 #include <cstring>
+#include <cstdint>
 #include <cstdlib>
 
 namespace tnerf {
 
 std::atomic<long long> g_launches{0};
-int pdl_mask() { const char* e = getenv("TNERF_PDL"); return e ? atoi(e) : 7; }
+int pdl_mask() { static const int mask = [] { const char* e = getenv("TNERF_PDL"); return e ? atoi(e) : 7; }(); return mask; }   // read once per process
 static thread_local std::string t_error;
 void set_error(const std::string& msg) { t_error = msg; }
 int count_launch() {
@@ -217,6 +218,10 @@ int tnerf_create(tnerf_handle** out, int device, int in_dim, int hidden, int dep
     h->num_freqs = (in_dim >= 3 && (in_dim - 3) % 6 == 0) ? (in_dim - 3) / 6 : (in_dim % 6 == 0 ? in_dim / 6 : -1);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     h->fused_ok = fused_shape_supported(h);
+    // developer knobs are environment DEFAULTS read once here (a getenv per launch is host time on a 160 us step); tnerf_set_option changes them
+    if (const char* e = getenv("TNERF_TRAIN_SYNC")) h->opt_train_sync = atoi(e);
+    if (const char* e = getenv("TNERF_BULK_REDUCE")) h->opt_bulk_reduce = atoi(e);
+    if (const char* e = getenv("TNERF_TRAIN_UNROLL_FROM")) h->opt_unroll_from = atoi(e);
     *out = h;
     return 0;
 }
@@ -233,6 +238,15 @@ int tnerf_set_encoding(tnerf_handle* h, int num_freqs, int include_input) {
     if (!h || num_freqs < 0 || h->in_dim != 6 * num_freqs + (include_input ? 3 : 0)) return bad("tnerf_set_encoding: in_dim mismatch");
     h->num_freqs = num_freqs;
     h->fused_ok = fused_shape_supported(h);
+    return 0;
+}
+int tnerf_set_option(tnerf_handle* h, const char* name, int value) {
+    if (!h || !name) return bad("tnerf_set_option: NULL argument");
+    const std::string n(name);
+    if (n == "train_sync") h->opt_train_sync = value;
+    else if (n == "bulk_reduce") h->opt_bulk_reduce = value;
+    else if (n == "unroll_from") h->opt_unroll_from = value;
+    else return bad("tnerf_set_option: unknown option");
     return 0;
 }
 int tnerf_set_debug_buffer(tnerf_handle* h, void* buf) {
@@ -356,7 +370,7 @@ int tnerf_render_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long lo
     const RaySource rs = to_device_source(rays_host);
     if (precision == TNERF_PREC_F16_TC)
         return fused_train(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, nullptr, 1.f, g_comp, g_depth, g_acc, g_weights,
-                           grad_scale, grad_scale_dev, nullptr, nullptr, grads, (cudaStream_t)stream);
+                           grad_scale, grad_scale_dev, nullptr, nullptr, nullptr, grads, (cudaStream_t)stream);
     F32Job job{};
     job.mode = 1; job.gC = g_comp; job.gD = g_depth; job.gA = g_acc; job.gW = g_weights; job.grads = grads;
     return run_f32(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, job, (cudaStream_t)stream);
@@ -364,7 +378,7 @@ int tnerf_render_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long lo
 
 int tnerf_train_fwd_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, const float* target, long long n_rays, float near_,
                         float far_, int n_samples, const float* jitter, int white_bkgd, int precision, float loss_denom,
-                        float* comp_rgb, float* loss_sum, float* grads, void* stream) {
+                        float* comp_rgb, float* loss_sum, float* grads, const float* loss_scale_dev, float* found_inf, void* stream) {
     TN_ON_DEVICE(h);
     if (n_rays == 0) return 0;
     if (!h || h->params.empty() || !target || !grads || !loss_sum || n_rays < 0 || n_samples < 1 || !(loss_denom > 0.f))
@@ -373,10 +387,16 @@ int tnerf_train_fwd_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, cons
     const RaySource rs = to_device_source(rays_host);
     if (precision == TNERF_PREC_F16_TC)
         return fused_train(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, target, loss_denom, nullptr, nullptr, nullptr,
-                           nullptr, 0.f, nullptr, comp_rgb, loss_sum, grads, (cudaStream_t)stream);
+                           nullptr, 0.f, loss_scale_dev, found_inf, comp_rgb, loss_sum, grads, (cudaStream_t)stream);
+    // fp32 path: no loss scale is needed; the overflow flag is the plain non-finite test of the gradient vector and the loss
     F32Job job{};
     job.mode = 2; job.target = target; job.loss_denom = loss_denom; job.comp = comp_rgb; job.loss_sum = loss_sum; job.grads = grads;
-    return run_f32(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, job, (cudaStream_t)stream);
+    if (int e = run_f32(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, job, (cudaStream_t)stream)) return e;
+    if (found_inf) {
+        if (int e = launch_found_inf(grads, h->param_count, found_inf, (cudaStream_t)stream)) return e;
+        return launch_found_inf(loss_sum, 1, found_inf, (cudaStream_t)stream);
+    }
+    return 0;
 }
 
 int tnerf_mse_psnr(const float* pred, const float* target, long long n, float* out2, void* stream) {
@@ -408,8 +428,19 @@ static bool params_are_flat(const tnerf_handle* h, const float* flat) {
         if (h->params[t] != flat + h->offsets[t]) return false;
     return true;
 }
+static int to_scaler_args(const tnerf_scaler* sc, ScalerArgs& out) {
+    out = ScalerArgs{};
+    if (!sc) return 0;
+    if (!sc->state || (reinterpret_cast<uintptr_t>(sc->state) & 7) || !(sc->growth_factor >= 1.f) || !(sc->backoff_factor > 0.f && sc->backoff_factor <= 1.f) ||
+        sc->growth_interval < 1)
+        return bad("tnerf_scaler: need an 8-byte aligned state of 16 floats, growth >= 1, 0 < backoff <= 1, interval >= 1");
+    out.state = sc->state; out.found = sc->found_inf; out.clear = sc->clear_next; out.growth = sc->growth_factor; out.backoff = sc->backoff_factor;
+    out.interval = sc->growth_interval; out.call = sc->call;
+    return 0;
+}
 int tnerf_optimizer_step(tnerf_handle* h, float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n,
-                         long long n_clear, int step, float lr, float beta1, float beta2, float eps, float* tail_out, int repack, void* stream) {
+                         long long n_clear, int step, float lr, float beta1, float beta2, float eps, float* tail_out, int repack,
+                         const tnerf_scaler* scaler_host, void* stream) {
     DeviceGuard device_guard_(h ? h->device : device_of(params));
     if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || n_clear < n || step < 1) return bad("tnerf_optimizer_step: invalid argument");
     RepackMap mp{};
@@ -417,23 +448,35 @@ int tnerf_optimizer_step(tnerf_handle* h, float* params, float* grads, float* ex
         if (!params_are_flat(h, params) || n != h->param_count) return bad("tnerf_optimizer_step: repack needs the handle's parameters bound as one flat vector");
         if (!build_repack_map(h, mp)) return bad("tnerf_optimizer_step: no packed image to refresh (call tnerf_pack_weights once first)");
     }
-    return launch_adam_fused(params, grads, exp_avg, exp_avg_sq, n, n_clear, step, lr, beta1, beta2, eps, tail_out, mp, (cudaStream_t)stream);
+    ScalerArgs sc;
+    if (int e = to_scaler_args(scaler_host, sc)) return e;
+    return launch_adam_fused(params, grads, exp_avg, exp_avg_sq, n, n_clear, step, lr, beta1, beta2, eps, tail_out, mp, sc, (cudaStream_t)stream);
 }
 int tnerf_allreduce_adam_step(tnerf_handle* h, float* params, float* exp_avg, float* exp_avg_sq, long long n, const float* const* peer_grads,
                               unsigned int* const* peer_flags, int world, int rank, unsigned int epoch, int step, float lr,
-                              float beta1, float beta2, float eps, float* reduced_out, float* zero_next, int repack, void* stream) {
+                              float beta1, float beta2, float eps, float* reduced_out, float* zero_next, int repack,
+                              const tnerf_scaler* scaler_host, void* stream) {
     DeviceGuard device_guard_(h ? h->device : device_of(params));
     if (!params || !exp_avg || !exp_avg_sq || !peer_grads || !peer_flags || n < 0 || step < 1) return bad("tnerf_allreduce_adam_step: invalid argument");
     if (world < 1 || world > 8 || rank < 0 || rank >= world || epoch == 0) return bad("tnerf_allreduce_adam_step: need 1 <= world <= 8, 0 <= rank < world, epoch >= 1");
     for (int r = 0; r < world; ++r)
-        if (!peer_grads[r] || !peer_flags[r]) return bad("tnerf_allreduce_adam_step: NULL peer pointer");
+        if (!peer_grads[r] || !peer_flags[r] || (reinterpret_cast<uintptr_t>(peer_grads[r]) & 15)) return bad("tnerf_allreduce_adam_step: NULL or unaligned (16 B) peer pointer");
     RepackMap mp{};
     if (repack) {
         if (!params_are_flat(h, params) || n != h->param_count) return bad("tnerf_allreduce_adam_step: repack needs the handle's parameters bound as one flat vector");
         if (!build_repack_map(h, mp)) return bad("tnerf_allreduce_adam_step: no packed image to refresh (call tnerf_pack_weights once first)");
     }
+    ScalerArgs sc;
+    if (int e = to_scaler_args(scaler_host, sc)) return e;
+    // a peer that has not published its vector after this long is reported by a trap instead of a hung device: TNERF_PEER_TIMEOUT_S
+    // seconds (default 60; 0 = wait forever) -- rank-local work between steps (checkpoints, previews) must stay below it
+    static const long long timeout_cycles = [] {
+        const char* e = getenv("TNERF_PEER_TIMEOUT_S");
+        const double sec = e ? atof(e) : 60.0;
+        return sec > 0.0 ? (long long)(sec * 2.0e9) : 0LL;
+    }();
     return launch_allreduce_adam(params, exp_avg, exp_avg_sq, n, peer_grads, peer_flags, world, rank, epoch, step, lr, beta1, beta2, eps,
-                                 reduced_out, zero_next, mp, (cudaStream_t)stream);
+                                 reduced_out, zero_next, mp, sc, timeout_cycles, (cudaStream_t)stream);
 }
 int tnerf_check_finite(const float* grads, long long n, int* found_inf, void* stream) {
     TN_ON_DEVICE_OF(grads);

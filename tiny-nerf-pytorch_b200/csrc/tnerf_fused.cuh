@@ -173,11 +173,22 @@ __device__ __forceinline__ void repack_param(const RepackMap& mp, long long i, f
     if (bias && mp.bias_hilo[l]) img[img_idx(n, kk + 1, N)] = __float2half_rn(val - __half2float(hi));
 }
 bool build_repack_map(const tnerf_handle* h, RepackMap& mp);
+// GradScaler semantics of the optimiser kernels (src/train.py:81,126-128), all on the device.  state (16 floats, 64-byte aligned):
+// [0] loss scale, [1] clean steps since the scale last changed, [2] optimiser steps applied, [8..15] as four doubles: beta1^t and
+// beta2^t, one pair per call parity (a kernel reads pair call&1 and writes the other, so blocks never race with the updater).
+struct ScalerArgs {
+    float* state;              // NULL: no scaler -- the step is always applied, bias corrections come from the host's step count
+    const float* found;        // this call's overflow flag (non-zero: skip the step); the exchange kernel reads it from the vectors
+    float* clear;              // flag to clear for the NEXT call (the other parity slot)
+    float growth, backoff;
+    int interval;
+    unsigned int call;
+};
 int launch_adam_fused(float* p, float* g, float* m, float* v, long long n, long long n_clear, int step, float lr, float b1, float b2,
-                      float eps, float* tail_out, const RepackMap& mp, cudaStream_t s);
+                      float eps, float* tail_out, const RepackMap& mp, const ScalerArgs& sc, cudaStream_t s);
 int launch_allreduce_adam(float* p, float* m, float* v, long long n, const float* const* peer_grads, unsigned int* const* peer_flags,
                           int world, int rank, unsigned int epoch, int step, float lr, float b1, float b2, float eps, float* reduced_out,
-                          float* zero_next, const RepackMap& mp, cudaStream_t s);
+                          float* zero_next, const RepackMap& mp, const ScalerArgs& sc, long long timeout_cycles, cudaStream_t s);
 
 bool build_plan(const tnerf_handle* h, FusedPlan& pl);
 int fused_render_fwd_fast(const FwdParams& p, int grid, cudaStream_t s);   // tnerf_fused_fast.cu (n_samples % 32 == 0)

@@ -52,6 +52,10 @@ struct tnerf_handle {
     bool fused_ok = false;
     int num_freqs = 0;                    // (in_dim-3)/6 when in_dim = 3+6L
     void* debug = nullptr;                // optional device buffer (1024 int64) for kernel phase stamps
+    // training-kernel schedule (tnerf_set_option; defaults from TNERF_TRAIN_SYNC / TNERF_BULK_REDUCE / TNERF_TRAIN_UNROLL_FROM, read
+    // ONCE when the handle is created): -1 = built-in choice
+    int opt_train_sync = -1, opt_bulk_reduce = -1, opt_unroll_from = -1;
+    float* auto_scale = nullptr;          // device float: loss scale chosen from the upstream gradients (tnerf_render_bwd, automatic mode)
 };
 
 namespace tnerf {
@@ -84,7 +88,8 @@ int fused_render_fwd(tnerf_handle* h, const RaySource& rs, long long n, float nr
                      float* comp, float* depth, float* acc, float* weights, float* rays_d_out, cudaStream_t s);
 int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, float fr, int S, const float* jitter, int white,
                 const float* target, float loss_denom, const float* gC, const float* gD, const float* gA, const float* gW,
-                float grad_scale, const float* grad_scale_dev, float* comp, float* loss_sum, float* grads, cudaStream_t s);
+                float grad_scale, const float* grad_scale_dev, float* found, float* comp, float* loss_sum, float* grads, cudaStream_t s);
+int launch_found_inf(const float* g, long long n, float* found, cudaStream_t s);
 // wide MLP (hidden = 256) on CTA pairs (tnerf_fused_wide.cu)
 bool wide_shape_supported(const tnerf_handle* h);
 int wide_pack_weights(tnerf_handle* h, cudaStream_t s);

@@ -433,17 +433,48 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
     p[i] = p[i] - lr_over_bc1 * (mi / denom);
 }
+// GradScaler bookkeeping shared by the two optimiser kernels: thread 0 of every block derives this call's decision and step sizes
+// from the device-resident state; thread 0 of block 0 also writes the state the NEXT call will read (other parity slot).
+// out[0] = skip (non-zero), out[1] = lr / (1 - beta1^t), out[2] = 1 / sqrt(1 - beta2^t).
+__device__ __forceinline__ void scaler_decide(const ScalerArgs& sc, bool skip, bool writer, float lr, float b1, float b2, float* out) {
+    double* pw = reinterpret_cast<double*>(sc.state + 8);
+    const int cur = (int)(sc.call & 1u), nxt = cur ^ 1;
+    double b1p = pw[2 * cur], b2p = pw[2 * cur + 1];
+    if (!skip) { b1p *= (double)b1; b2p *= (double)b2; }
+    out[0] = skip ? 1.f : 0.f;
+    out[1] = (float)((double)lr / (1.0 - b1p));
+    out[2] = (float)(1.0 / sqrt(1.0 - b2p));
+    if (writer) {
+        pw[2 * nxt] = b1p; pw[2 * nxt + 1] = b2p;
+        float scale = sc.state[0], clean = sc.state[1];
+        if (skip) { scale *= sc.backoff; clean = 0.f; }                       // torch.amp.GradScaler.update(): back off, restart the count
+        else if (++clean >= (float)sc.interval) { scale *= sc.growth; clean = 0.f; }
+        sc.state[0] = scale; sc.state[1] = clean;
+        if (!skip) sc.state[2] += 1.f;
+        if (sc.clear) *sc.clear = 0.f;
+    }
+}
+
 // a9 + N1: Adam on the flat parameter vector, the gradient vector cleared for the next step and the fp16 operand image of
-// the tensor-core kernels refreshed in place -- one launch instead of memset + Adam + re-pack.
+// the tensor-core kernels refreshed in place -- one launch instead of memset + Adam + re-pack.  With a scaler the launch also
+// carries GradScaler.step()/update(): an overflowed step leaves parameters and moments untouched and halves the loss scale.
 __global__ void adam_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                                  long long n, long long n_clear, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps,
-                                  float* __restrict__ tail_out, const __grid_constant__ RepackMap mp) {
+                                  long long n, long long n_clear, float lr_over_bc1, float inv_sqrt_bc2, float lr, float b1, float b2, float eps,
+                                  float* __restrict__ tail_out, const __grid_constant__ RepackMap mp, const ScalerArgs sc) {
+    __shared__ float dec[3];
     asm volatile("griddepcontrol.wait;" ::: "memory");       // programmatic stream serialisation: set up under the previous kernel's tail
+    if (sc.state) {
+        if (threadIdx.x == 0) scaler_decide(sc, sc.found && !(*sc.found == 0.f), blockIdx.x == 0, lr, b1, b2, dec);
+        __syncthreads();
+        lr_over_bc1 = dec[1]; inv_sqrt_bc2 = dec[2];
+    }
+    const bool skip = sc.state && dec[0] != 0.f;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n_clear) return;
     const float gi = g[i];
     g[i] = 0.f;
     if (i >= n) { if (tail_out) tail_out[i - n] = gi; return; }      // e.g. the loss slot behind the gradient
+    if (skip) return;
     const float mi = fmaf(1.f - b1, gi - m[i], m[i]);
     const float vi = fmaf(v[i], b2, (1.f - b2) * gi * gi);
     m[i] = mi; v[i] = vi;
@@ -453,12 +484,12 @@ __global__ void adam_fused_kernel(float* __restrict__ p, float* __restrict__ g, 
     if (mp.valid) repack_param(mp, i, pn);
 }
 
-// (e) ray-sharded data parallel: one-shot all-reduce of the flat [gradient | loss] vectors over NVLink peer memory, fused with
-// the Adam step (replaces ncclAllReduce + adam_kernel).  Every rank runs this kernel on its own GPU.
+// (e) ray-sharded data parallel: one-shot all-reduce of the flat [gradient | loss (| overflow flag)] vectors over NVLink peer memory,
+// fused with the Adam step (replaces ncclAllReduce + adam_kernel).  Every rank runs this kernel on its own GPU.
 //   1. block 0 publishes "my vector for epoch e is complete" into every peer's flag array (release, system scope);
 //   2. every block waits until all ranks have published epoch e (acquire, system scope), bounded spin;
-//   3. thread i sums element i over the ranks IN RANK ORDER (bit-identical result on every rank, so the replicas never
-//      drift), applies Adam to parameter i; element n is the loss.
+//   3. a thread sums FOUR consecutive elements over the ranks IN RANK ORDER with 16-byte peer loads (bit-identical result on every
+//      rank, so the replicas never drift) and applies Adam to them; element n is the loss, element n+1 (scaler) the overflow flag.
 // The vectors are double-buffered by the caller (epoch parity): a rank can be at most one step ahead of its peers.
 struct PeerSet { const float* grads[8]; unsigned int* flags[8]; };
 
@@ -470,12 +501,19 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ float4 ld_cv4(const float* p) {      // 16-byte load that always goes to the owner's memory (no stale L1/L2 line)
+    float4 v;
+    asm volatile("ld.global.cv.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
 
 __global__ void allreduce_adam_kernel(PeerSet ps, int world, int rank, unsigned int epoch, float* __restrict__ p,
                                       float* __restrict__ m, float* __restrict__ v, long long n, float lr_over_bc1,
-                                      float inv_sqrt_bc2, float b1, float b2, float eps, float* __restrict__ reduced_out,
-                                      float* __restrict__ zero_next, const __grid_constant__ RepackMap mp) {
+                                      float inv_sqrt_bc2, float lr, float b1, float b2, float eps, float* __restrict__ reduced_out,
+                                      float* __restrict__ zero_next, const __grid_constant__ RepackMap mp, const ScalerArgs sc,
+                                      long long timeout_cycles) {
     __shared__ int timed_out;
+    __shared__ float dec[3];
     if (threadIdx.x == 0) timed_out = 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");       // programmatic stream serialisation: this rank's gradient (previous kernel) is complete
     if (blockIdx.x == 0 && threadIdx.x < world) {
@@ -485,28 +523,51 @@ __global__ void allreduce_adam_kernel(PeerSet ps, int world, int rank, unsigned 
     if (threadIdx.x < world) {
         const unsigned int* mine = ps.flags[rank] + threadIdx.x;
         const long long t0 = clock64();
+        unsigned int spins = 0;
         while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
-            if (clock64() - t0 > 6000000000LL) { timed_out = 1; break; }   // a peer never arrived (~3 s): fail loudly, do not hang
-            __nanosleep(64);
+            // a peer that never arrives: fail loudly instead of hanging the device (timeout_cycles <= 0: wait forever)
+            if (timeout_cycles > 0 && clock64() - t0 > timeout_cycles) { timed_out = 1; break; }
+            if (++spins > 64) __nanosleep(32);               // spin tightly through the usual few-microsecond skew, back off after that
         }
     }
     __syncthreads();
     if (timed_out) { __trap(); }
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i > n) return;
-    float g = 0.f;
-    for (int r = 0; r < world; ++r) g += __ldcv(ps.grads[r] + i);
-    if (reduced_out) reduced_out[i] = g;
-    // every rank is past the barrier, so nobody still reads this rank's OTHER-parity vector: clear it for the next step
-    if (zero_next) zero_next[i] = 0.f;
-    if (i == n) return;                                             // the loss element
-    const float mi = fmaf(1.f - b1, g - m[i], m[i]);
-    const float vi = fmaf(v[i], b2, (1.f - b2) * g * g);
-    m[i] = mi; v[i] = vi;
-    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-    const float pn = p[i] - lr_over_bc1 * (mi / denom);
-    p[i] = pn;
-    if (mp.valid) repack_param(mp, i, pn);
+    const long long total = n + (sc.state ? 2 : 1);          // [gradient | loss | overflow flag]
+    if (sc.state) {
+        if (threadIdx.x == 0) {
+            float f = 0.f;
+            for (int r = 0; r < world; ++r) f += __ldcv(ps.grads[r] + n + 1);
+            scaler_decide(sc, !(f == 0.f), blockIdx.x == 0, lr, b1, b2, dec);
+        }
+        __syncthreads();
+        lr_over_bc1 = dec[1]; inv_sqrt_bc2 = dec[2];
+    }
+    const bool skip = sc.state && dec[0] != 0.f;
+    const long long i0 = 4 * (blockIdx.x * (long long)blockDim.x + threadIdx.x);
+    if (i0 >= total) return;
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    if (i0 + 4 <= total) {                                   // the vectors are 16-byte aligned and padded by the caller
+        for (int r = 0; r < world; ++r) { const float4 x = ld_cv4(ps.grads[r] + i0); g[0] += x.x; g[1] += x.y; g[2] += x.z; g[3] += x.w; }
+    } else {
+        for (int r = 0; r < world; ++r)
+            for (int k = 0; k < 4; ++k) if (i0 + k < total) g[k] += __ldcv(ps.grads[r] + i0 + k);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long long i = i0 + k;
+        if (i >= total) break;
+        if (reduced_out) reduced_out[i] = g[k];
+        // every rank is past the barrier, so nobody still reads this rank's OTHER-parity vector: clear it for the next step
+        if (zero_next) zero_next[i] = 0.f;
+        if (i >= n || skip) continue;                        // the loss / flag elements; an overflowed step
+        const float mi = fmaf(1.f - b1, g[k] - m[i], m[i]);
+        const float vi = fmaf(v[i], b2, (1.f - b2) * g[k] * g[k]);
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+        const float pn = p[i] - lr_over_bc1 * (mi / denom);
+        p[i] = pn;
+        if (mp.valid) repack_param(mp, i, pn);
+    }
 }
 
 __global__ void check_finite_kernel(const float* __restrict__ g, long long n, int* __restrict__ flag) {
@@ -623,7 +684,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, int s
     return count_launch();
 }
 int launch_adam_fused(float* p, float* g, float* m, float* v, long long n, long long n_clear, int step, float lr, float b1, float b2,
-                      float eps, float* tail_out, const RepackMap& mp, cudaStream_t s) {
+                      float eps, float* tail_out, const RepackMap& mp, const ScalerArgs& sc, cudaStream_t s) {
     if (n_clear <= 0) return 0;
     const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
     cudaLaunchConfig_t cfg{};
@@ -631,23 +692,24 @@ int launch_adam_fused(float* p, float* g, float* m, float* v, long long n, long 
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 4) ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, adam_fused_kernel, p, g, m, v, n, n_clear, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), b1, b2, eps, tail_out, mp);
+    cudaLaunchKernelEx(&cfg, adam_fused_kernel, p, g, m, v, n, n_clear, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), lr, b1, b2, eps, tail_out, mp, sc);
     return count_launch();
 }
 int launch_allreduce_adam(float* p, float* m, float* v, long long n, const float* const* peer_grads, unsigned int* const* peer_flags,
                           int world, int rank, unsigned int epoch, int step, float lr, float b1, float b2, float eps, float* reduced_out,
-                          float* zero_next, const RepackMap& mp, cudaStream_t s) {
+                          float* zero_next, const RepackMap& mp, const ScalerArgs& sc, long long timeout_cycles, cudaStream_t s) {
     if (n <= 0) return 0;
     PeerSet ps{};
     for (int r = 0; r < world; ++r) { ps.grads[r] = peer_grads[r]; ps.flags[r] = peer_flags[r]; }
     const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+    const long long total = n + (sc.state ? 2 : 1);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)blocks_for(n + 1, 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cfg.gridDim = dim3((unsigned)blocks_for((total + 3) / 4, 128)); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 4) ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, allreduce_adam_kernel, ps, world, rank, epoch, p, m, v, n, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), b1, b2,
-                       eps, reduced_out, zero_next, mp);
+    cudaLaunchKernelEx(&cfg, allreduce_adam_kernel, ps, world, rank, epoch, p, m, v, n, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), lr, b1, b2,
+                       eps, reduced_out, zero_next, mp, sc, timeout_cycles);
     return count_launch();
 }
 int launch_check_finite(const float* g, long long n, int* flag, cudaStream_t s) {

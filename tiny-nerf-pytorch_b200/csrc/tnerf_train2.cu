@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         const float gscale = p.scale_dev ? *p.scale_dev : p.scale;
         const float bs = p.b_sigma[0], br = p.b_rgb[0], bg = p.b_rgb[1], bb = p.b_rgb[2];
         float hb[4] = {0.f, 0.f, 0.f, 0.f}, loss_acc = 0.f;
+        bool overflow = false;          // a scaled head gradient left the fp16-safe range (or is not finite): GradScaler's found_inf
         const long long j0 = 2LL * blockIdx.x + s;
         const int S = p.S, W = S < 32 ? S : 32, sl = lane & (W - 1);
         const bool camera = p.rs.rays_d == nullptr;
@@ -489,6 +490,9 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                 if (lane == 0) mbar_arrive(bar_dzh);
                 T2_STAMP();
                 hb[0] += s0; hb[1] += s1; hb[2] += s2; hb[3] += s3;      // head bias gradients: per-thread partials, reduced at the end
+                // the hidden layers amplify |dZ| by a few units per layer at most: 2^10 at the heads keeps every fp16 operand of the
+                // backward chain far from 65504 (cvt.satfinite would clip silently); NaN fails the comparison too
+                overflow |= !(fmaxf(fmaxf(fabsf(s0), fabsf(s1)), fmaxf(fabsf(s2), fabsf(s3))) <= 1024.f);
             };
             if (S == 64) composite(std::integral_constant<int, 64>{});
             else if (S == 128) composite(std::integral_constant<int, 128>{});
@@ -519,6 +523,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             }
             if (p.loss_sum && loss_acc != 0.f) atomicAdd(p.loss_sum, loss_acc);
         }
+        if (p.found && __any_sync(0xffffffffu, overflow) && lane == 0) *p.found = 1.f;
         __syncthreads();                                          // (B)
     } else {
         // ------------------------------ drain threads of stream s (thread <-> feature row) ------------------------------
@@ -800,12 +805,11 @@ int fused_train2(tnerf_handle* h, const FusedPlan& fp, const TrainParams& p, int
     //   * half a tile apart + ROLLED: the previous default (the foreign dW1 half is drained in the middle of the own tile, each drain
     //     body exists once because the streams execute different steps at the same time); kept as the comparison arm
     //     (TNERF_TRAIN_SYNC=0).
-    // TNERF_TRAIN_UNROLL_FROM = tiles per stream from which the unrolled program runs (tuning / tests).
+    // Option unroll_from = tiles per stream from which the unrolled program runs (tuning / tests).
     TrainParams q = p;
-    const char* uf = getenv("TNERF_TRAIN_UNROLL_FROM");
     const long long per_stream = q.n_tiles / (2ll * grid);
     if (q.sync_streams < 0) q.sync_streams = 1;
-    const bool unroll = uf ? per_stream >= atoi(uf) : (q.sync_streams || q.S == 128);
+    const bool unroll = h->opt_unroll_from >= 0 ? per_stream >= h->opt_unroll_from : (q.sync_streams || q.S == 128);
     auto kern = unroll ? (Kx == 64 ? t2::fused_train2_kernel<64, true> : Kx == 48 ? t2::fused_train2_kernel<48, true>
                           : Kx == 32 ? t2::fused_train2_kernel<32, true> : t2::fused_train2_kernel<16, true>)
                        : (Kx == 64 ? t2::fused_train2_kernel<64, false> : Kx == 48 ? t2::fused_train2_kernel<48, false>

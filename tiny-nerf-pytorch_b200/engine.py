@@ -71,13 +71,9 @@ class _FusedRender(torch.autograd.Function):
         grads = torch.zeros(h.param_count, dtype=torch.float32, device=dev)
         rs = ray_source(ro, o_stride, rd)
         gC, gD, gA = (E.f32c(g) if g is not None else None for g in (gC, gD, gA))
-        scale_dev = None
-        if prec == E.PREC_F16_TC:
-            # power-of-two loss scale chosen on the device (no host sync): largest upstream gradient -> ~64
-            amax = torch.stack([g.abs().max() for g in (gC, gD, gA) if g is not None]).max().clamp_min(1e-30)
-            scale_dev = torch.exp2(torch.floor(torch.log2(64.0 / amax))).clamp(2.0 ** -24, 2.0 ** 40).reshape(1).float()
+        # grad_scale = 0: the tensor-core path picks its power-of-two loss scale on the device from the largest upstream gradient
         E.check(E.lib().tnerf_render_bwd(h.h, C.byref(rs), n, near, far, S, E.ptr(jitter), int(white), prec, E.ptr(gC), E.ptr(gD),
-                                         E.ptr(gA), None, 0.0, E.ptr(scale_dev), E.ptr(grads), E.stream(dev)), "tnerf_render_bwd")
+                                         E.ptr(gA), None, 0.0, None, E.ptr(grads), E.stream(dev)), "tnerf_render_bwd")
         views = E.flat_grad_views(module, grads)
         return (None,) * 12 + tuple(v if p.requires_grad else None for v, p in zip(views, ps))
 
@@ -171,17 +167,23 @@ def render_weights(model, ro, o_stride, rd, n, S, near, far, jitter, white, prec
 
 
 class Trainer:
-    """The training-step host path (src/train.py:106-128) on the fused kernels: one
-    tnerf_train_fwd_bwd launch (rays generated in-kernel from pose + pixel ids, MSE inside), an
-    optional NCCL all-reduce of the flat gradient (+loss) for ray-sharded data parallel, one fused Adam
-    launch and one weight re-pack launch.  No host synchronisation anywhere in ``step``.
+    """The training-step host path (src/train.py:106-128) on the fused kernels: one tnerf_train_fwd_bwd call (rays generated
+    in-kernel from pose + pixel ids, MSE inside; training kernel + gradient scatter) and ONE optimiser launch (Adam + clearing
+    of the gradient vector + in-place refresh of the fp16 operand image; with several ranks the same launch first all-reduces
+    the gradient over NVLink peer memory).  No host synchronisation anywhere in ``step``.
 
-    Parameters stay ordinary ``nn.Parameter``s: they are re-pointed at views of one flat fp32 buffer so
-    the optimiser is a single kernel; ``state_dict()`` / ``load_state_dict()`` speak torch.optim.Adam's
-    format, so checkpoints interchange with the reference (src/train.py:85-92,142-156)."""
+    ``grad_scaler`` (default on) carries torch.amp.GradScaler's semantics (src/train.py:81,126-128) as device-resident state:
+    a step whose scaled gradients overflow (or whose loss is not finite) is skipped -- parameters, moments and Adam's step
+    count untouched -- and the loss scale is halved; after ``growth_interval`` clean steps it is doubled.
+
+    Parameters stay ordinary ``nn.Parameter``s: they are re-pointed at views of one flat fp32 buffer so the optimiser is a
+    single kernel; ``state_dict()`` / ``load_state_dict()`` speak torch.optim.Adam's format, so checkpoints interchange with
+    the reference (src/train.py:85-92,142-156)."""
 
     def __init__(self, model, encoder, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, near=2.0, far=6.0, n_samples=64,
-                 white_bkgd=True, precision: Optional[str] = None, process_group=None, comm: Optional[str] = None):
+                 white_bkgd=True, precision: Optional[str] = None, process_group=None, comm: Optional[str] = None,
+                 grad_scaler: bool = True, init_scale: Optional[float] = None, growth_factor: float = 2.0, backoff_factor: float = 0.5,
+                 growth_interval: int = 2000):
         self.model, self.encoder = model, encoder
         ps = model._params()
         dev = E.need_cuda(*ps)
@@ -196,8 +198,9 @@ class Trainer:
             self.flat[off:off + n].copy_(p.detach().reshape(-1))
             p.data = self.flat[off:off + n].view_as(p)
             off += n
-        self.gbuf = torch.zeros(self.P + 1, dtype=torch.float32, device=dev)   # [gradient | loss]
-        self.loss_view = self.gbuf[self.P:]
+        # [gradient | loss | overflow flag (even calls) | overflow flag (odd calls)]: one buffer = one all-reduce
+        self.gbuf = torch.zeros(self.P + 3, dtype=torch.float32, device=dev)
+        self.loss_view = self.gbuf[self.P:self.P + 1]
         self.loss_out = torch.zeros(1, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(self.P, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(self.P, dtype=torch.float32, device=dev)
@@ -208,12 +211,20 @@ class Trainer:
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
-        self.steps = 0
+        self.steps = 0               # optimiser CALLS (skipped ones included); the applied count lives on the device with the scaler
+        # GradScaler state (include/tnerf.h, tnerf_scaler): [scale, clean steps, applied steps, ..., 4 doubles of beta powers]
+        self.scaler_state = torch.zeros(16, dtype=torch.float32, device=dev) if grad_scaler else None
+        self._scale_init = init_scale
+        self._scaler_cfg = (float(growth_factor), float(backoff_factor), int(growth_interval))
+        if grad_scaler:
+            self._reset_beta_powers(0)
+            if init_scale is not None:
+                self.scaler_state[0] = float(init_scale)
         self.h.bind()
         if self.prec == E.PREC_F16_TC:
             self.h.ensure_packed(force=True)
         # gradient exchange of ray-sharded data parallel: "p2p" = one kernel that all-reduces over NVLink peer memory and
-        # applies Adam (tnerf_allreduce_adam_step); "nccl" = torch.distributed.all_reduce + tnerf_adam_step
+        # applies Adam (tnerf_allreduce_adam_step); "nccl" = torch.distributed.all_reduce + tnerf_optimizer_step
         self.comm = "none"
         if self.world > 1:
             want = comm or os.environ.get("TNERF_COMM", "p2p")
@@ -227,13 +238,38 @@ class Trainer:
                         raise
                     print(f"[tnerf] peer-memory gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL", flush=True)
 
+    # ---- GradScaler state ------------------------------------------------------------------------
+    def _reset_beta_powers(self, steps_done: int):
+        pw = self.scaler_state[8:16].view(torch.float64)
+        b1p, b2p = self.betas[0] ** steps_done, self.betas[1] ** steps_done
+        pw.copy_(torch.tensor([b1p, b2p, b1p, b2p], dtype=torch.float64))
+        self.scaler_state[2] = float(steps_done)
+
+    @property
+    def loss_scale(self) -> Optional[torch.Tensor]:
+        """device tensor (1,) holding the current loss scale (None without the scaler)"""
+        return None if self.scaler_state is None else self.scaler_state[0:1]
+
+    def applied_steps(self) -> int:
+        """optimiser steps actually applied (skipped steps do not count); synchronises"""
+        return self.steps if self.scaler_state is None else int(self.scaler_state[2].item())
+
+    def _scaler_struct(self, found, clear_next, call):
+        if self.scaler_state is None:
+            return None
+        sc = E.Scaler()
+        sc.state, sc.found_inf, sc.clear_next = E.ptr(self.scaler_state), E.ptr(found), E.ptr(clear_next)
+        sc.growth_factor, sc.backoff_factor, sc.growth_interval = self._scaler_cfg
+        sc.call = call
+        return C.byref(sc)
+
     def _setup_p2p(self):
-        """symmetric [grad | loss] buffers (double-buffered by step parity) + arrival flags, mapped into every rank"""
+        """symmetric [grad | loss | overflow flag] buffers (double-buffered by step parity) + arrival flags, mapped into every rank"""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         group = self.pg if self.pg is not None else dist.group.WORLD
         self.rank = dist.get_rank(group)
-        stride = (self.P + 1 + 63) // 64 * 64
+        stride = (self.P + 2 + 63) // 64 * 64
         self._sym_stride = stride
         self.sym = symm_mem.empty(2 * stride + 64, dtype=torch.float32, device=self.device)
         self.sym.zero_()
@@ -245,13 +281,14 @@ class Trainer:
         VP = C.c_void_p * self.world
         self._peer_grads = [VP(*[b + 4 * k * stride for b in bases]) for k in range(2)]
         self._peer_flags = VP(*[b + 4 * 2 * stride for b in bases])
-        self._gviews = [self.sym[k * stride:k * stride + self.P + 1] for k in range(2)]
-        self.reduced = torch.zeros(self.P + 1, dtype=torch.float32, device=self.device)
+        self._gviews = [self.sym[k * stride:k * stride + self.P + 2] for k in range(2)]
+        self.reduced = torch.zeros(self.P + 2, dtype=torch.float32, device=self.device)
 
     # ---- one optimisation step ------------------------------------------------------------------
     def _finish(self):
         """optimiser step: ONE launch (Adam + clearing of the next step's gradient vector + in-place refresh of the fp16
         operand image); with several ranks the same launch first all-reduces the gradient over NVLink peer memory"""
+        call = self.steps                # parity of THIS call: selects the overflow flag / beta-power slots
         self.steps += 1
         st = E.stream(self.device)
         repack = 1 if self.prec == E.PREC_F16_TC else 0
@@ -259,28 +296,39 @@ class Trainer:
             # the optimiser kernel writes the flat parameters without touching their version counters: a later fp16 render
             # (previews, render_frames) must not reuse an operand image packed from older weights
             self.h.generation += 1
+        P = self.P
         if self.comm == "p2p":
             k = self.steps & 1
-            E.check(E.lib().tnerf_allreduce_adam_step(self.h.h, E.ptr(self.flat), E.ptr(self.exp_avg), E.ptr(self.exp_avg_sq), self.P,
+            sc = self._scaler_struct(None, None, call)
+            E.check(E.lib().tnerf_allreduce_adam_step(self.h.h, E.ptr(self.flat), E.ptr(self.exp_avg), E.ptr(self.exp_avg_sq), P,
                                                       self._peer_grads[k], self._peer_flags, self.world, self.rank, self.steps, self.steps,
                                                       self.lr, self.betas[0], self.betas[1], self.eps, E.ptr(self.reduced),
-                                                      E.ptr(self._gviews[k ^ 1]), repack, st), "tnerf_allreduce_adam_step")
-            return self.reduced[self.P:]
+                                                      E.ptr(self._gviews[k ^ 1]), repack, sc, st), "tnerf_allreduce_adam_step")
+            return self.reduced[P:P + 1]
         if self.world > 1:
             torch.distributed.all_reduce(self.gbuf, group=self.pg)
         # the gradient vector and its loss slot are cleared by the optimiser launch; the loss is handed out through loss_out
-        E.check(E.lib().tnerf_optimizer_step(self.h.h, E.ptr(self.flat), E.ptr(self.gbuf), E.ptr(self.exp_avg), E.ptr(self.exp_avg_sq), self.P,
-                                             self.P + 1, self.steps, self.lr, self.betas[0], self.betas[1], self.eps, E.ptr(self.loss_out),
-                                             repack, st),
+        sc = self._scaler_struct(self.gbuf[P + 1 + (call & 1):], self.gbuf[P + 1 + ((call + 1) & 1):], call)
+        E.check(E.lib().tnerf_optimizer_step(self.h.h, E.ptr(self.flat), E.ptr(self.gbuf), E.ptr(self.exp_avg), E.ptr(self.exp_avg_sq), P,
+                                             P + 1, self.steps, self.lr, self.betas[0], self.betas[1], self.eps, E.ptr(self.loss_out),
+                                             repack, sc, st),
                 "tnerf_optimizer_step")
         return self.loss_out
 
     def _launch(self, rs, target, n, jitter, global_rays):
         st = E.stream(self.device)
-        gbuf = self._gviews[(self.steps + 1) & 1] if self.comm == "p2p" else self.gbuf      # [gradient | loss] of this step, zero on entry
+        P = self.P
+        gbuf = self._gviews[(self.steps + 1) & 1] if self.comm == "p2p" else self.gbuf      # [gradient | loss | flag(s)] of this step, zero on entry
         denom = 3.0 * float(global_rays if global_rays else n * self.world)
+        scale = found = None
+        if self.scaler_state is not None:
+            if self._scale_init is None:         # default initial scale: largest loss gradient 2/denom -> [64, 128) (fp16-friendly)
+                self._scale_init = 2.0 ** (math.ceil(math.log2(denom)) + 6)
+                self.scaler_state[0] = self._scale_init
+            scale = self.scaler_state
+            found = gbuf[P + 1:] if self.comm == "p2p" else gbuf[P + 1 + (self.steps & 1):]
         E.check(E.lib().tnerf_train_fwd_bwd(self.h.h, C.byref(rs), E.ptr(target), n, self.near, self.far, self.S, E.ptr(jitter),
-                                            int(self.white), self.prec, denom, None, E.ptr(gbuf[self.P:]), E.ptr(gbuf), st),
+                                            int(self.white), self.prec, denom, None, E.ptr(gbuf[P:]), E.ptr(gbuf), E.ptr(scale), E.ptr(found), st),
                 "tnerf_train_fwd_bwd")
         return self._finish()
 
@@ -312,15 +360,16 @@ class Trainer:
     # ---- torch.optim.Adam-compatible state ---------------------------------------------------------
     def state_dict(self):
         state, off = {}, 0
+        applied = self.applied_steps()
         for i, p in enumerate(self.model._params()):
             n = p.numel()
-            state[i] = {"step": torch.tensor(float(self.steps)), "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
+            state[i] = {"step": torch.tensor(float(applied)), "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
                         "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
             off += n
         group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False, "maximize": False,
                  "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False,
                  "params": list(range(len(state)))}
-        return {"state": state if self.steps else {}, "param_groups": [group]}
+        return {"state": state if applied else {}, "param_groups": [group]}
 
     def load_state_dict(self, sd):
         off = 0
@@ -335,6 +384,8 @@ class Trainer:
         if sd.get("param_groups"):
             g = sd["param_groups"][0]
             self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
+        if self.scaler_state is not None:
+            self._reset_beta_powers(self.steps)
 
     def refresh(self):
         """call after parameters were changed from outside (load_state_dict on the model)"""

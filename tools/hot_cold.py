@@ -32,7 +32,7 @@ for nsets in (1, 124):
         for i in range(reps):
             k = i % nsets
             E.check(E.lib().tnerf_train_fwd_bwd(tr.h.h, C.byref(rss[k]), E.ptr(tgt[k]), n, 2.0, 6.0, S, E.ptr(jit[k]), 1, tr.prec, 3.0 * n, None,
-                                                E.ptr(tr.loss_view), E.ptr(tr.gbuf), E.stream(dev)))
+                                                E.ptr(tr.loss_view), E.ptr(tr.gbuf), None, None, E.stream(dev)))
         b.record()
         torch.cuda.synchronize()
         d = dbg.cpu().tolist()

@@ -28,7 +28,7 @@ for S, n in cases:
     t0 = time.time()
     for k in range(launches):
         E.check(E.lib().tnerf_train_fwd_bwd(tr.h.h, C.byref(rs), E.ptr(tgt), n, 2.0, 6.0, S, E.ptr(jit), 1, tr.prec, 3.0 * n, None,
-                                            E.ptr(tr.loss_view), E.ptr(tr.gbuf), E.stream(dev)))
+                                            E.ptr(tr.loss_view), E.ptr(tr.gbuf), None, None, E.stream(dev)))
         if k % 10 == 9:
             torch.cuda.synchronize()
             print(f"S={S} n={n}: {k + 1} launches ok, {time.time() - t0:.1f} s", flush=True)

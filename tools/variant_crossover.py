@@ -26,8 +26,8 @@ for n in (100, 1000, 2048, 4096, 4097, 6144, 8192, 16384, 65536):
     rss = [engine.ray_source(c2w=pose, H=100, W=100, focal=138.9, pixel_index=pix[k]) for k in range(nsets)]
     res = []
     for mode, sync in (("1000000000", "0"), ("1", "1")):
-        os.environ["TNERF_TRAIN_UNROLL_FROM"] = mode
-        os.environ["TNERF_TRAIN_SYNC"] = sync
+        tr.h.set_option("unroll_from", int(mode))
+        tr.h.set_option("train_sync", int(sync))
         reps = max(20, 400000 // n)
         for timed in (False, True):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -35,10 +35,10 @@ for n in (100, 1000, 2048, 4096, 4097, 6144, 8192, 16384, 65536):
             for i in range(reps):
                 k = i % nsets
                 E.check(E.lib().tnerf_train_fwd_bwd(tr.h.h, C.byref(rss[k]), E.ptr(tgt[k]), n, 2.0, 6.0, S, E.ptr(jit[k]), 1, tr.prec, 3.0 * n, None,
-                                                    E.ptr(tr.loss_view), E.ptr(tr.gbuf), E.stream(dev)))
+                                                    E.ptr(tr.loss_view), E.ptr(tr.gbuf), None, None, E.stream(dev)))
             b.record()
             torch.cuda.synchronize()
         res.append(a.elapsed_time(b) / reps * 1e3)
     tiles = n * S / 64 / 296
     print(f"n={n:6d} ({tiles:6.1f} tiles/stream): rolled / half a tile apart {res[0]:8.1f} us, unrolled / in phase {res[1]:8.1f} us  ({res[0] / res[1]:.3f}x)", flush=True)
-os.environ.pop("TNERF_TRAIN_UNROLL_FROM", None)
+
