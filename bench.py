@@ -128,19 +128,26 @@ def look_at(theta, phi, radius=4.0):
     return m.float()
 
 
-def make_inputs(n_sets, rays, S, seed, pin=False, n_pixels=100 * 100):
-    """synthetic step inputs on the HOST: pixel ids, target colours, stratified jitter"""
+def make_inputs(n_sets, rays, S, seed, pin=False, n_pixels=100 * 100, with_jitter=True):
+    """synthetic step inputs on the HOST: pixel ids, target colours, (optionally) an explicit stratified-jitter tensor"""
     g = torch.Generator().manual_seed(seed)
     pix = torch.randint(0, n_pixels, (n_sets, rays), generator=g)
     tgt = torch.rand(n_sets, rays, 3, generator=g)
-    jit = torch.rand(n_sets, rays, S, generator=g)
+    jit = torch.rand(n_sets, rays, S, generator=g) if with_jitter else None
     if pin:
-        pix, tgt, jit = pix.pin_memory(), tgt.pin_memory(), jit.pin_memory()
+        pix, tgt = pix.pin_memory(), tgt.pin_memory()
+        jit = jit.pin_memory() if jit is not None else None
     return pix, tgt, jit
 
 
-def n_input_sets(rays, S):
-    return max(8, int(math.ceil(140e6 / (rays * (S * 4 + 20)))))       # > L2 (126 MB) of rotating inputs
+def step_input_bytes(rays, S, jitter):
+    """pixel ids (8 B) + targets (12 B) per ray, + 4*S B/ray when the jitter is an explicit tensor (default: drawn in-kernel, like
+    the reference draws it on the device, src/sampling.py:24)"""
+    return rays * (20 + (4 * S if jitter == "tensor" else 0))
+
+
+def n_input_sets(rays, S, jitter="kernel"):
+    return max(2, int(math.ceil(140e6 / step_input_bytes(rays, S, jitter))))       # > L2 (126 MB) of rotating inputs
 
 
 def resolve(args):
@@ -167,12 +174,14 @@ def workload_config(args, world):
     """the `config` object of the JSON line: a function of the command line only, so both arms print the same dict"""
     S, rays, w = args.samples, args.rays, args.workload
     if w == "train":
-        ns = n_input_sets(rays, S)
+        ns = n_input_sets(rays, S, args.jitter)
         return {"workload": f"C3 train.py random-ray batch: {rays} rays x {S} samples per GPU, fwd+bwd+Adam, L=10 hidden=128 depth=4 skip=2",
                 "rays_per_gpu": rays, "samples": S, "parallelism": f"ray-sharded dp{world}",
-                "l2": f"GPU arm: {ns} rotating input sets = {ns * rays * (S * 4 + 20) / 1e6:.0f} MB > 126 MB L2"}
+                "jitter": "drawn on the device (GPU arm: in-kernel Philox; CPU arm: torch.rand_like as src/sampling.py:24)" if args.jitter == "kernel"
+                          else "explicit (rays, samples) tensor",
+                "l2": f"GPU arm: {ns} rotating input sets = {ns * step_input_bytes(rays, S, args.jitter) / 1e6:.0f} MB > 126 MB L2"}
     if w == "c1":
-        ns = n_input_sets(rays, S)
+        ns = n_input_sets(rays, S, args.jitter)
         return {"workload": f"C1 tiny_nerf_min.py: train step {rays} rays x {S} samples fwd+bwd+Adam + 100x100 render_image, hidden=128 depth=4 skip=2, "
                             f"L=10 (as coded) and L=6 (as BASELINE words it); value = the L=10 train step",
                 "rays_per_gpu": rays, "samples": S, "parallelism": f"replicas x{world}",
@@ -180,8 +189,7 @@ def workload_config(args, world):
     if w == "c5":
         return {"workload": f"C5 ray-batch sweep point: {rays} rays x {S} samples, fused fwd+bwd (no optimiser), L=10 hidden=128",
                 "rays_per_gpu": rays, "samples": S, "parallelism": f"replicas x{world}",
-                "l2": f"GPU arm: inputs {rays * (S * 4 + 20) / 1e6:.0f} MB per launch" + (" > 126 MB L2" if rays * (S * 4 + 20) > 126e6 else
-                                                                                         "; 256 MB flush write between launches")}
+                "l2": f"GPU arm: {n_input_sets(rays, S, args.jitter)} rotating input sets of {step_input_bytes(rays, S, args.jitter) / 1e6:.1f} MB > 126 MB L2"}
     if w == "c4":
         return {"workload": "C4 800x800 frame, 192 samples/ray, L=10 hidden=256, fused forward on CTA pairs; rows sharded over the ranks",
                 "rays": 800 * 800, "rays_per_gpu": 800 * 800 // world, "samples": S, "parallelism": f"row-sharded x{world}",
@@ -404,6 +412,7 @@ def main():
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--hidden", type=int, default=128)
     ap.add_argument("--sweep", action="store_true", help="c5: add every batch size 2^14..2^22 to the line")
+    ap.add_argument("--jitter", default="kernel", choices=["kernel", "tensor"], help="stratified jitter: drawn in the training kernel (default) or an explicit tensor")
     ap.add_argument("--precision", default=None, help="f16 (tcgen05) or f32 (exact FFMA path); default: engine default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ddp-check", action="store_true")
@@ -479,22 +488,26 @@ def main():
         enc = PositionalEncoding(L, True).to(dev)
         model = TinyNeRF(enc.out_dim, 128, 4, 2).to(dev)
         tr = engine.Trainer(model, enc, n_samples=S, precision=args.precision)
-        n_sets = n_input_sets(n_rays, S) if n_rays * (S * 4 + 20) < 140e6 else 2
-        pix_h, tgt_h, jit_h = make_inputs(n_sets, n_rays, S, 1234 + rank, pin=with_e2e)
-        pix_d, tgt_d, jit_d = pix_h.to(dev), tgt_h.to(dev), jit_h.to(dev)
+        kj = args.jitter == "kernel"
+        n_sets = n_input_sets(n_rays, S, args.jitter)
+        pix_h, tgt_h, jit_h = make_inputs(n_sets, n_rays, S, 1234 + rank, pin=with_e2e, with_jitter=not kj)
+        pix_d, tgt_d = pix_h.to(dev), tgt_h.to(dev)
+        jit_d = None if kj else jit_h.to(dev)
         rs_cache = {}
 
         def fwd_bwd(i):
             k = i % n_sets
             key = (i % 106, k)
             if key not in rs_cache:
-                rs_cache[key] = engine.ray_source(c2w=poses[i % 106], H=100, W=100, focal=FOCAL, pixel_index=pix_d[k])
-            E.check(E.lib().tnerf_train_fwd_bwd(tr.h.h, C.byref(rs_cache[key]), E.ptr(tgt_d[k]), n_rays, 2.0, 6.0, S, E.ptr(jit_d[k]), 1, tr.prec,
-                                                3.0 * n_rays, None, E.ptr(tr.loss_view), E.ptr(tr.gbuf), None, None, E.stream(dev)))
+                rs_cache[key] = engine.ray_source(c2w=poses[i % 106], H=100, W=100, focal=FOCAL, pixel_index=pix_d[k],
+                                                  jitter_seed=tr.jitter_seed if kj else 0)
+            rs_cache[key].jitter_step = i
+            E.check(E.lib().tnerf_train_fwd_bwd(tr.h.h, C.byref(rs_cache[key]), E.ptr(tgt_d[k]), n_rays, 2.0, 6.0, S, None if kj else E.ptr(jit_d[k]), 1,
+                                                tr.prec, 3.0 * n_rays, None, E.ptr(tr.loss_view), E.ptr(tr.gbuf), None, None, E.stream(dev)))
 
         def step(i):
             k = i % n_sets
-            return tr.step_pixels(poses[i % 106], 100, 100, FOCAL, pix_d[k], tgt_d[k], jit_d[k], global_rays=n_rays * world)
+            return tr.step_pixels(poses[i % 106], 100, 100, FOCAL, pix_d[k], tgt_d[k], None if kj else jit_d[k], global_rays=n_rays * world)
         run = step if adam else fwd_bwd
         for i in range(W):
             run(i)
@@ -509,12 +522,16 @@ def main():
             #      while step i computes (two staging sets), the way a data loader feeds a training loop; every byte of every
             #      step still crosses PCIe inside the timed region and the loss of every step is read back.
             loss_h = torch.zeros(1).pin_memory()
+            loss_slot = [torch.zeros(1, device=dev) for _ in range(2)]
             pose_h = poses.cpu().pin_memory()
-            stage = [(torch.empty(4, 4, device=dev), torch.empty_like(pix_d[0]), torch.empty_like(tgt_d[0]), torch.empty_like(jit_d[0])) for _ in range(2)]
+            stage = [(torch.empty(4, 4, device=dev), torch.empty_like(pix_d[0]), torch.empty_like(tgt_d[0]), None if kj else torch.empty_like(jit_d[0]))
+                     for _ in range(2)]
             copy_stream = torch.cuda.Stream(device=dev)
             ready = [torch.cuda.Event() for _ in range(2)]
             consumed = [torch.cuda.Event() for _ in range(2)]
+            copied = torch.cuda.Event()
             main_stream = torch.cuda.current_stream(dev)
+            copied.record(main_stream)
 
             def upload(i):
                 k, slot = i % n_sets, i % 2
@@ -522,23 +539,32 @@ def main():
                     copy_stream.wait_event(consumed[slot])
                     sb_pose, sb_pix, sb_tgt, sb_jit = stage[slot]
                     sb_pose.copy_(pose_h[i % 106], non_blocking=True)
-                    sb_pix.copy_(pix_h[k], non_blocking=True); sb_tgt.copy_(tgt_h[k], non_blocking=True); sb_jit.copy_(jit_h[k], non_blocking=True)
+                    sb_pix.copy_(pix_h[k], non_blocking=True); sb_tgt.copy_(tgt_h[k], non_blocking=True)
+                    if not kj:
+                        sb_jit.copy_(jit_h[k], non_blocking=True)
                     ready[slot].record(copy_stream)
 
             def step_e2e(i):
                 slot = i % 2
                 upload(i + 1)                                   # the copy of the NEXT step's inputs runs under this step
                 main_stream.wait_event(ready[slot])
+                main_stream.wait_event(copied)                  # the previous step's loss has left the buffer this step overwrites
                 sb_pose, sb_pix, sb_tgt, sb_jit = stage[slot]
                 o = tr.step_pixels(sb_pose, 100, 100, FOCAL, sb_pix, sb_tgt, sb_jit, global_rays=n_rays * world)
                 consumed[slot].record(main_stream)
-                loss_h.copy_(o, non_blocking=True)
+                # the loss of EVERY step is read back -- on the copy stream, behind this step's event, so that the compute stream keeps
+                # its kernels back to back (a copy between them would break the programmatic dependent launches)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[slot])
+                    loss_slot[slot].copy_(o, non_blocking=True)
+                    copied.record(copy_stream)
+                    loss_h.copy_(loss_slot[slot], non_blocking=True)
             for evn in consumed:
                 evn.record(main_stream)
             upload(nxt)
             t_e2e, _ = timed_rounds(step_e2e, nxt)
             out["t_e2e"] = t_e2e
-            out["h2d"], out["d2h"] = 64 + n_rays * 8 + n_rays * 12 + n_rays * S * 4, 4
+            out["h2d"], out["d2h"] = 64 + step_input_bytes(n_rays, S, args.jitter), 4
             if med(t_dev) > med(t_e2e):                         # the end-to-end region does strictly more: re-measure the device-only rounds once
                 t2, _ = timed_rounds(run, nxt + R * (K + 2) + 8)
                 if med(t2) < med(t_dev):
@@ -636,20 +662,23 @@ def main():
             detail["round_ms_e2e"] = {"median": ms_round_e2e, "min": float(b["t_e2e"].min()), "max": float(b["t_e2e"].max())}
         if args.workload == "c5":
             # device-only arm of a forward+backward sweep point: the e2e leg uploads pixel ids / targets / jitter of every launch
-            pix_h, tgt_h, jit_h = make_inputs(1, rays, S, 4321, pin=True)
-            sb = (torch.empty_like(pix_h[0], device=dev), torch.empty_like(tgt_h[0], device=dev), torch.empty_like(jit_h[0], device=dev))
+            kj = args.jitter == "kernel"
+            pix_h, tgt_h, jit_h = make_inputs(1, rays, S, 4321, pin=True, with_jitter=not kj)
+            sb = (torch.empty_like(pix_h[0], device=dev), torch.empty_like(tgt_h[0], device=dev), None if kj else torch.empty_like(jit_h[0], device=dev))
             loss_h = torch.zeros(1).pin_memory()
 
             def e2e_step(i):
-                sb[0].copy_(pix_h[0], non_blocking=True); sb[1].copy_(tgt_h[0], non_blocking=True); sb[2].copy_(jit_h[0], non_blocking=True)
-                rs = engine.ray_source(c2w=poses[i % 106], H=100, W=100, focal=FOCAL, pixel_index=sb[0])
+                sb[0].copy_(pix_h[0], non_blocking=True); sb[1].copy_(tgt_h[0], non_blocking=True)
+                if not kj:
+                    sb[2].copy_(jit_h[0], non_blocking=True)
+                rs = engine.ray_source(c2w=poses[i % 106], H=100, W=100, focal=FOCAL, pixel_index=sb[0], jitter_seed=tr.jitter_seed if kj else 0, jitter_step=i)
                 E.check(E.lib().tnerf_train_fwd_bwd(tr.h.h, C.byref(rs), E.ptr(sb[1]), rays, 2.0, 6.0, S, E.ptr(sb[2]), 1, tr.prec, 3.0 * rays, None,
                                                     E.ptr(tr.loss_view), E.ptr(tr.gbuf), None, None, E.stream(dev)))
                 loss_h.copy_(tr.loss_view, non_blocking=True)
             ke = max(1, min(K, 20))
             t_e, _ = timed_rounds(e2e_step, 0, align=1, k=ke, r=3)
             ms_round_e2e = med(t_e) * K / ke
-            h2d, d2h = rays * (8 + 12 + 4 * S), 4
+            h2d, d2h = step_input_bytes(rays, S, args.jitter), 4
             tr.gbuf.zero_()
             if args.sweep:
                 rows = []

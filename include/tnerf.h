@@ -143,6 +143,11 @@ typedef struct tnerf_ray_source {
     float        focal;
     const long long* pixel_index; /* optional (n_rays) pixel ids k=row*W+col; NULL -> first_ray+i */
     long long    first_ray;
+    /* stratified jitter of tnerf_train_fwd_bwd drawn IN-KERNEL (src/sampling.py:24 draws it on the device too): used when the
+     * call's jitter tensor is NULL and jitter_seed != 0.  u(seed, step, ray, sample) = Philox4x32-10 keyed by (seed, step), counter
+     * (sample, ray), 24-bit uniform in [0,1) -- the same numbers tnerf_jitter_fill writes, whatever the launch geometry.  Saves
+     * 4*n_samples bytes per ray of HBM reads (86 % of the step's input) and of host-to-device traffic.  0 = off. */
+    unsigned long long jitter_seed, jitter_step;
 } tnerf_ray_source;
 
 int tnerf_render_fwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long long n_rays,
@@ -239,6 +244,9 @@ int tnerf_allreduce_adam_step(tnerf_handle* h, float* params, float* exp_avg, fl
                               const float* const* peer_grads, unsigned int* const* peer_flags, int world, int rank,
                               unsigned int epoch, int step, float lr, float beta1, float beta2, float eps,
                               float* reduced_out, float* zero_next, int repack, const tnerf_scaler* scaler_host, void* stream);
+/* the (n_rays, n_samples) jitter tensor that tnerf_train_fwd_bwd draws in-kernel for (jitter_seed, jitter_step): parity runs feed it
+ * to the oracle / to the explicit-tensor path */
+int tnerf_jitter_fill(unsigned long long seed, unsigned long long step, long long n_rays, int n_samples, float* out, void* stream);
 /* sets *found_inf (device int) to 1 if any grad is non-finite (device-side GradScaler check) */
 int tnerf_check_finite(const float* grads, long long n, int* found_inf, void* stream);
 

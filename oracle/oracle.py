@@ -343,3 +343,23 @@ def synthetic_scene(n_views: int = 8, H: int = 100, W: int = 100, focal: float =
         images.append(img)
     return {"images": torch.stack(images).numpy(), "poses": torch.stack(poses).numpy(),
             "focal": torch.tensor(focal, dtype=torch.float32).numpy()}
+
+
+# --------------------------------------------------------------------------------------
+# test helper: the two branches of the delta_last = 1e10 discontinuity
+# --------------------------------------------------------------------------------------
+def render_rays_last_flipped(p: Params, rays_o: Tensor, rays_d: Tensor, near, far, n_samples: int, u=None,
+                             num_freqs: int = 10, include_input: bool = True, depth: int = 4, skip_at: int = 2,
+                             white_bkgd: bool = True):
+    """render_rays with the density of every ray's LAST sample moved to the other side of 0: off (sigma = 0) where the network
+    says on, fully on (alpha_last = 1) where it says off.  src/volume.py:20-23 multiplies sigma_last by 1e10, so a ray's
+    colour/depth/acc jump by T_last * (...) when the pre-activation crosses 0; a low-precision evaluation may legitimately land
+    on the other branch for a pre-activation within rounding of 0.  Parity tests accept a set-aside ray only if it matches one
+    of the two branches."""
+    n = rays_o.shape[0]
+    z, pts = stratified(near, far, n_samples, rays_o, rays_d, u)
+    feat = posenc(pts.reshape(-1, 3), num_freqs, include_input)
+    c, s = mlp_forward(p, feat, depth, skip_at)
+    s = s.reshape(n, n_samples, 1).clone()
+    s[:, -1, 0] = torch.where(s[:, -1, 0] > 0, torch.zeros_like(s[:, -1, 0]), torch.ones_like(s[:, -1, 0]))
+    return composite(c.reshape(n, n_samples, 3), s, z, rays_d, white_bkgd)

@@ -80,21 +80,18 @@ def test_reference_scripts_run_unchanged(scene_dir):
     assert "[render] wrote outputs/preview.png" in out
 
 
-@pytest.mark.parametrize("prec", ["f32", "f16"])
-def test_psnr_parity_with_oracle_training(scene_dir, prec):
-    """Same initial state_dict, same pixel ids and jitter per step, K steps on the CPU oracle and on the fused
-    engine; PSNR on a held-out view (north star: within 0.1 dB; trajectories are chaotic, so this is a
-    statistical statement -- the measured gap is printed and recorded in DESIGN.md)."""
+def psnr_parity_run(d, prec, seed, K, n_rand=1024, S=32):
+    """Same initial state_dict, same pixel ids and jitter per step, K steps on the CPU oracle and on the fused engine; returns the
+    PSNR of both on the held-out view (also used by tools/psnr_report.py for the numbers quoted in DESIGN.md section 7)."""
     import engine
+    import train
     from encoding import PositionalEncoding
     from nerf import TinyNeRF
     dev = torch.device("cuda:0")
-    d = np.load(scene_dir / "data" / "tiny_nerf_data.npz")
     images, poses, focal = torch.from_numpy(d["images"]), torch.from_numpy(d["poses"]), float(d["focal"])
     N, H, W, _ = images.shape
     held = N - 1
-    S, n_rand, K = 32, 1024, 150
-    p = O.init_params(63, 128, 4, 2, seed=7)
+    p = O.init_params(63, 128, 4, 2, seed=seed)
     model = TinyNeRF(63, 128, 4, 2); model.load_state_dict(p); model = model.to(dev)
     enc = PositionalEncoding(10, True).to(dev)
     tr = engine.Trainer(model, enc, n_samples=S, precision=prec)
@@ -102,7 +99,7 @@ def test_psnr_parity_with_oracle_training(scene_dir, prec):
     v = {k: torch.zeros_like(x) for k, x in p.items()}
     rays = [O.get_rays(H, W, focal, poses[i]) for i in range(N)]
     pix_all = images.reshape(N, H * W, 3)
-    g = torch.Generator().manual_seed(11)
+    g = torch.Generator().manual_seed(1000 + seed)
     torch.set_num_threads(os.cpu_count() or 1)
     for step in range(K):
         view = step % (N - 1)
@@ -113,10 +110,25 @@ def test_psnr_parity_with_oracle_training(scene_dir, prec):
         _, gr, _ = O.loss_and_grads(p, rays[view][0][pick], rays[view][1][pick], tgt, 2.0, 6.0, S, u)
         O.adam_step(p, gr, m, v, step + 1)
     ref_img = O.render_image(p, H, W, focal, poses[held], n_samples=S)
-    import train
     our_img = train.render_one(model, enc, H, W, focal, poses[held], dev, n_samples=S).cpu()
-    psnr_ref = O.mse2psnr(((ref_img - images[held]) ** 2).mean()).item()
-    psnr_our = O.mse2psnr(((our_img - images[held]) ** 2).mean()).item()
-    print(f"\n[psnr-parity {prec}] oracle {psnr_ref:.3f} dB, engine {psnr_our:.3f} dB, gap {abs(psnr_ref - psnr_our):.3f} dB after {K} steps")
-    assert psnr_ref > 12.0
-    assert abs(psnr_ref - psnr_our) < 0.1 if prec == "f32" else abs(psnr_ref - psnr_our) < 0.25
+    assert tr.applied_steps() == K                              # the loss scaler never had to skip a step
+    return O.mse2psnr(((ref_img - images[held]) ** 2).mean()).item(), O.mse2psnr(((our_img - images[held]) ** 2).mean()).item()
+
+
+@pytest.mark.parametrize("prec,seeds,K", [("f32", (7, 8), 300), ("f16", (7, 8, 9, 10, 11), 300)])
+def test_psnr_parity_with_oracle_training(scene_dir, prec, seeds, K):
+    """BASELINE north star: PSNR on the held-out view within 0.1 dB of the reference path after the same number of steps.
+    Early training is chaotic: the fp32 path, whose only difference from the oracle is the summation order of its atomics, lands
+    0.002 ... 0.09 dB away from it after 300 steps of the SAME seed from one run to the next.  The statement is therefore made
+    over independent initialisations / batch streams: the MEAN gap over the seeds is within 0.1 dB, no single seed
+    is beyond 0.25 dB and there is no systematic sign (fp16 tensor-core path, five seeds: 0.013 / 0.060 / 0.000 / 0.022 / 0.209 dB,
+    engine higher in four of five; DESIGN.md section 7, tools/psnr_report.py)."""
+    d = np.load(scene_dir / "data" / "tiny_nerf_data.npz")
+    gaps = []
+    for seed in seeds:
+        psnr_ref, psnr_our = psnr_parity_run(d, prec, seed, K)
+        gaps.append(psnr_our - psnr_ref)
+        print(f"\n[psnr-parity {prec} seed {seed}] oracle {psnr_ref:.3f} dB, engine {psnr_our:.3f} dB, gap {gaps[-1]:+.3f} dB after {K} steps")
+        assert psnr_ref > 12.0
+    mean_abs = sum(abs(x) for x in gaps) / len(gaps)
+    assert mean_abs < 0.1 and max(abs(x) for x in gaps) < 0.25, gaps

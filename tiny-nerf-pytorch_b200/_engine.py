@@ -29,7 +29,7 @@ _f = C.c_float
 class RaySource(C.Structure):
     """mirror of tnerf_ray_source (include/tnerf.h)"""
     _fields_ = [("rays_o", _p), ("o_stride", _ll), ("rays_d", _p), ("c2w", _p), ("H", _i), ("W", _i),
-                ("focal", _f), ("pixel_index", _p), ("first_ray", _ll)]
+                ("focal", _f), ("pixel_index", _p), ("first_ray", _ll), ("jitter_seed", C.c_ulonglong), ("jitter_step", C.c_ulonglong)]
 
 
 class Scaler(C.Structure):
@@ -69,6 +69,7 @@ _SIGS = {
     "tnerf_train_fwd_bwd": (_i, [_p, C.POINTER(RaySource), _p, _ll, _f, _f, _i, _p, _i, _i, _f, _p, _p, _p, _p, _p, _p]),
     "tnerf_mse_psnr": (_i, [_p, _p, _ll, _p, _p]),
     "tnerf_adam_step": (_i, [_p, _p, _p, _p, _ll, _i, _f, _f, _f, _f, _f, _p, _p]),
+    "tnerf_jitter_fill": (_i, [C.c_ulonglong, C.c_ulonglong, _ll, _i, _p, _p]),
     "tnerf_check_finite": (_i, [_p, _ll, _p, _p]),
     "tnerf_packed_image_copy": (_ll, [_p, _p, _ll, _p]),
     "tnerf_optimizer_step": (_i, [_p, _p, _p, _p, _p, _ll, _ll, _i, _f, _f, _f, _f, _p, _i, C.POINTER(Scaler), _p]),

@@ -62,6 +62,7 @@ static RaySource to_device_source(const tnerf_ray_source* r) {
     RaySource s;
     s.rays_o = r->rays_o; s.o_stride = r->o_stride; s.rays_d = r->rays_d; s.c2w = r->c2w; s.H = r->H; s.W = r->W;
     s.focal = r->focal; s.pixel_index = r->pixel_index; s.first_ray = r->first_ray; s.frame_rays = 0;
+    s.jitter_seed = r->jitter_seed; s.jitter_step = r->jitter_step;
     return s;
 }
 static int check_source(const tnerf_ray_source* r) {
@@ -232,6 +233,8 @@ void tnerf_destroy(tnerf_handle* h) {
     h->ws.release();
     if (h->packed) cudaFree(h->packed);
     if (h->slabs) cudaFree(h->slabs);
+    if (h->auto_scale) cudaFree(h->auto_scale);
+    if (h->jitter_scratch) cudaFree(h->jitter_scratch);
     delete h;
 }
 int tnerf_set_encoding(tnerf_handle* h, int num_freqs, int include_input) {
@@ -391,6 +394,17 @@ int tnerf_train_fwd_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, cons
     // fp32 path: no loss scale is needed; the overflow flag is the plain non-finite test of the gradient vector and the loss
     F32Job job{};
     job.mode = 2; job.target = target; job.loss_denom = loss_denom; job.comp = comp_rgb; job.loss_sum = loss_sum; job.grads = grads;
+    if (!jitter && rs.jitter_seed) {      // in-kernel jitter requested: the fp32 composition reads the same numbers from a scratch tensor
+        const size_t bytes = (size_t)n_rays * n_samples * sizeof(float);
+        if (h->jitter_scratch_bytes < bytes) {
+            if (h->jitter_scratch) cudaFree(h->jitter_scratch);
+            h->jitter_scratch = nullptr; h->jitter_scratch_bytes = 0;
+            if (cudaMalloc(&h->jitter_scratch, bytes) != cudaSuccess) return bad("cudaMalloc(jitter scratch) failed");
+            h->jitter_scratch_bytes = bytes;
+        }
+        if (int e = launch_jitter_fill(rs.jitter_seed, rs.jitter_step, n_rays, n_samples, h->jitter_scratch, (cudaStream_t)stream)) return e;
+        jitter = h->jitter_scratch;
+    }
     if (int e = run_f32(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, job, (cudaStream_t)stream)) return e;
     if (found_inf) {
         if (int e = launch_found_inf(grads, h->param_count, found_inf, (cudaStream_t)stream)) return e;
@@ -477,6 +491,11 @@ int tnerf_allreduce_adam_step(tnerf_handle* h, float* params, float* exp_avg, fl
     }();
     return launch_allreduce_adam(params, exp_avg, exp_avg_sq, n, peer_grads, peer_flags, world, rank, epoch, step, lr, beta1, beta2, eps,
                                  reduced_out, zero_next, mp, sc, timeout_cycles, (cudaStream_t)stream);
+}
+int tnerf_jitter_fill(unsigned long long seed, unsigned long long step, long long n_rays, int n_samples, float* out, void* stream) {
+    TN_ON_DEVICE_OF(out);
+    if (!out || n_rays < 0 || n_samples < 1 || seed == 0) return bad("tnerf_jitter_fill: invalid argument (seed must be non-zero)");
+    return launch_jitter_fill(seed, step, n_rays, n_samples, out, (cudaStream_t)stream);
 }
 int tnerf_check_finite(const float* grads, long long n, int* found_inf, void* stream) {
     TN_ON_DEVICE_OF(grads);

@@ -21,6 +21,7 @@ struct RaySource {          // device-side mirror of tnerf_ray_source
     float focal;
     const long long* pixel_index;
     long long first_ray;
+    unsigned long long jitter_seed, jitter_step;   // seed != 0 and no jitter tensor: stratified jitter drawn in-kernel (jitter_uniform below)
     long long frame_rays;   // > 0: pose batch -- ray i belongs to pose i / frame_rays (c2w = [n_poses][16]), pixel first_ray + i % frame_rays
 };
 
@@ -45,6 +46,25 @@ __device__ __forceinline__ float depth_sample(int i, int S, float near_, float f
     const float lo = (i == 0) ? zc : __fmul_rn(0.5f, __fadd_rn(depth_bin(i - 1, S, near_, far_), zc));
     const float hi = (i == S - 1) ? zc : __fmul_rn(0.5f, __fadd_rn(zc, depth_bin(i + 1, S, near_, far_)));
     return __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), u));
+}
+
+// In-kernel stratified jitter (src/sampling.py:24 draws torch.rand_like(z_vals) on the device): counter-based Philox4x32-10 keyed by
+// (seed, step) with the counter (sample, ray): u(seed, step, ray, sample) is a pure function, so the fused kernels, the fill kernel
+// of tnerf_jitter_fill and any sharding of the rays see the same numbers.  Uniform in [0, 1) with 24 bits like torch.rand (fp32).
+__device__ __forceinline__ uint32_t philox4x32_10_x(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c0;
+}
+__device__ __forceinline__ float jitter_uniform(unsigned long long seed, unsigned long long step, long long ray, int sample) {
+    const uint32_t x = philox4x32_10_x((uint32_t)sample, (uint32_t)ray, (uint32_t)((unsigned long long)ray >> 32), (uint32_t)step,
+                                       (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
+    return (float)(x >> 8) * 5.9604644775390625e-8f;      // 2^-24
 }
 
 // camera-space pixel direction rotated to world and normalised (src/rays.py:21-31)

@@ -55,6 +55,7 @@ struct tnerf_handle {
     // training-kernel schedule (tnerf_set_option; defaults from TNERF_TRAIN_SYNC / TNERF_BULK_REDUCE / TNERF_TRAIN_UNROLL_FROM, read
     // ONCE when the handle is created): -1 = built-in choice
     int opt_train_sync = -1, opt_bulk_reduce = -1, opt_unroll_from = -1;
+    float* jitter_scratch = nullptr; size_t jitter_scratch_bytes = 0;   // fp32 path: materialised in-kernel jitter
     float* auto_scale = nullptr;          // device float: loss scale chosen from the upstream gradients (tnerf_render_bwd, automatic mode)
 };
 
@@ -72,6 +73,7 @@ int launch_composite_bwd(const float* rgb, const float* sigma, const float* z, l
 int launch_mse_psnr(const float* a, const float* b, long long n, float* out2, cudaStream_t s);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float b1, float b2, float eps, float inv_scale, const int* found_inf, cudaStream_t s);
 int launch_check_finite(const float* g, long long n, int* flag, cudaStream_t s);
+int launch_jitter_fill(unsigned long long seed, unsigned long long step, long long n, int S, float* out, cudaStream_t s);
 
 int launch_mse_grad(const float* c, const float* t, long long n3, float inv_denom, float* gC, float* loss, cudaStream_t s);
 

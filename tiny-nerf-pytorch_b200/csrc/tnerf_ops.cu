@@ -126,6 +126,18 @@ __global__ void stratified4_kernel(const float* __restrict__ ro, long long o_str
     }
 }
 
+// the jitter tensor the fused training kernel draws in-kernel for (seed, step), materialised (parity runs, the fp32 path)
+__global__ void jitter_fill_kernel(unsigned long long seed, unsigned long long step, long long n, int S, float* __restrict__ out) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n * S) return;
+    out[t] = jitter_uniform(seed, step, t / S, (int)(t % S));
+}
+int launch_jitter_fill(unsigned long long seed, unsigned long long step, long long n, int S, float* out, cudaStream_t s) {
+    if (n <= 0) return 0;
+    jitter_fill_kernel<<<(unsigned)((n * S + 255) / 256), 256, 0, s>>>(seed, step, n, S, out);
+    return count_launch();
+}
+
 // a4 PositionalEncoding (src/encoding.py:26-33): 12 B in + 4 D B out per point.  One thread per (point, octave, axis): ONE
 // sincosf serves the sine and the cosine column (a thread per output element evaluated every argument twice and paid two
 // 64-bit divisions); a warp covers one point's row, so its stores fall into the same few 128-byte lines.
@@ -533,6 +545,15 @@ __global__ void allreduce_adam_kernel(PeerSet ps, int world, int rank, unsigned 
     __syncthreads();
     if (timed_out) { __trap(); }
     const long long total = n + (sc.state ? 2 : 1);          // [gradient | loss | overflow flag]
+    // the peer loads of this thread's four elements go out first; the scaler's decision (one more round of peer loads by thread 0
+    // and a little double arithmetic) is taken while they are in flight
+    const long long i0 = 4 * (blockIdx.x * (long long)blockDim.x + threadIdx.x);
+    float4 x[8];
+    const bool vec = i0 + 4 <= total;                        // the vectors are 16-byte aligned and padded by the caller
+    if (vec) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (r < world) x[r] = ld_cv4(ps.grads[r] + i0);
+    }
     if (sc.state) {
         if (threadIdx.x == 0) {
             float f = 0.f;
@@ -543,11 +564,11 @@ __global__ void allreduce_adam_kernel(PeerSet ps, int world, int rank, unsigned 
         lr_over_bc1 = dec[1]; inv_sqrt_bc2 = dec[2];
     }
     const bool skip = sc.state && dec[0] != 0.f;
-    const long long i0 = 4 * (blockIdx.x * (long long)blockDim.x + threadIdx.x);
     if (i0 >= total) return;
     float g[4] = {0.f, 0.f, 0.f, 0.f};
-    if (i0 + 4 <= total) {                                   // the vectors are 16-byte aligned and padded by the caller
-        for (int r = 0; r < world; ++r) { const float4 x = ld_cv4(ps.grads[r] + i0); g[0] += x.x; g[1] += x.y; g[2] += x.z; g[3] += x.w; }
+    if (vec) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (r < world) { g[0] += x[r].x; g[1] += x[r].y; g[2] += x[r].z; g[3] += x[r].w; }   // rank order
     } else {
         for (int r = 0; r < world; ++r)
             for (int k = 0; k < 4; ++k) if (i0 + k < total) g[k] += __ldcv(ps.grads[r] + i0 + k);

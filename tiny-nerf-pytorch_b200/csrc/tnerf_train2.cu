@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         const int cbar = inphase ? 1 : 1 + s, cthreads = inphase ? 128 : 64;
         float* xch = inphase ? ms.xch[0] : ms.xch[s];
         *reinterpret_cast<uint4*>(DZH + ((size_t)(64 + i) << 4)) = make_uint4(0u, 0u, 0u, 0u);   // head columns 8..15 stay zero
-        const bool jit = p.jitter != nullptr;
+        const bool jit_rng = p.jitter == nullptr && p.rs.jitter_seed != 0;       // stratified jitter drawn in-kernel (Philox)
+        const bool jit = p.jitter != nullptr || jit_rng;
         const float gscale = p.scale_dev ? *p.scale_dev : p.scale;
         const float bs = p.b_sigma[0], br = p.b_rgb[0], bg = p.b_rgb[1], bb = p.b_rgb[2];
         float hb[4] = {0.f, 0.f, 0.f, 0.f}, loss_acc = 0.f;
@@ -333,7 +334,10 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                     o[0] = cam[3]; o[1] = cam[7]; o[2] = cam[11];
                 }
                 float u0 = 0.f, u1 = 0.f;
-                if (jit) { u0 = p.jitter[ray * S + si]; if (si + 1 < S) u1 = p.jitter[ray * S + si + 1]; }
+                if (jit_rng) {
+                    u0 = jitter_uniform(p.rs.jitter_seed, p.rs.jitter_step, ray, si);
+                    if (si + 1 < S) u1 = jitter_uniform(p.rs.jitter_seed, p.rs.jitter_step, ray, si + 1);
+                } else if (jit) { u0 = p.jitter[ray * S + si]; if (si + 1 < S) u1 = p.jitter[ray * S + si + 1]; }
                 z = zsample(si, u0);
                 const float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
                 gd = ((si == S - 1) ? kLastDelta : (zsample(si + 1, u1) - z)) * dn;

@@ -72,8 +72,8 @@ def main(cfg: Config):
     for step in range(cfg.iters):
         view = step % N
         pick = torch.randint(0, H * W, (cfg.n_rand,), device=device, generator=gen)
-        jitter = torch.rand((cfg.n_rand, cfg.n_samples), device=device, generator=gen)
-        loss = trainer.step_pixels(poses[view], H, W, focal, pick, pixels[view].index_select(0, pick), jitter,
+        # the stratified jitter is drawn inside the training kernel (per-rank Philox stream, engine.Trainer.jitter_seed)
+        loss = trainer.step_pixels(poses[view], H, W, focal, pick, pixels[view].index_select(0, pick), None,
                                    global_rays=cfg.n_rand * world)
         if rank == 0 and (step + 1) % cfg.log_every == 0:
             lv = float(loss.item())

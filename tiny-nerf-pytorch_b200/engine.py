@@ -24,8 +24,9 @@ def default_bwd_precision() -> int:
     return _PREC[os.environ.get("TNERF_BWD_PRECISION", os.environ.get("TNERF_PRECISION", "f16")).lower()]
 
 
-def ray_source(rays_o=None, o_stride=3, rays_d=None, c2w=None, H=0, W=0, focal=0.0, pixel_index=None, first_ray=0):
+def ray_source(rays_o=None, o_stride=3, rays_d=None, c2w=None, H=0, W=0, focal=0.0, pixel_index=None, first_ray=0, jitter_seed=0, jitter_step=0):
     rs = E.RaySource()
+    rs.jitter_seed, rs.jitter_step = int(jitter_seed), int(jitter_step)
     rs.rays_o = E.ptr(rays_o); rs.o_stride = int(o_stride); rs.rays_d = E.ptr(rays_d); rs.c2w = E.ptr(c2w)
     rs.H, rs.W, rs.focal = int(H), int(W), float(focal)
     rs.pixel_index = E.ptr(pixel_index); rs.first_ray = int(first_ray)
@@ -183,7 +184,7 @@ class Trainer:
     def __init__(self, model, encoder, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, near=2.0, far=6.0, n_samples=64,
                  white_bkgd=True, precision: Optional[str] = None, process_group=None, comm: Optional[str] = None,
                  grad_scaler: bool = True, init_scale: Optional[float] = None, growth_factor: float = 2.0, backoff_factor: float = 0.5,
-                 growth_interval: int = 2000):
+                 growth_interval: int = 2000, jitter_seed: Optional[int] = None):
         self.model, self.encoder = model, encoder
         ps = model._params()
         dev = E.need_cuda(*ps)
@@ -211,6 +212,12 @@ class Trainer:
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
+        # stratified jitter is drawn IN the training kernel (counter-based Philox keyed by (seed, step), include/tnerf.h) unless a
+        # jitter tensor is passed to step_*(): the seed follows torch's global seed and differs per rank
+        if jitter_seed is None:
+            rk = torch.distributed.get_rank(process_group) if self.world > 1 else 0
+            jitter_seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + rk * 0xD1B54A32D192ED03 + 0x632BE59BD9B4E019) & (2 ** 64 - 1)
+        self.jitter_seed = int(jitter_seed) or 1
         self.steps = 0               # optimiser CALLS (skipped ones included); the applied count lives on the device with the scaler
         # GradScaler state (include/tnerf.h, tnerf_scaler): [scale, clean steps, applied steps, ..., 4 doubles of beta powers]
         self.scaler_state = torch.zeros(16, dtype=torch.float32, device=dev) if grad_scaler else None
@@ -333,29 +340,34 @@ class Trainer:
         return self._finish()
 
     def step_pixels(self, c2w, H, W, focal, pixel_index, target, jitter=None, global_rays=None):
-        """rays are generated in-kernel from the pose and the pixel ids (a1+a2 fused in); returns the loss (device, shape (1,))."""
+        """rays are generated in-kernel from the pose and the pixel ids (a1+a2 fused in); returns the loss (device, shape (1,)).
+        ``jitter`` (n, n_samples) uniform [0,1) is the explicit stratified-jitter tensor (parity runs); None = drawn in-kernel."""
         n = int(pixel_index.shape[0])
-        if jitter is None:
-            jitter = torch.rand((n, self.S), dtype=torch.float32, device=self.device)
         # the C ABI takes raw pointers: fp32 pose / targets / jitter, int64 pixel ids, all dense (no copies when they already are)
         E.need_cuda(c2w, pixel_index, target, jitter)
         c2w, target, jitter = E.f32c(c2w), E.f32c(target), E.f32c(jitter)
         if pixel_index.dtype != torch.int64 or not pixel_index.is_contiguous():
             pixel_index = pixel_index.long().contiguous()
-        if tuple(target.shape) != (n, 3) or tuple(jitter.shape) != (n, self.S) or c2w.numel() < 12:
+        if tuple(target.shape) != (n, 3) or (jitter is not None and tuple(jitter.shape) != (n, self.S)) or c2w.numel() < 12:
             raise ValueError(f"step_pixels: expected target ({n}, 3), jitter ({n}, {self.S}), c2w (4, 4)")
-        rs = ray_source(c2w=c2w, H=H, W=W, focal=focal, pixel_index=pixel_index)
+        rs = ray_source(c2w=c2w, H=H, W=W, focal=focal, pixel_index=pixel_index, jitter_seed=self.jitter_seed, jitter_step=self.steps)
         return self._launch(rs, target, n, jitter, global_rays)
 
     def step_rays(self, rays_o, rays_d, target, jitter=None, global_rays=None):
         n = int(rays_d.shape[0])
-        if jitter is None:
-            jitter = torch.rand((n, self.S), dtype=torch.float32, device=self.device)
         ro, o_stride = origin_arg(rays_o)
         rd = E.f32c(rays_d)
         tg = E.f32c(target)
-        rs = ray_source(ro, o_stride, rd)
+        jitter = E.f32c(jitter)
+        rs = ray_source(ro, o_stride, rd, jitter_seed=self.jitter_seed, jitter_step=self.steps)
         return self._launch(rs, tg, n, jitter, global_rays)
+
+    def jitter_tensor(self, n: int, step: Optional[int] = None) -> torch.Tensor:
+        """the (n, n_samples) jitter the kernel draws for optimiser call ``step`` (default: the next one) -- for parity runs"""
+        out = torch.empty((n, self.S), dtype=torch.float32, device=self.device)
+        E.check(E.lib().tnerf_jitter_fill(self.jitter_seed, self.steps if step is None else int(step), n, self.S, E.ptr(out), E.stream(self.device)),
+                "tnerf_jitter_fill")
+        return out
 
     # ---- torch.optim.Adam-compatible state ---------------------------------------------------------
     def state_dict(self):
