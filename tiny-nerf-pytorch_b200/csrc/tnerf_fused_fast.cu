@@ -23,7 +23,7 @@ constexpr int FF_MAX_CHUNKS = 32;
 struct FastSmem {
     float part[2][2][FF_MAX_CHUNKS][8];   // [slot][unit parity][chunk] = {P, sum w r, sum w g, sum w b, sum w z, sum w, -, -}
     float tin[2][FF_MAX_CHUNKS];          // transmittance entering each chunk (weights output only)
-    uint64_t bar_w, bar_x[2], bar_a[2], bar_acc[2], bar_head[2], bar_xfree[2], bar_hfree[2];
+    uint64_t bar_w, bar_w0, bar_x[2], bar_a[2], bar_acc[2], bar_head[2], bar_xfree[2], bar_hfree[2];
     uint32_t tmem_slot;
 };
 
@@ -43,8 +43,10 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_w = smem_u32(&sm.bar_w);
 
+    const uint32_t bar_w0 = smem_u32(&sm.bar_w0);
     if (warp == 16 && lane == 0) {
         mbar_init(bar_w, 1);
+        mbar_init(bar_w0, 1);
         for (int w = 0; w < 2; ++w) {
             mbar_init(smem_u32(&sm.bar_x[w]), 128);
             mbar_init(smem_u32(&sm.bar_a[w]), 128);
@@ -54,6 +56,16 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
             mbar_init(smem_u32(&sm.bar_hfree[w]), 128);
         }
         fence_barrier_init();
+        // The weight image is requested FIRST, before tensor-memory allocation and the block-wide set-up, and in two parts: layer 0
+        // (16 KB: the first GEMM of the first tile waits only for it) and the rest.  A single 100x100 frame is 17 tiles per slot: the
+        // ~140 KB per CTA used to be requested after the set-up and awaited as a whole before the first instruction was issued.
+        const uint32_t w0_bytes = p.plan.layer[1].b_off;       // layers are packed in order, layer 0 at offset 0
+        mbar_expect_tx(bar_w0, w0_bytes);
+        for (uint32_t off = 0; off < w0_bytes; off += 32768u)
+            bulk_g2s(smem_u32(smem) + off, reinterpret_cast<const uint8_t*>(p.image) + off, min(32768u, w0_bytes - off), bar_w0);
+        mbar_expect_tx(bar_w, p.plan.image_bytes - w0_bytes);
+        for (uint32_t off = w0_bytes; off < p.plan.image_bytes; off += 32768u)
+            bulk_g2s(smem_u32(smem) + off, reinterpret_cast<const uint8_t*>(p.image) + off, min(32768u, p.plan.image_bytes - off), bar_w);
     }
     if (warp == 0) { tmem_alloc(smem_u32(&sm.tmem_slot), 512); tmem_relinquish(); }
     tc_fence_before();
@@ -85,17 +97,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
             for (int l = 0; l < depth; ++l)
                 for (int sgi = 0; sgi < p.plan.layer[l].nseg; ++sgi)
                     if (p.plan.layer[l].seg_kind[sgi] == SEG_X) last_x = l;
-            if (w == 0 && lane == 0) {
-                mbar_expect_tx(bar_w, p.plan.image_bytes);
-                uint32_t off = 0;
-                while (off < p.plan.image_bytes) {
-                    const uint32_t n = min(32768u, p.plan.image_bytes - off);
-                    bulk_g2s(smem_u32(smem) + off, reinterpret_cast<const uint8_t*>(p.image) + off, n, bar_w);
-                    off += n;
-                }
-            }
-            __syncwarp();
-            mbar_wait(bar_w, 0);
+            bool w_rest = false;                                // "the layers behind layer 0 have landed" has been observed
+            mbar_wait(bar_w0, 0);
             uint32_t ph_x = 0, ph_a = 0, ph_hf = 0;
             bool first_head = true;
             const uint32_t wbase = smem_u32(smem);
@@ -128,6 +131,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
                         mbar_wait(bar_x, ph_x); ph_x ^= 1; tc_fence_after();
                         if (elect_one()) { FF_TS(XS, tACC, tX, b0, 256u, i128, 0u); tc_commit(bar_acc); }
                         __syncwarp();
+                        if (!w_rest) { mbar_wait(bar_w, 0); w_rest = true; }
                         mbar_wait(bar_a, ph_a); ph_a ^= 1; tc_fence_after();
                         if (elect_one()) { FF_TS(8, tACC, tACT, b1, 256u, i128, 0u); FF_TS(1, tACC, tONES, b1 + 8 * 256u, 256u, i128, 1u); tc_commit(bar_acc); }
                         __syncwarp();
@@ -149,7 +153,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
                     }
                 }
 #undef FF_TS
-            } else
+            } else {
+            mbar_wait(bar_w, 0);
             for (long long u = 2LL * blockIdx.x + w; u < p.n_units; u += stride) {
                 for (int g = 0; g < p.G; ++g) {
                     for (int step = 0; step <= depth; ++step) {
@@ -186,6 +191,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fused_fwd_fast_kernel(const __g
                         if (step == depth) first_head = false;
                     }
                 }
+            }
             }
         }
     } else if (warp < 8) {

@@ -529,7 +529,8 @@ __global__ void allreduce_adam_kernel(PeerSet ps, int world, int rank, unsigned 
     if (threadIdx.x == 0) timed_out = 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");       // programmatic stream serialisation: this rank's gradient (previous kernel) is complete
     if (blockIdx.x == 0 && threadIdx.x < world) {
-        __threadfence_system();
+        // this rank's vector was written by the PREVIOUS kernels of the stream (complete and flushed: griddepcontrol.wait / stream
+        // order); the system-scope release of the flag store orders it behind them for the peers -- no separate fence
         st_release_sys(ps.flags[threadIdx.x] + rank, epoch);
     }
     if (threadIdx.x < world) {

@@ -15,7 +15,7 @@ rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-res = ddp_train.exchange_self_check(dev, steps=6)
+res = ddp_train.exchange_self_check(dev, steps=4)
 ok = res["ok"] and (res["comm"] == "p2p" or os.environ.get("TNERF_COMM") == "nccl")
 if rank == 0:
     print(f"DDP_CHECK {'OK' if ok else 'FAIL'} " + " ".join(f"{k}={v}" for k, v in res.items()), flush=True)
