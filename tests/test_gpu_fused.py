@@ -546,8 +546,10 @@ def test_grad_scaler_skips_an_overflowed_step_and_recovers(dev, prec):
     p_bad, log_bad, scale_bad = run(True)
     assert scale_bad == 0.5 * scale_clean
     # same trajectory: the halved scale only moves fp16 roundings of the backward operands (nothing at all on the fp32 path)
-    tol = 0.0 if prec == "f32" else 2e-4
-    assert (p_clean - p_bad).abs().max().item() <= tol + (5e-7 if prec == "f32" else 0.0), (p_clean - p_bad).abs().max().item()
+    # fp32 path: the split-K weight-gradient GEMMs add their partials with atomics (order varies run to run: last-bit gradient
+    # differences), and Adam's m / sqrt(v) turns those into up to ~1e-2 of one lr = 5e-4 step on near-zero-gradient parameters
+    tol = 5e-6 if prec == "f32" else 2e-4
+    assert (p_clean - p_bad).abs().max().item() <= tol, (p_clean - p_bad).abs().max().item()
     assert max(abs(a - b) for a, b in zip(log_clean, log_bad)) < 1e-4
 
 

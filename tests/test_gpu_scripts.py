@@ -80,9 +80,12 @@ def test_reference_scripts_run_unchanged(scene_dir):
     assert "[render] wrote outputs/preview.png" in out
 
 
-def psnr_parity_run(d, prec, seed, K, n_rand=1024, S=32):
+def psnr_parity_run(d, prec, seed, K, n_rand=1024, S=32, n_eval=8, eval_every=5):
     """Same initial state_dict, same pixel ids and jitter per step, K steps on the CPU oracle and on the fused engine; returns the
-    PSNR of both on the held-out view (also used by tools/psnr_report.py for the numbers quoted in DESIGN.md section 7)."""
+    PSNR of both on the held-out view (also used by tools/psnr_report.py for the numbers quoted in DESIGN.md section 7).
+    The held-out MSE is averaged over the last `n_eval` checkpoints, `eval_every` steps apart: at lr = 5e-4 the PSNR of ONE
+    trajectory moves by a few tenths of a dB from step to step this early in training, and two trajectories that differ in the
+    last bits decorrelate within tens of steps -- a single-checkpoint comparison measures that jitter, not the arithmetic."""
     import engine
     import train
     from encoding import PositionalEncoding
@@ -101,6 +104,7 @@ def psnr_parity_run(d, prec, seed, K, n_rand=1024, S=32):
     pix_all = images.reshape(N, H * W, 3)
     g = torch.Generator().manual_seed(1000 + seed)
     torch.set_num_threads(os.cpu_count() or 1)
+    mse_ref, mse_our = [], []
     for step in range(K):
         view = step % (N - 1)
         pick = torch.randint(0, H * W, (n_rand,), generator=g)
@@ -109,10 +113,12 @@ def psnr_parity_run(d, prec, seed, K, n_rand=1024, S=32):
         tr.step_pixels(poses[view].to(dev), H, W, focal, pick.to(dev), tgt.to(dev), u.to(dev))
         _, gr, _ = O.loss_and_grads(p, rays[view][0][pick], rays[view][1][pick], tgt, 2.0, 6.0, S, u)
         O.adam_step(p, gr, m, v, step + 1)
-    ref_img = O.render_image(p, H, W, focal, poses[held], n_samples=S)
-    our_img = train.render_one(model, enc, H, W, focal, poses[held], dev, n_samples=S).cpu()
-    assert tr.applied_steps() == K                              # the loss scaler never had to skip a step
-    return O.mse2psnr(((ref_img - images[held]) ** 2).mean()).item(), O.mse2psnr(((our_img - images[held]) ** 2).mean()).item()
+        if step + 1 > K - n_eval * eval_every and (K - step - 1) % eval_every == 0:
+            ref_img = O.render_image(p, H, W, focal, poses[held], n_samples=S)
+            our_img = train.render_one(model, enc, H, W, focal, poses[held], dev, n_samples=S).cpu()
+            mse_ref.append(((ref_img - images[held]) ** 2).mean()); mse_our.append(((our_img - images[held]) ** 2).mean())
+    assert tr.applied_steps() == K and len(mse_ref) == n_eval   # the loss scaler never had to skip a step
+    return O.mse2psnr(torch.stack(mse_ref).mean()).item(), O.mse2psnr(torch.stack(mse_our).mean()).item()
 
 
 @pytest.mark.parametrize("prec,seeds,K", [("f32", (7, 8), 300), ("f16", (7, 8, 9, 10, 11), 300)])

@@ -31,7 +31,7 @@ constexpr uint32_t S_X0 = 200704, S_X1 = 208896, S_DZH0 = 217088, S_DZH1 = 21913
 
 struct Misc {
     float xch[2][48];          // cross-warp carries of the compositing scans (a ray spans 2 warps at 64 samples, all 4 at 128)
-    uint64_t bar_w, bar_x[2], bar_in[2], bar_d[2], bar_head[2], bar_dzh[2], bar_g[2][2], bar_gfree[2], bar_xfree[2], bar_wg[2], bar_dread[2], bar_in2[2];
+    uint64_t bar_w, bar_x[2], bar_in[2], bar_d[2], bar_head[2], bar_dzh[2], bar_g[2][2], bar_gfree[2], bar_xfree[2], bar_wg[2], bar_dread[2], bar_in2[2], bar_xq[2], bar_qfree[2];
     uint32_t tmem_slot;
 };
 
@@ -98,34 +98,68 @@ __device__ __forceinline__ void drain_store(uint8_t* slot, int f, const uint32_t
         *reinterpret_cast<uint4*>(slot + ((size_t)(c * 128 + f) << 4)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
 }
 
+// five / two shuffles of one scan level issued back to back into DISTINCT registers: written as separate __shfl_up_sync calls the
+// register allocator funnelled them through one register (shuffle, consume, shuffle, ...), five dependent shuffle latencies per level
+__device__ __forceinline__ void shfl_up5(float (&o)[5], float i0, float i1, float i2, float i3, float i4, int off, int width) {
+    const int c = (32 - width) << 8;
+    asm volatile("shfl.sync.up.b32 %0, %5, %10, %11, 0xffffffff;\n\tshfl.sync.up.b32 %1, %6, %10, %11, 0xffffffff;\n\t"
+                 "shfl.sync.up.b32 %2, %7, %10, %11, 0xffffffff;\n\tshfl.sync.up.b32 %3, %8, %10, %11, 0xffffffff;\n\t"
+                 "shfl.sync.up.b32 %4, %9, %10, %11, 0xffffffff;"
+                 : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]) : "f"(i0), "f"(i1), "f"(i2), "f"(i3), "f"(i4), "r"(off), "r"(c));
+}
+__device__ __forceinline__ void shfl_down2(float (&o)[2], float i0, float i1, int off, int width) {
+    const int c = ((32 - width) << 8) | 0x1f;
+    asm volatile("shfl.sync.down.b32 %0, %2, %4, %5, 0xffffffff;\n\tshfl.sync.down.b32 %1, %3, %4, %5, 0xffffffff;"
+                 : "=f"(o[0]), "=f"(o[1]) : "f"(i0), "f"(i1), "r"(off), "r"(c));
+}
+
+// ---- MMA issue: the tile program of ONE stream as fourteen numbered operations (wait for the operands, issue, commit) ----
+// The whole warp runs this code with warp-uniform values; one elected lane issues (operands stay in uniform registers).
+// Descriptors are rebuilt from an opaque copy of the base every tile: hoisted out of the loop they would occupy ~100 registers,
+// rebuilt they are one uniform add each.  Two ways to run it:
+//   * one issuer warp per stream (streams half a tile apart, TNERF_TRAIN_SYNC=0): each warp loops over its own operations;
+//   * ONE warp for both streams (streams in phase, the default): operation k of stream 0, then operation k of stream 1.  With two
+//     issuer warps the tensor pipe alternates between their instructions, both batches of a step complete together at TWICE the
+//     batch time, both accumulators are drained together and the next step collides again -- a self-sustaining lock step.  Issued
+//     batch after batch, stream 0's accumulator is complete one batch time before stream 1's, its drain and its next batch start that
+//     much earlier, and from then on every batch has the pipe to itself (the streams stay one batch apart).
+constexpr int N_OPS = 14;
 template <int KX, int SS>
-__device__ __forceinline__ void issuer_loop(Misc& ms, uint32_t sbase, uint32_t tmem, int s_rt, long long n_tiles_mine, long long* dbg) {
-    const int s = SS >= 0 ? SS : s_rt;
-    int dbg_n = 0;
-    constexpr int XS = KX / 16;
-    const uint32_t bar_x = smem_u32(&ms.bar_x[s]), bar_in = smem_u32(&ms.bar_in[s]), bar_d = smem_u32(&ms.bar_d[s]);
-    const uint32_t bar_head = smem_u32(&ms.bar_head[s]), bar_dzh = smem_u32(&ms.bar_dzh[s]), bar_gfree = smem_u32(&ms.bar_gfree[s]);
-    const uint32_t bar_g0 = smem_u32(&ms.bar_g[s][0]), bar_g1 = smem_u32(&ms.bar_g[s][1]), bar_xfree = smem_u32(&ms.bar_xfree[s]);
-    const uint32_t bar_wg = smem_u32(&ms.bar_wg[s]), bar_dread = smem_u32(&ms.bar_dread[s]), bar_in2 = smem_u32(&ms.bar_in2[s]);
-    // ONE body serves both streams (the kernel's hot code must stay close to the instruction-cache size): the stream only enters
-    // through four per-stream bases, everything else is an immediate
-    constexpr uint32_t P = S_P0, Q = S_Q0, X = S_X0, DZH = S_DZH0;   // byte offsets of stream 0
+struct StreamIssuer {
+    static constexpr int XS = KX / 16;
+    static constexpr uint32_t P = S_P0, Q = S_Q0, X = S_X0, DZH = S_DZH0;   // byte offsets of stream 0; the stream enters through the bases
     static_assert(S_P1 - S_P0 == 32768 && S_Q1 - S_Q0 == 32768 && S_X1 - S_X0 == 8192 && S_DZH1 - S_DZH0 == 2048, "stream strides");
-    const uint32_t D = tmem + C_D + 64 * s;
-    const uint32_t i64kk = make_idesc_f16(128, 64, 0, 0), i64kt = make_idesc_f16(128, 64, 0, 1), i64tk = make_idesc_f16(128, 64, 1, 0),
-                   i64tt = make_idesc_f16(128, 64, 1, 1), i16tk = make_idesc_f16(128, 16, 1, 0), i16kt = make_idesc_f16(128, 16, 0, 1),
-                   i128kk = make_idesc_f16(128, 128, 0, 0), iXkt = make_idesc_f16(128, KX, 0, 1);
-    uint32_t ph_x = 0, ph_in = 0, ph_dzh = 0, ph_gf = 0, ph_dr = 0, ph_in2 = 0;
-#define T2_WAIT(bar, ph) do { T2_STAMP(); mbar_wait(bar, ph); ph ^= 1; tc_fence_after(); T2_STAMP(); } while (0)
-    // the whole warp runs this loop with warp-uniform values; one elected lane issues (operands stay in uniform registers)
+    enum { PH_X = 1, PH_IN = 2, PH_DZH = 4, PH_GF = 8, PH_DR = 16, PH_IN2 = 32, PH_XQ = 64 };
+    uint32_t mb, tmem, ph = 0;      // shared-memory address of Misc, tensor-memory base, phase bits of the barriers this warp waits on
+    long long* dbg;
+    int dbg_n = 0;
+    __device__ __forceinline__ StreamIssuer(Misc& ms, uint32_t tmem_, long long* dbg_) : mb(smem_u32(&ms)), tmem(tmem_), dbg(dbg_) {}
+#define T2_BAR(field) (mb + (uint32_t)offsetof(Misc, field) + 8u * SS)
+    __device__ __forceinline__ void wait(uint32_t bar, uint32_t bit) {
+        T2_STAMP();
+        mbar_wait(bar, (ph & bit) ? 1u : 0u);
+        ph ^= bit;
+        tc_fence_after();
+        T2_STAMP();
+    }
 #define T2_ISSUE(...) do { if (elect_one()) { __VA_ARGS__ } __syncwarp(); } while (0)
-    mbar_wait(smem_u32(&ms.bar_w), 0);
-    for (long long t = 0; t < n_tiles_mine; ++t) {
-        // descriptors are rebuilt from an opaque copy of the base every tile: hoisted out of the loop they would
-        // occupy ~100 registers, rebuilt they are one uniform add each
-        uint32_t sb = sbase >> 4;
-        asm volatile("" : "+r"(sb));
-        const uint32_t sbA = sb + s * (32768u >> 4), sbX = sb + s * (8192u >> 4), sbZ = sb + s * (2048u >> 4), sbH = sb + s * (16384u >> 4);
+    // layer 0 of a tile is issued EARLY, at the end of the previous tile (the first one from here): the encoding buffer X is single
+    // and stays busy until the tile's last GEMM (dW0), so the sample warps stage a second copy of the next tile's features in the Q
+    // slot as soon as its last reader (dH0) has completed; F0 reads that copy while the drain threads still store dZ0 and dW0 runs.
+    // The regular X buffer is refilled after dW0 and is first needed by layer 2.
+    __device__ __forceinline__ void first(uint32_t sb, long long n) {
+        if (n <= 0) return;
+        const uint32_t D = tmem + C_D + 64 * SS;
+        wait(T2_BAR(bar_xq), PH_XQ);
+        T2_ISSUE(gemm<XS>(D, kmaj(sb, S_W0, 128), kmaj(sb + SS * (32768u >> 4), Q, 64), make_idesc_f16(128, 64, 0, 0), 0); tc_commit(T2_BAR(bar_d)););
+    }
+    template <int OP>
+    __device__ __forceinline__ void op(uint32_t sb, long long t, long long n) {
+        constexpr uint32_t i64kk = make_idesc_f16(128, 64, 0, 0), i64kt = make_idesc_f16(128, 64, 0, 1), i64tk = make_idesc_f16(128, 64, 1, 0),
+                           i64tt = make_idesc_f16(128, 64, 1, 1), i16tk = make_idesc_f16(128, 16, 1, 0), i16kt = make_idesc_f16(128, 16, 0, 1),
+                           i128kk = make_idesc_f16(128, 128, 0, 0), iXkt = make_idesc_f16(128, KX, 0, 1);
+        const uint32_t D = tmem + C_D + 64 * SS;
+        const uint32_t sbA = sb + SS * (32768u >> 4), sbX = sb + SS * (8192u >> 4), sbZ = sb + SS * (2048u >> 4), sbH = sb + SS * (16384u >> 4);
         // operands (descriptor words); weights are rows = output features
         const Op aW0 = kmaj(sb, S_W0, 128), aW1 = kmaj(sb, S_W1, 128), aW2h = kmaj(sb, S_W2, 128),
                  aW2x = kmaj(sb, S_W2 + 32768, 128), aW3 = kmaj(sb, S_W3, 128);
@@ -139,45 +173,100 @@ __device__ __forceinline__ void issuer_loop(Misc& ms, uint32_t sbase, uint32_t t
         // land on accumulator lanes 64 s .. 64 s + 63 (stream 1 starts one slot early), the other rows are ignored
         const Op aQhead = mnmaj(sbH, Q, 128);                        // stream 1: Q1 - 16384 = Q0 + 16384
         const Op bDZHt = mnmaj(sbZ, DZH, 64), bDZHk = kmaj(sbZ, DZH, 64);
-        T2_WAIT(bar_x, ph_x);
-        T2_ISSUE(gemm<XS>(D, aW0, bXk, i64kk, 0); tc_commit(bar_d););                                   // F0: H0
-        T2_WAIT(bar_in, ph_in);
-        T2_ISSUE(gemm<8>(D, aW1, bP, i64kt, 0); tc_commit(bar_d););                                     // F1: H1
-        T2_WAIT(bar_in, ph_in);
-        T2_ISSUE(gemm<8>(D, aW2h, bQ, i64kt, 0); gemm<XS>(D, aW2x, bXk, i64kk, 1); tc_commit(bar_d););  // F2: H2
-        T2_WAIT(bar_in, ph_in);
-        T2_ISSUE(gemm<8>(D, aW3, bP, i64kt, 0); tc_commit(bar_d););                                     // F3: H3
-        T2_WAIT(bar_in, ph_in);
-        T2_ISSUE(gemm<8>(D, aQhead, bWH, i16tk, 0); tc_commit(bar_head););                              // heads (samples on lanes)
-        T2_WAIT(bar_dzh, ph_dzh);
-        T2_ISSUE(gemm<4>(D + 16, aQ, bDZHt, i16kt, 0); tc_commit(bar_d););                              // head wgrad: H3 . dZh
-        T2_WAIT(bar_in, ph_in);
-        T2_ISSUE(gemm<1>(D, aWHt, bDZHk, i64tk, 0); tc_commit(bar_d););                                 // head dgrad -> dH3
-        T2_WAIT(bar_in, ph_in);
-        // layers 3 and 2: dgrad first on its own barrier, the wgrad GEMMs behind it -- the drain threads turn dH into the
-        // packed dZ row while the wgrad still reads the slot, and store once the wgrad has committed
-        T2_ISSUE(gemm<8>(D, aW3t, bQ, i64tt, 0); tc_commit(bar_d);                                      // dH2
-                 gemm<4>(tmem + C_DW3, aQ, aP, i128kk, 1); tc_commit(bar_wg););                         // dW3 += dZ3 . H2^T
-        T2_WAIT(bar_in, ph_in);
-        T2_ISSUE(gemm<8>(D, aW2t, bP, i64tt, 0); tc_commit(bar_d);                                      // dH1
-                 gemm<4>(tmem + C_DW2, aP, aQ, i128kk, 1);                                              // dW2[:, :128] += dZ2 . H1^T
-                 gemm<4>(tmem + C_DW2 + 128, aP, bXt, iXkt, 1); tc_commit(bar_wg););                    // dW2[:, 128:] += dZ2 . X^T
-        T2_WAIT(bar_dread, ph_dr);                                                                      // dH1 has been read out
-        T2_ISSUE(gemm<XS>(D, aW0, bXk, i64kk, 0); tc_commit(bar_d););                                   // recompute H0 under the dZ1 drain
-        // "dZ1 stored" has its own barrier: with the H0 recompute already in flight the drain threads can complete this phase AND
-        // the next one (H0 stored) before this warp looks -- two unobserved phases of ONE mbarrier alias to "not complete" (deadlock)
-        T2_WAIT(bar_in2, ph_in2);                                                                       // dZ1 stored
-        T2_WAIT(bar_in, ph_in);
-        T2_ISSUE(gemm<4>(D, aQ, bP_lo, i64kk, 0); tc_commit(bar_g0););                                  // dW1[:, :64] partial
-        T2_WAIT(bar_gfree, ph_gf);
-        T2_ISSUE(gemm<4>(D, aQ, bP_hi, i64kk, 0); tc_commit(bar_g1););                                  // dW1[:, 64:] partial
-        T2_WAIT(bar_gfree, ph_gf);
-        T2_ISSUE(gemm<8>(D, aW1t, bQ, i64tt, 0); tc_commit(bar_d););                                    // dH0
-        T2_WAIT(bar_in, ph_in);
-        T2_ISSUE(gemm<4>(tmem + C_DW0, aP, bXt, iXkt, 1); tc_commit(bar_xfree););                       // dW0 += dZ0 . X^T ; tile done
+        const Op bXq = kmaj(sbA, Q, 64);                             // staged copy of the NEXT tile's features
+        const uint32_t bar_in = T2_BAR(bar_in), bar_d = T2_BAR(bar_d), bar_wg = T2_BAR(bar_wg), bar_gfree = T2_BAR(bar_gfree);
+        if constexpr (OP == 0) {            // F1: H1 (F0 was issued early)
+            wait(bar_in, PH_IN);
+            T2_ISSUE(gemm<8>(D, aW1, bP, i64kt, 0); tc_commit(bar_d););
+        } else if constexpr (OP == 1) {     // F2: H2 (needs the refilled X buffer)
+            wait(bar_in, PH_IN);
+            wait(T2_BAR(bar_x), PH_X);
+            T2_ISSUE(gemm<8>(D, aW2h, bQ, i64kt, 0); gemm<XS>(D, aW2x, bXk, i64kk, 1); tc_commit(bar_d););
+        } else if constexpr (OP == 2) {     // F3: H3
+            wait(bar_in, PH_IN);
+            T2_ISSUE(gemm<8>(D, aW3, bP, i64kt, 0); tc_commit(bar_d););
+        } else if constexpr (OP == 3) {     // heads (samples on lanes)
+            wait(bar_in, PH_IN);
+            T2_ISSUE(gemm<8>(D, aQhead, bWH, i16tk, 0); tc_commit(T2_BAR(bar_head)););
+        } else if constexpr (OP == 4) {     // head wgrad: H3 . dZh
+            wait(T2_BAR(bar_dzh), PH_DZH);
+            T2_ISSUE(gemm<4>(D + 16, aQ, bDZHt, i16kt, 0); tc_commit(bar_d););
+        } else if constexpr (OP == 5) {     // head dgrad -> dH3
+            wait(bar_in, PH_IN);
+            T2_ISSUE(gemm<1>(D, aWHt, bDZHk, i64tk, 0); tc_commit(bar_d););
+        } else if constexpr (OP == 6) {
+            // layers 3 and 2: dgrad first on its own barrier, the wgrad GEMMs behind it -- the drain threads turn dH into the
+            // packed dZ row while the wgrad still reads the slot, and store once the wgrad has committed
+            wait(bar_in, PH_IN);
+            T2_ISSUE(gemm<8>(D, aW3t, bQ, i64tt, 0); tc_commit(bar_d);                                  // dH2
+                     gemm<4>(tmem + C_DW3, aQ, aP, i128kk, 1); tc_commit(bar_wg););                     // dW3 += dZ3 . H2^T
+        } else if constexpr (OP == 7) {
+            wait(bar_in, PH_IN);
+            T2_ISSUE(gemm<8>(D, aW2t, bP, i64tt, 0); tc_commit(bar_d);                                  // dH1
+                     gemm<4>(tmem + C_DW2, aP, aQ, i128kk, 1);                                          // dW2[:, :128] += dZ2 . H1^T
+                     gemm<4>(tmem + C_DW2 + 128, aP, bXt, iXkt, 1); tc_commit(bar_wg););                // dW2[:, 128:] += dZ2 . X^T
+        } else if constexpr (OP == 8) {     // recompute H0 under the dZ1 drain
+            wait(T2_BAR(bar_dread), PH_DR);                                                             // dH1 has been read out
+            T2_ISSUE(gemm<XS>(D, aW0, bXk, i64kk, 0); tc_commit(bar_d););
+        } else if constexpr (OP == 9) {     // dW1[:, :64] partial
+            // "dZ1 stored" has its own barrier: with the H0 recompute already in flight the drain threads can complete this phase AND
+            // the next one (H0 stored) before this warp looks -- two unobserved phases of ONE mbarrier alias to "not complete" (deadlock)
+            wait(T2_BAR(bar_in2), PH_IN2);                                                              // dZ1 stored
+            wait(bar_in, PH_IN);
+            T2_ISSUE(gemm<4>(D, aQ, bP_lo, i64kk, 0); tc_commit(mb + (uint32_t)offsetof(Misc, bar_g) + 16u * SS););
+        } else if constexpr (OP == 10) {    // dW1[:, 64:] partial
+            wait(bar_gfree, PH_GF);
+            T2_ISSUE(gemm<4>(D, aQ, bP_hi, i64kk, 0); tc_commit(mb + (uint32_t)offsetof(Misc, bar_g) + 16u * SS + 8u););
+        } else if constexpr (OP == 11) {    // dH0; Q is free behind it
+            wait(bar_gfree, PH_GF);
+            T2_ISSUE(gemm<8>(D, aW1t, bQ, i64tt, 0); tc_commit(bar_d); tc_commit(T2_BAR(bar_qfree)););
+        } else if constexpr (OP == 12) {    // F0 of the NEXT tile
+            if (t + 1 < n) {
+                wait(T2_BAR(bar_dread), PH_DR);                                                         // dH0 has been read out
+                wait(T2_BAR(bar_xq), PH_XQ);                                                            // next tile's features staged in Q
+                T2_ISSUE(gemm<XS>(D, aW0, bXq, i64kk, 0); tc_commit(bar_d););
+            }
+        } else {                            // dW0 += dZ0 . X^T ; tile done
+            wait(bar_in, PH_IN);
+            T2_ISSUE(gemm<4>(tmem + C_DW0, aP, bXt, iXkt, 1); tc_commit(T2_BAR(bar_xfree)););
+        }
     }
 #undef T2_ISSUE
-#undef T2_WAIT
+#undef T2_BAR
+};
+template <int OP, int KX, int SS>
+__device__ __forceinline__ void run_ops(StreamIssuer<KX, SS>& a, uint32_t sb, long long t, long long n) {
+    if constexpr (OP < N_OPS) { a.template op<OP>(sb, t, n); run_ops<OP + 1>(a, sb, t, n); }
+}
+template <int OP, int KX>
+__device__ __forceinline__ void run_ops2(StreamIssuer<KX, 0>& a, StreamIssuer<KX, 1>& b, uint32_t sb, long long t, long long n0, long long n1) {
+    if constexpr (OP < N_OPS) {
+        a.template op<OP>(sb, t, n0);
+        if (t < n1) b.template op<OP>(sb, t, n1);
+        run_ops2<OP + 1>(a, b, sb, t, n0, n1);
+    }
+}
+__device__ __forceinline__ uint32_t opaque_base(uint32_t sbase) {
+    uint32_t sb = sbase >> 4;
+    asm volatile("" : "+r"(sb));
+    return sb;
+}
+template <int KX, int SS>
+__device__ __forceinline__ void issuer_loop(Misc& ms, uint32_t sbase, uint32_t tmem, long long n_tiles_mine, long long* dbg) {
+    StreamIssuer<KX, SS> a(ms, tmem, dbg);
+    mbar_wait(smem_u32(&ms.bar_w), 0);
+    a.first(opaque_base(sbase), n_tiles_mine);
+    for (long long t = 0; t < n_tiles_mine; ++t) run_ops<0>(a, opaque_base(sbase), t, n_tiles_mine);
+}
+// both streams from one warp; n0 >= n1 (tiles are dealt round-robin, stream 0 first)
+template <int KX>
+__device__ __forceinline__ void issuer_loop_merged(Misc& ms, uint32_t sbase, uint32_t tmem, long long n0, long long n1, long long* dbg) {
+    StreamIssuer<KX, 0> a(ms, tmem, dbg);
+    StreamIssuer<KX, 1> b(ms, tmem, nullptr);
+    mbar_wait(smem_u32(&ms.bar_w), 0);
+    a.first(opaque_base(sbase), n0);
+    b.first(opaque_base(sbase), n1);
+    for (long long t = 0; t < n0; ++t) run_ops2<0>(a, b, opaque_base(sbase), t, n0, n1);
 }
 
 template <int KX, bool UNROLL>
@@ -204,6 +293,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             mbar_init(smem_u32(&ms.bar_wg[s]), 1);
             mbar_init(smem_u32(&ms.bar_dread[s]), 4);
             mbar_init(smem_u32(&ms.bar_in2[s]), 4);
+            mbar_init(smem_u32(&ms.bar_xq[s]), 2);
+            mbar_init(smem_u32(&ms.bar_qfree[s]), 1);
         }
         fence_barrier_init();
     }
@@ -229,6 +320,12 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // tiles are dealt round-robin over (cta, stream) pairs
+#ifdef T2_SOLO      // experiment: stream 0 alone carries the CTA's tiles (length of one stream's chain without pipe collisions)
+    const long long nstreams = gridDim.x;
+    long long n_my[2];
+    n_my[0] = (blockIdx.x < p.n_tiles) ? (p.n_tiles - blockIdx.x + nstreams - 1) / nstreams : 0;
+    n_my[1] = 0;
+#else
     const long long nstreams = 2LL * gridDim.x;
     long long n_my[2];
 #pragma unroll
@@ -236,6 +333,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         const long long j = 2LL * blockIdx.x + s;
         n_my[s] = (j < p.n_tiles) ? (p.n_tiles - j + nstreams - 1) / nstreams : 0;
     }
+#endif
     float* slab = p.slabs + (size_t)blockIdx.x * p.sm.total;
 
     if (wg == 3) {
@@ -254,13 +352,17 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                 }
             }
         }
-#ifndef T2_ISSUER_SHARED        // one issuer body per stream: every offset is an immediate (3 % faster than one shared body)
-        if (warp == 12) issuer_loop<KX, 0>(ms, sbase, tmem, 0, n_my[0], (p.debug && blockIdx.x == 0 && lane == 0) ? p.debug + 256 : nullptr);
-        if (warp == 13) issuer_loop<KX, 1>(ms, sbase, tmem, 1, n_my[1], nullptr);
+        long long* idbg = (p.debug && blockIdx.x == 0 && lane == 0) ? p.debug + 256 : nullptr;
+#ifdef T2_NO_MERGE
+        if (false) {
 #else
-        if (warp <= 13)
-            issuer_loop<KX, -1>(ms, sbase, tmem, warp - 12, n_my[warp - 12], (p.debug && blockIdx.x == 0 && warp == 12 && lane == 0) ? p.debug + 256 : nullptr);
+        if (UNROLL && (p.S == 128 || p.sync_streams > 0)) {       // streams in phase: one warp issues for both (see StreamIssuer)
 #endif
+            if (warp == 12) issuer_loop_merged<KX>(ms, sbase, tmem, n_my[0], n_my[1], idbg);
+        } else {
+            if (warp == 12) issuer_loop<KX, 0>(ms, sbase, tmem, n_my[0], idbg);
+            if (warp == 13) issuer_loop<KX, 1>(ms, sbase, tmem, n_my[1], nullptr);
+        }
         __syncthreads();                                          // (A)
         __syncthreads();                                          // (B)
     } else if (wg == 2) {
@@ -271,7 +373,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         uint8_t* X = smem + (s ? S_X1 : S_X0);
         uint8_t* DZH = smem + (s ? S_DZH1 : S_DZH0);
         const uint32_t bar_x = smem_u32(&ms.bar_x[s]), bar_head = smem_u32(&ms.bar_head[s]), bar_dzh = smem_u32(&ms.bar_dzh[s]),
-                       bar_xfree = smem_u32(&ms.bar_xfree[s]);
+                       bar_xfree = smem_u32(&ms.bar_xfree[s]), bar_xq = smem_u32(&ms.bar_xq[s]), bar_qfree = smem_u32(&ms.bar_qfree[s]);
+        uint8_t* XQ = smem + (s ? S_Q1 : S_Q0);              // early copy of the next tile's features (layer 0 is issued ahead)
         // n_samples = 128 ("in-phase" mode): the two streams of the CTA carry the two halves of ONE ray, the four sample warps
         // composite it together (chain of four 32-sample chunks); otherwise a ray lives inside one stream's tile
         const bool inphase = p.S == 128;
@@ -286,7 +389,11 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         const float bs = p.b_sigma[0], br = p.b_rgb[0], bg = p.b_rgb[1], bb = p.b_rgb[2];
         float hb[4] = {0.f, 0.f, 0.f, 0.f}, loss_acc = 0.f;
         bool overflow = false;          // a scaled head gradient left the fp16-safe range (or is not finite): GradScaler's found_inf
+#ifdef T2_SOLO
+        const long long j0 = blockIdx.x;
+#else
         const long long j0 = 2LL * blockIdx.x + s;
+#endif
         const int S = p.S, W = S < 32 ? S : 32, sl = lane & (W - 1);
         const bool camera = p.rs.rays_d == nullptr;
         uint32_t pk[KX / 2];
@@ -347,15 +454,15 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             z_out = z; gap_out = gd;
             if (p.include_input) encode_stream<KX, true>(pt, p.L, pk); else encode_stream<KX, false>(pt, p.L, pk);
         };
-        auto store_x = [&]() {
+        auto store_x = [&](uint8_t* dst, uint32_t bar) {
 #pragma unroll
             for (int c = 0; c < KX / 8; ++c)
-                *reinterpret_cast<uint4*>(X + ((size_t)(c * 64 + i) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                *reinterpret_cast<uint4*>(dst + ((size_t)(c * 64 + i) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_x);
+            if (lane == 0) mbar_arrive(bar);
         };
-        uint32_t ph_head = 0, ph_xfree = 0;
+        uint32_t ph_head = 0, ph_xfree = 0, ph_qfree = 0;
         float z_cur = 0.f, gap_cur = 0.f;
         long long* dbg = (p.debug && blockIdx.x == 0 && warp == 8 && lane == 0) ? p.debug + 512 : nullptr;
         int dbg_n = 0;
@@ -396,9 +503,9 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             //      (src/volume.py:18-44 and its backward).  The body is specialised on the number of
             //      samples per ray (64 and 128 at compile time: no width tests around the shuffles, unrolled chunk stitching);
             //      other counts take the generic instance.
-            //      Forward: ONE inclusive scan of the per-sample maps (T, C) -> (T q, C + T alpha c) gives the transmittance in
-            //      front of every sample and, in the segment's last lane, the four ray sums (colour, opacity) -- five shuffle
-            //      levels instead of five for the product scan plus five for the sums.
+            //      Forward, generic instance: ONE inclusive scan of the per-sample maps (T, C) -> (T q, C + T alpha c) gives the
+            //      transmittance in front of every sample and, in the segment's last lane, the four ray sums (colour, opacity).
+            //      64 / 128 samples: product scan of q + one integer REDUX per ray sum (see below).
             //      Reverse: suffix composition of R -> g alpha + q R (division-free). ----
             T2_STAMP();                                              // heads read and activated
             auto composite = [&](auto SC) __attribute__((always_inline)) {
@@ -409,21 +516,44 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                 const float e = valid ? __expf(-own.x * gap_cur) : 1.f;
                 const float alpha = valid ? 1.f - e : 0.f;
                 const float q = valid ? 1.f - alpha + kEpsT : 1.f;
-                float Qi = q, A0 = alpha * own.y, A1 = alpha * own.z, A2 = alpha * own.w, A3 = alpha;
+                float Qi = q, A0, A1, A2, A3;
+                float excl;
+                if constexpr (SCT >= 32) {
+                    // a warp holds one 32-sample chunk of ONE ray: product scan of q alone (five one-shuffle levels), then the four
+                    // chunk sums of the weights relative to the chunk start as 2^-30 fixed point -- one REDUX each instead of five
+                    // more shuffle levels of four values (terms and sums lie in [0, 1]: exact to 2^-30, below fp32 rounding)
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    if (SCT >= 32 || off < Wc) {
-                        const float qu = __shfl_up_sync(0xffffffffu, Qi, off, Wc);
-                        const float a0 = __shfl_up_sync(0xffffffffu, A0, off, Wc), a1 = __shfl_up_sync(0xffffffffu, A1, off, Wc);
-                        const float a2 = __shfl_up_sync(0xffffffffu, A2, off, Wc), a3 = __shfl_up_sync(0xffffffffu, A3, off, Wc);
-                        if (slc >= off) {      // earlier segment (qu, a) followed by this one: (qu Q, a + qu A)
-                            A0 = fmaf(qu, A0, a0); A1 = fmaf(qu, A1, a1); A2 = fmaf(qu, A2, a2); A3 = fmaf(qu, A3, a3);
-                            Qi *= qu;
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const float qu = __shfl_up_sync(0xffffffffu, Qi, off);
+                        if (lane >= off) Qi *= qu;
+                    }
+                    excl = __shfl_up_sync(0xffffffffu, Qi, 1);
+                    if (lane == 0) excl = 1.f;
+                    const float wl = alpha * excl * 1073741824.f;
+                    const int i0 = __float2int_rn(wl * own.y), i1 = __float2int_rn(wl * own.z), i2 = __float2int_rn(wl * own.w), i3 = __float2int_rn(wl);
+                    A0 = (float)__reduce_add_sync(0xffffffffu, i0) * 9.313225746154785e-10f;
+                    A1 = (float)__reduce_add_sync(0xffffffffu, i1) * 9.313225746154785e-10f;
+                    A2 = (float)__reduce_add_sync(0xffffffffu, i2) * 9.313225746154785e-10f;
+                    A3 = (float)__reduce_add_sync(0xffffffffu, i3) * 9.313225746154785e-10f;
+                    if (__any_sync(0xffffffffu, !(wl * own.y * own.z * own.w == wl * own.y * own.z * own.w)))     // non-finite heads stay visible in the loss
+                        A0 = A1 = A2 = A3 = __int_as_float(0x7fc00000);
+                } else {
+                    A0 = alpha * own.y; A1 = alpha * own.z; A2 = alpha * own.w; A3 = alpha;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        if (off < Wc) {
+                            float up[5];
+                            shfl_up5(up, Qi, A0, A1, A2, A3, off, Wc);
+                            const float qu = up[0], a0 = up[1], a1 = up[2], a2 = up[3], a3 = up[4];
+                            if (slc >= off) {      // earlier segment (qu, a) followed by this one: (qu Q, a + qu A)
+                                A0 = fmaf(qu, A0, a0); A1 = fmaf(qu, A1, a1); A2 = fmaf(qu, A2, a2); A3 = fmaf(qu, A3, a3);
+                                Qi *= qu;
+                            }
                         }
                     }
+                    excl = __shfl_up_sync(0xffffffffu, Qi, 1, Wc);
+                    if (slc == 0) excl = 1.f;
                 }
-                float excl = __shfl_up_sync(0xffffffffu, Qi, 1, Wc);
-                if (slc == 0) excl = 1.f;
                 T2_STAMP();                                          // forward scan done
                 float c0, c1, c2, asum, Tc = 1.f;
                 if (nch > 1) {       // stitch the chunks of the ray: chunk c enters with T = product of the earlier chunks' transmittances
@@ -466,8 +596,9 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) {
                     if (SCT >= 32 || off < Wc) {
-                        const float An = __shfl_down_sync(0xffffffffu, Aa, off, Wc);
-                        const float Qn = __shfl_down_sync(0xffffffffu, Qq, off, Wc);
+                        float dn[2];
+                        shfl_down2(dn, Aa, Qq, off, Wc);
+                        const float An = dn[0], Qn = dn[1];
                         if (slc + off < Wc) { Aa = fmaf(Qq, An, Aa); Qq *= Qn; }
                     }
                 }
@@ -509,10 +640,15 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             if (more) encode(tile + nstreams, z_next, gap_next);
             T2_STAMP();
             if (t >= 0) {
+                mbar_wait(bar_qfree, ph_qfree); ph_qfree ^= 1;   // dH0 has completed: the Q slot is free
+                T2_STAMP();
+            }
+            if (more) store_x(XQ, bar_xq);                       // early copy for layer 0 of the next tile
+            if (t >= 0) {
                 mbar_wait(bar_xfree, ph_xfree); ph_xfree ^= 1;   // last GEMM of the tile has completed: X may be replaced
                 T2_STAMP();
             }
-            if (more) { store_x(); z_cur = z_next; gap_cur = gap_next; }
+            if (more) { store_x(X, bar_x); z_cur = z_next; gap_cur = gap_next; }
         }
         loss_acc = warp_sum(loss_acc);
 #pragma unroll
@@ -537,7 +673,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         const uint32_t D_own = tl + C_D + 64 * s, D_oth = tl + C_D + 64 * (1 - s);
         uint8_t* P = smem + (s ? S_P1 : S_P0);
         uint8_t* Q = smem + (s ? S_Q1 : S_Q0);
-        const uint32_t bar_in = smem_u32(&ms.bar_in[s]), bar_d = smem_u32(&ms.bar_d[s]), bar_wg = smem_u32(&ms.bar_wg[s]), bar_dread = smem_u32(&ms.bar_dread[s]), bar_in2 = smem_u32(&ms.bar_in2[s]);
+        const uint32_t bar_in = smem_u32(&ms.bar_in[s]), bar_d = smem_u32(&ms.bar_d[s]), bar_wg = smem_u32(&ms.bar_wg[s]), bar_dread = smem_u32(&ms.bar_dread[s]), bar_in2 = smem_u32(&ms.bar_in2[s]), bar_xfree = smem_u32(&ms.bar_xfree[s]);
         const uint32_t bar_g_own = smem_u32(&ms.bar_g[s][s]), bar_g_oth = smem_u32(&ms.bar_g[1 - s][s]);
         const uint32_t bar_gfree_own = smem_u32(&ms.bar_gfree[s]), bar_gfree_oth = smem_u32(&ms.bar_gfree[1 - s]);
         float dw1[64];                  // dW1[f][64 s + j]: this warpgroup's half of the columns, BOTH streams
@@ -549,7 +685,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         uint32_t mk0a = 0u, mk0b = 0u, mk1a = 0u, mk1b = 0u, mk2a = 0u, mk2b = 0u, mk3a = 0u, mk3b = 0u;   // ReLU masks of H0 (recomputed), H1, H2, H3
         float dwh[4] = {0.f, 0.f, 0.f, 0.f}, db1 = 0.f, db3 = 0.f;
         const float b1 = p.b1[f], b3 = p.b3[f];
-        uint32_t ph_d = 0, ph_g_own = 0, ph_g_oth = 0, ph_wg = 0;
+        uint32_t ph_d = 0, ph_g_own = 0, ph_g_oth = 0, ph_wg = 0, ph_xf = 0;
         long long g_oth_left = n_my[1 - s];
         const bool inphase = p.S == 128 || p.sync_streams > 0;
         long long* dbg = (p.debug && blockIdx.x == 0 && (warp & 3) == 0 && lane == 0) ? p.debug + (s ? 768 : 0) : nullptr;
@@ -623,13 +759,14 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                     const float bias = (step == 1) ? b1 : b3;
                     const bool park = step == 1;
                     uint32_t va[2][32];
-                    uint32_t mk[2] = {0u, 0u};
+                    uint32_t o[32];
                     tmem_ld32(D_own, va[0]);
                     tc_wait_ld();
                     tmem_ld32(D_own + 32, va[1]);
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         if (c == 1) tc_wait_ld();
+                        else if (step == 0 && t > 0) { mbar_wait(bar_xfree, ph_xf); ph_xf ^= 1; }   // layer 0 ran ahead: dW0 of the previous tile still read P
                         uint32_t (&v)[32] = va[c];
                         if (biased) {
 #pragma unroll
@@ -637,20 +774,30 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            uint4 o;
-                            o.x = pack_relu_h2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-                            o.y = pack_relu_h2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-                            o.z = pack_relu_h2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-                            o.w = pack_relu_h2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-                            *reinterpret_cast<uint4*>(slot + ((size_t)((c * 4 + j) * 128 + f) << 4)) = o;
-                            if (step != 0)        // the first H0 is recomputed before its mask is needed
-                                mk[c] = mask_collect(mask_collect(mask_collect(mask_collect(mk[c], o.x, 4 * j), o.y, 4 * j + 1), o.z, 4 * j + 2), o.w, 4 * j + 3);
-                            if (park) { stash[(c * 4 + j) * 4 + 0] = o.x; stash[(c * 4 + j) * 4 + 1] = o.y; stash[(c * 4 + j) * 4 + 2] = o.z; stash[(c * 4 + j) * 4 + 3] = o.w; }
+                            const int w = (c * 4 + j) * 4;
+                            o[w + 0] = pack_relu_h2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                            o[w + 1] = pack_relu_h2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                            o[w + 2] = pack_relu_h2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                            o[w + 3] = pack_relu_h2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                            *reinterpret_cast<uint4*>(slot + ((size_t)((c * 4 + j) * 128 + f) << 4)) = make_uint4(o[w], o[w + 1], o[w + 2], o[w + 3]);
                         }
                     }
-                    if (step == 1) { mk1a = mk[0]; mk1b = mk[1]; } else if (step == 2) { mk2a = mk[0]; mk2b = mk[1]; }
-                    else if (step == 3) { mk3a = mk[0]; mk3b = mk[1]; } else if (step == 9) { mk0a = mk[0]; mk0b = mk[1]; }
                     T2_SIGNAL(bar_in);
+                    // bookkeeping AFTER the hand-off (off the tile's serial chain, under the next GEMM): ReLU masks, parked copy
+                    if (step != 0) {          // the first H0 is recomputed before its mask is needed
+                        uint32_t mk[2] = {0u, 0u};
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) mk[c] = mask_collect(mk[c], o[c * 16 + k], k);
+                        asm volatile("" : "+r"(mk[0]), "+r"(mk[1]));     // pin: sunk to its use half a tile later, the packed row stays live (spills)
+                        if (step == 1) { mk1a = mk[0]; mk1b = mk[1]; } else if (step == 2) { mk2a = mk[0]; mk2b = mk[1]; }
+                        else if (step == 3) { mk3a = mk[0]; mk3b = mk[1]; } else if (step == 9) { mk0a = mk[0]; mk0b = mk[1]; }
+                    }
+                    if (park) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) stash[i] = o[i];
+                    }
                 } else if (kind == K_SMALL) {
                     uint32_t v[4];
                     tmem_ld4(D_own + 16, v);
@@ -664,17 +811,18 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                     uint32_t o[32];
                     const uint32_t ma = step == 6 ? mk3a : step == 7 ? mk2a : step == 8 ? mk1a : mk0a;
                     const uint32_t mb = step == 6 ? mk3b : step == 7 ? mk2b : step == 8 ? mk1b : mk0b;
-                    drain_bwd_compute(D_own, ma, mb, o, step == 8 ? bar_dread : 0u);
-                    if (step == 6 || step == 8) {                     // bias gradient of layer 3 / 1 = row sum of dZ3 / dZ1
-                        float sum = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) sum += (h2sum(o[i]) + h2sum(o[i + 1])) + (h2sum(o[i + 2]) + h2sum(o[i + 3]));
-                        if (step == 6) db3 += sum; else db1 += sum;
-                    }
+                    drain_bwd_compute(D_own, ma, mb, o, (step == 8 || step == 11) ? bar_dread : 0u);
                     if (step == 7 || step == 8) { T2_STAMP(); mbar_wait(bar_wg, ph_wg); ph_wg ^= 1; T2_STAMP(); }
                     drain_store(slot, f, o);
                     if (step == 7) drain_store(Q, f, stash);                                         // H1 back into Q (dZ3 is dead)
                     T2_SIGNAL(step == 8 ? bar_in2 : bar_in);
+                    if (step == 6 || step == 8) {                     // bias gradient of layer 3 / 1 = row sum of dZ3 / dZ1 (after the hand-off)
+                        float sum = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) sum += (h2sum(o[i]) + h2sum(o[i + 1])) + (h2sum(o[i + 2]) + h2sum(o[i + 3]));
+                        asm volatile("" : "+f"(sum));
+                        if (step == 6) db3 += sum; else db1 += sum;
+                    }
                 }
                 return 0;
         };
