@@ -236,7 +236,10 @@ struct StreamIssuer {
 };
 template <int OP, int KX, int SS>
 __device__ __forceinline__ void run_ops(StreamIssuer<KX, SS>& a, uint32_t sb, long long t, long long n) {
-    if constexpr (OP < N_OPS) { a.template op<OP>(sb, t, n); run_ops<OP + 1>(a, sb, t, n); }
+    if constexpr (OP < N_OPS) {
+        a.template op<OP>(sb, t, n);
+        run_ops<OP + 1>(a, sb, t, n);
+    }
 }
 template <int OP, int KX>
 __device__ __forceinline__ void run_ops2(StreamIssuer<KX, 0>& a, StreamIssuer<KX, 1>& b, uint32_t sb, long long t, long long n0, long long n1) {
