@@ -391,7 +391,28 @@ def reference_arm(args, rank, world):
             "cpu_baseline": {"value": value, "unit": unit, "cores": arm.cores, "kind": arm.kind, "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     line.update(extra)
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """stdout carries ONE JSON line: libraries that write to file descriptor 1 (NCCL prints its version banner there on some boxes)
+    are pointed at stderr for the duration of the run; emit() writes the line to the real stdout."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.write(_STDOUT_FD, (json.dumps(line) + "\n").encode())
+    else:
+        emit(line)
 
 
 def cpu_baseline(args):
@@ -417,6 +438,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ddp-check", action="store_true")
     args = resolve(ap.parse_args())
+    quiet_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -741,7 +763,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -49,6 +49,47 @@ __global__ void get_rays_kernel(int H, int W, float focal, const float* __restri
     }
 }
 
+// Flat variant (16-byte aligned outputs): thread q writes float4 number q of the flat (n, 3) direction array -- consecutive
+// threads, consecutive 16 bytes, every store instruction of a warp one contiguous 512-byte run (the kernel above writes 16 bytes
+// every 48: each 32-byte sector is touched by two different store instructions).  Four consecutive floats span at most two rays; both
+// are evaluated (same operations in the same order as above: identical bits).
+__global__ void get_rays_flat_kernel(int H, int W, float focal, const float* __restrict__ c2w, long long first,
+                                     long long n, float* __restrict__ ro, float* __restrict__ rd) {
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long f0 = 4 * q, total = 3 * n;
+    if (f0 >= total) return;
+    const long long ray0 = f0 / 3;
+    const int c0 = (int)(f0 - 3 * ray0);
+    const long long k0 = first + ray0;
+    int row = (int)(k0 / W), col = (int)(k0 - (long long)row * W);
+    float d[6];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float cx = __fdiv_rn((float)col - (float)W * 0.5f, focal);
+        const float cy = -__fdiv_rn((float)row - (float)H * 0.5f, focal);
+        const float wx = fmaf(-1.f, c2w[2], fmaf(cy, c2w[1], cx * c2w[0]));
+        const float wy = fmaf(-1.f, c2w[6], fmaf(cy, c2w[5], cx * c2w[4]));
+        const float wz = fmaf(-1.f, c2w[10], fmaf(cy, c2w[9], cx * c2w[8]));
+        const float nn = fmaxf(sqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx))), 1e-12f);
+        d[3 * j] = __fdiv_rn(wx, nn); d[3 * j + 1] = __fdiv_rn(wy, nn); d[3 * j + 2] = __fdiv_rn(wz, nn);
+        if (++col == W) { col = 0; ++row; }
+    }
+    const float o3[3] = {c2w[3], c2w[7], c2w[11]};
+    float v[4], w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c0 + j;                   // 0 .. 5: component c of ray0, or component c - 3 of the next ray
+        v[j] = c == 0 ? d[0] : c == 1 ? d[1] : c == 2 ? d[2] : c == 3 ? d[3] : c == 4 ? d[4] : d[5];
+        w[j] = o3[c >= 3 ? c - 3 : c];
+    }
+    if (f0 + 4 <= total) {
+        *reinterpret_cast<float4*>(rd + f0) = make_float4(v[0], v[1], v[2], v[3]);
+        if (ro) *reinterpret_cast<float4*>(ro + f0) = make_float4(w[0], w[1], w[2], w[3]);
+    } else {
+        for (int j = 0; f0 + j < total; ++j) { rd[f0 + j] = v[j]; if (ro) ro[f0 + j] = w[j]; }
+    }
+}
+
 // a2 gather (src/train.py:110-112)
 __global__ void gather3_kernel(const long long* __restrict__ idx, long long n, long long n_src,
                                const float* __restrict__ sa, float* __restrict__ da,
@@ -138,24 +179,43 @@ int launch_jitter_fill(unsigned long long seed, unsigned long long step, long lo
     return count_launch();
 }
 
-// a4 PositionalEncoding (src/encoding.py:26-33): 12 B in + 4 D B out per point.  One thread per (point, octave, axis): ONE
-// sincosf serves the sine and the cosine column (a thread per output element evaluated every argument twice and paid two
-// 64-bit divisions); a warp covers one point's row, so its stores fall into the same few 128-byte lines.
-template <typename IDX>
-__global__ void posenc_kernel(const float* __restrict__ x, long long n, int L, int inc, float* __restrict__ out) {
-    const int D = 6 * L + (inc ? 3 : 0), items = 3 * L + (inc ? 3 : 0), base = inc ? 3 : 0;
-    const IDX t = (IDX)blockIdx.x * (IDX)blockDim.x + (IDX)threadIdx.x;
-    if ((long long)t >= n * items) return;
-    const IDX p = t / (IDX)items;
-    int c = (int)(t - p * (IDX)items);
-    float* o = out + (long long)p * D;
-    if (inc && c < 3) { o[c] = x[3 * (long long)p + c]; return; }
-    c -= base;
-    const int k = c / 3, axis = c - 3 * k;
-    float sv, cv;
-    sincosf(x[3 * (long long)p + axis] * (float)(1 << k), &sv, &cv);   // exact power-of-two scaling
-    o[base + 6 * k + axis] = sv;
-    o[base + 6 * k + 3 + axis] = cv;
+// a4 PositionalEncoding (src/encoding.py:26-33): 12 B in + 4 D B out per point.  A thread owns one (point, axis): ONE double-precision
+// sincos of x, then every octave by the double-angle recurrence s' = 2 s c, c' = 1 - 2 s^2 IN FP64 (x 2^k is exact in fp32, so the
+// reference evaluates sin / cos of exactly 2^k x; the recurrence doubles the absolute error per octave: 2^L x 1e-16, far below the fp32
+// rounding of the result).  Three FP64 instructions and two conversions per octave instead of a sincosf (~45 instructions): the kernel
+// was bound by those, at 29 % of the copy bandwidth.  The block's rows are assembled in shared memory and leave as one contiguous,
+// 16-byte-vectorised stream (a thread's own outputs are 12 bytes apart in 252-byte rows).
+constexpr int PE_POINTS = 64;        // points per block (192 threads)
+__global__ void __launch_bounds__(3 * PE_POINTS) posenc_kernel(const float* __restrict__ x, long long n, int L, int inc, float* __restrict__ out) {
+    extern __shared__ float pe_tile[];                       // PE_POINTS rows of D floats
+    const int D = 6 * L + (inc ? 3 : 0), base = inc ? 3 : 0;
+    const long long p0 = (long long)blockIdx.x * PE_POINTS;
+    const int t = threadIdx.x, pl = t / 3, axis = t - 3 * pl;
+    const long long np = (n - p0 < PE_POINTS) ? (n - p0) : PE_POINTS;
+    if (pl < np) {
+        const float xv = x[3 * p0 + t];
+        float* row = pe_tile + pl * D;
+        if (inc) row[axis] = xv;
+        double sv, cv;
+        sincos((double)xv, &sv, &cv);
+        for (int k = 0; k < L; ++k) {
+            row[base + 6 * k + axis] = (float)sv;
+            row[base + 6 * k + 3 + axis] = (float)cv;
+            const double s2 = 2.0 * sv;
+            sv = s2 * cv;                    // sin 2a = 2 sin a cos a  (uses the old cosine)
+            cv = fma(-s2, 0.5 * s2, 1.0);    // cos 2a = 1 - 2 sin^2 a
+        }
+    }
+    __syncthreads();
+    float* o = out + p0 * D;
+    const int total = (int)np * D;
+    if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+        const int nv = total >> 2;
+        for (int i = t; i < nv; i += 3 * PE_POINTS) reinterpret_cast<float4*>(o)[i] = reinterpret_cast<const float4*>(pe_tile)[i];
+        for (int i = (nv << 2) + t; i < total; i += 3 * PE_POINTS) o[i] = pe_tile[i];
+    } else {
+        for (int i = t; i < total; i += 3 * PE_POINTS) o[i] = pe_tile[i];
+    }
 }
 
 __global__ void posenc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, long long n, int L,
@@ -167,11 +227,14 @@ __global__ void posenc_bwd_kernel(const float* __restrict__ x, const float* __re
     const float xv = x[t];
     const float* gp = g + p * D;
     float acc = inc ? gp[axis] : 0.f;
+    double sv, cv;                         // octaves by the FP64 double-angle recurrence (see posenc_kernel)
+    sincos((double)xv, &sv, &cv);
     for (int k = 0; k < L; ++k) {
         const float f = (float)(1 << k);
-        float s, c;
-        sincosf(xv * f, &s, &c);
-        acc += f * (gp[base + 6 * k + axis] * c - gp[base + 6 * k + 3 + axis] * s);
+        acc += f * (gp[base + 6 * k + axis] * (float)cv - gp[base + 6 * k + 3 + axis] * (float)sv);
+        const double s2 = 2.0 * sv;
+        sv = s2 * cv;
+        cv = fma(-s2, 0.5 * s2, 1.0);
     }
     gx[t] = acc;
 }
@@ -334,8 +397,73 @@ __global__ void composite_fwd_kernel(const float* __restrict__ rgb, const float*
 
 // backward: g_i = gC.c_i - [white] sum(gC) + gD z_i + gA + gW_i;
 // dL/dalpha_i = T_i (g_i - R_i), R_{i-1} = g_i alpha_i + q_i R_i, R_{S-1} = 0; dL/dsigma = dL/dalpha * gap * exp(-sigma gap).
-// The recurrence is an affine map per sample; chunks of 32 are scanned with shuffles from the far end.
-__global__ void composite_bwd_kernel(const float* __restrict__ rgb, const float* __restrict__ sigma,
+// The recurrence is an affine map per sample; chunks of 32 are scanned with shuffles from the far end (composite_bwd_reg_kernel).
+
+// Register-resident variants for n_samples <= 32 NCH (NCH = 1, 2, 4, 8): a warp loads ALL of its ray's samples up front
+// (every load of the ray is in flight at once -- the looped kernels above issue one chunk's loads, scan, then the next chunk's, and
+// the backward reads depths and densities twice) and runs the chunk scans from registers.  Same arithmetic, same order of operations.
+template <int NCH>
+__global__ void __launch_bounds__(256) composite_fwd_reg_kernel(const float* __restrict__ rgb, const float* __restrict__ sigma,
+                                     const float* __restrict__ z, long long z_stride, const float* __restrict__ rd,
+                                     long long n, int S, int white, float* __restrict__ comp, float* __restrict__ depth,
+                                     float* __restrict__ acc_out, float* __restrict__ weights) {
+    const long long ray = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (ray >= n) return;
+    const float* zr = z + ray * z_stride;
+    float zi[NCH], zn[NCH], sg[NCH], c0[NCH], c1[NCH], c2[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        const int i = ch * 32 + lane;
+        zi[ch] = zn[ch] = sg[ch] = c0[ch] = c1[ch] = c2[ch] = 0.f;
+        if (i < S) {
+            zi[ch] = zr[i];
+            if (i + 1 < S) zn[ch] = zr[i + 1];
+            sg[ch] = sigma[ray * S + i];
+            const float* c = rgb + (ray * S + i) * 3;
+            c0[ch] = c[0]; c1[ch] = c[1]; c2[ch] = c[2];
+        }
+    }
+    const float d0 = rd[3 * ray], d1 = rd[3 * ray + 1], d2 = rd[3 * ray + 2];
+    const float dn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+    float T_carry = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, dsum = 0.f, asum = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        const int i = ch * 32 + lane;
+        const bool ok = i < S;
+        float alpha = 0.f, q = 1.f;
+        if (ok) {
+            const float gap = ((i == S - 1) ? kLastDelta : (zn[ch] - zi[ch])) * dn;
+            alpha = 1.f - expf(-sg[ch] * gap);
+            q = 1.f - alpha + kEpsT;
+        }
+        float incl = q;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl *= up;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.f;
+        const float w = alpha * (T_carry * excl);
+        if (ok) {
+            if (weights) weights[ray * S + i] = w;
+            cr += w * c0[ch]; cg += w * c1[ch]; cb += w * c2[ch];
+            dsum += w * zi[ch]; asum += w;
+        }
+        T_carry *= __shfl_sync(0xffffffffu, incl, 31);
+    }
+    cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); dsum = warp_sum(dsum); asum = warp_sum(asum);
+    if (lane == 0) {
+        const float bg = white ? 1.f - asum : 0.f;
+        comp[3 * ray] = cr + bg; comp[3 * ray + 1] = cg + bg; comp[3 * ray + 2] = cb + bg;
+        if (depth) depth[ray] = dsum;
+        if (acc_out) acc_out[ray] = asum;
+    }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(256) composite_bwd_reg_kernel(const float* __restrict__ rgb, const float* __restrict__ sigma,
                                      const float* __restrict__ z, long long z_stride, const float* __restrict__ rd,
                                      long long n, int S, int white, const float* __restrict__ gC,
                                      const float* __restrict__ gD, const float* __restrict__ gA,
@@ -344,21 +472,38 @@ __global__ void composite_bwd_kernel(const float* __restrict__ rgb, const float*
     const int lane = threadIdx.x & 31;
     if (ray >= n) return;
     const float* zr = z + ray * z_stride;
-    const float dn = sqrtf(rd[3 * ray] * rd[3 * ray] + rd[3 * ray + 1] * rd[3 * ray + 1] + rd[3 * ray + 2] * rd[3 * ray + 2]);
-    const float c0 = gC ? gC[3 * ray] : 0.f, c1 = gC ? gC[3 * ray + 1] : 0.f, c2 = gC ? gC[3 * ray + 2] : 0.f;
-    const float gd = gD ? gD[ray] : 0.f, ga = gA ? gA[ray] : 0.f;
-    const float gconst = ga - (white ? (c0 + c1 + c2) : 0.f);
-    const int nchunk = (S + 31) / 32;
-    // pass 1: transmittance entering each chunk
-    float T_in = 1.f;
-    float T_chunk[8];  // S <= 256 on this path (host checks)
-    for (int ch = 0; ch < nchunk; ++ch) {
-        T_chunk[ch] = T_in;
+    float zi[NCH], zn[NCH], sg[NCH], cr[NCH], cg[NCH], cb[NCH], gw[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
         const int i = ch * 32 + lane;
+        zi[ch] = zn[ch] = sg[ch] = cr[ch] = cg[ch] = cb[ch] = gw[ch] = 0.f;
+        if (i < S) {
+            zi[ch] = zr[i];
+            if (i + 1 < S) zn[ch] = zr[i + 1];
+            sg[ch] = sigma[ray * S + i];
+            const float* c = rgb + (ray * S + i) * 3;
+            cr[ch] = c[0]; cg[ch] = c[1]; cb[ch] = c[2];
+            if (gW) gw[ch] = gW[ray * S + i];
+        }
+    }
+    const float d0 = rd[3 * ray], d1 = rd[3 * ray + 1], d2 = rd[3 * ray + 2];
+    const float dn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+    const float k0 = gC ? gC[3 * ray] : 0.f, k1 = gC ? gC[3 * ray + 1] : 0.f, k2 = gC ? gC[3 * ray + 2] : 0.f;
+    const float gd = gD ? gD[ray] : 0.f, ga = gA ? gA[ray] : 0.f;
+    const float gconst = ga - (white ? (k0 + k1 + k2) : 0.f);
+    // pass 1: per-sample exp / gap once, transmittance entering each chunk
+    float e[NCH], gap[NCH], T_chunk[NCH];
+    float T_in = 1.f;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        const int i = ch * 32 + lane;
+        T_chunk[ch] = T_in;
+        e[ch] = 1.f; gap[ch] = 0.f;
         float q = 1.f;
         if (i < S) {
-            const float gap = ((i == S - 1) ? kLastDelta : (zr[i + 1] - zr[i])) * dn;
-            q = 1.f - (1.f - expf(-sigma[ray * S + i] * gap)) + kEpsT;
+            gap[ch] = ((i == S - 1) ? kLastDelta : (zn[ch] - zi[ch])) * dn;
+            e[ch] = expf(-sg[ch] * gap[ch]);
+            q = 1.f - (1.f - e[ch]) + kEpsT;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) q *= __shfl_xor_sync(0xffffffffu, q, o);
@@ -366,20 +511,12 @@ __global__ void composite_bwd_kernel(const float* __restrict__ rgb, const float*
     }
     // pass 2: chunks from the far end, carrying R
     float R_carry = 0.f;
-    for (int ch = nchunk - 1; ch >= 0; --ch) {
+#pragma unroll
+    for (int ch = NCH - 1; ch >= 0; --ch) {
         const int i = ch * 32 + lane;
         const bool ok = i < S;
-        float zi = 0.f, e = 1.f, gap = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
-        if (ok) {
-            zi = zr[i];
-            gap = ((i == S - 1) ? kLastDelta : (zr[i + 1] - zi)) * dn;
-            e = expf(-sigma[ray * S + i] * gap);
-            const float* c = rgb + (ray * S + i) * 3;
-            cr = c[0]; cg = c[1]; cb = c[2];
-        }
-        const float alpha = 1.f - e, q = ok ? (1.f - alpha + kEpsT) : 1.f;
-        const float g = ok ? (c0 * cr + c1 * cg + c2 * cb + gd * zi + gconst + (gW ? gW[ray * S + i] : 0.f)) : 0.f;
-        // exclusive transmittance inside the chunk
+        const float alpha = 1.f - e[ch], q = ok ? (1.f - alpha + kEpsT) : 1.f;
+        const float g = ok ? (k0 * cr[ch] + k1 * cg[ch] + k2 * cb[ch] + gd * zi[ch] + gconst + gw[ch]) : 0.f;
         float incl = q;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -389,7 +526,6 @@ __global__ void composite_bwd_kernel(const float* __restrict__ rgb, const float*
         float excl = __shfl_up_sync(0xffffffffu, incl, 1);
         if (lane == 0) excl = 1.f;
         const float T = T_chunk[ch] * excl;
-        // suffix composition of f_i(R) = a_i + q_i R : (Aa, Qq) <- f_i o f_{i+o}
         float Aa = ok ? g * alpha : 0.f, Qq = q;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -397,14 +533,13 @@ __global__ void composite_bwd_kernel(const float* __restrict__ rgb, const float*
             const float Qn = __shfl_down_sync(0xffffffffu, Qq, o);
             if (lane + o < 32) { Aa = fmaf(Qq, An, Aa); Qq *= Qn; }
         }
-        // F_i(R_carry) = R_{i-1}; R_i is lane i+1's value (lane 31 takes the carry itself)
         const float Rprev = fmaf(Qq, R_carry, Aa);
         float Ri = __shfl_down_sync(0xffffffffu, Rprev, 1);
         if (lane == 31) Ri = R_carry;
         if (ok) {
             const float w = alpha * T;
-            if (g_rgb) { float* o3 = g_rgb + (ray * S + i) * 3; o3[0] = w * c0; o3[1] = w * c1; o3[2] = w * c2; }
-            if (g_sigma) g_sigma[ray * S + i] = T * (g - Ri) * gap * e;
+            if (g_rgb) { float* o3 = g_rgb + (ray * S + i) * 3; o3[0] = w * k0; o3[1] = w * k1; o3[2] = w * k2; }
+            if (g_sigma) g_sigma[ray * S + i] = T * (g - Ri) * gap[ch] * e[ch];
         }
         R_carry = __shfl_sync(0xffffffffu, Rprev, 0);
     }
@@ -619,7 +754,9 @@ static inline unsigned blocks_for(long long n, int per) { return (unsigned)((n +
 int launch_get_rays(int H, int W, float focal, const float* c2w, long long first, long long n, float* ro, float* rd,
                     cudaStream_t s) {
     if (n <= 0) return 0;
-    get_rays_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, s>>>(H, W, focal, c2w, first, n, ro, rd);
+    const bool al = ((reinterpret_cast<uintptr_t>(rd) | reinterpret_cast<uintptr_t>(ro)) & 15) == 0;      // ro may be NULL
+    if (al) get_rays_flat_kernel<<<blocks_for((3 * n + 3) / 4, 256), 256, 0, s>>>(H, W, focal, c2w, first, n, ro, rd);
+    else get_rays_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, s>>>(H, W, focal, c2w, first, n, ro, rd);
     return count_launch();
 }
 int launch_gather3(const long long* idx, long long n, long long n_src, const float* sa, float* da, const float* sb,
@@ -640,9 +777,14 @@ int launch_stratified(const float* ro, long long os, const float* rd, long long 
 }
 int launch_posenc(const float* x, long long n, int L, int inc, float* out, cudaStream_t s) {
     if (n <= 0) return 0;
-    const long long tot = n * (3 * L + (inc ? 3 : 0));
-    if (tot < (1LL << 31)) posenc_kernel<unsigned><<<blocks_for(tot, 256), 256, 0, s>>>(x, n, L, inc, out);
-    else posenc_kernel<long long><<<blocks_for(tot, 256), 256, 0, s>>>(x, n, L, inc, out);
+    const int D = 6 * L + (inc ? 3 : 0);
+    if (D == 0) return 0;
+    const size_t smem = (size_t)PE_POINTS * D * sizeof(float);
+    if (smem > 48 * 1024) {          // num_freqs > 31: beyond any use of the reference, but legal
+        if (smem > 200 * 1024) { set_error("PositionalEncoding: num_freqs too large for the row buffer"); return (int)cudaErrorInvalidValue; }
+        cudaFuncSetAttribute(posenc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    posenc_kernel<<<(unsigned)((n + PE_POINTS - 1) / PE_POINTS), 3 * PE_POINTS, smem, s>>>(x, n, L, inc, out);
     return count_launch();
 }
 int launch_posenc_bwd(const float* x, const float* g, long long n, int L, int inc, float* gx, cudaStream_t s) {
@@ -677,14 +819,21 @@ int launch_head_grad(const float* rgb, const float* sigma, const float* g_rgb, c
 int launch_composite_fwd(const float* rgb, const float* sigma, const float* z, long long zs, const float* rd, long long n,
                          int S, int white, float* comp, float* depth, float* acc, float* w, cudaStream_t s) {
     if (n <= 0) return 0;
-    composite_fwd_kernel<<<blocks_for(n * 32, 256), 256, 0, s>>>(rgb, sigma, z, zs, rd, n, S, white, comp, depth, acc, w);
+    const unsigned nb = blocks_for(n * 32, 256);
+#define TN_FWD(N) composite_fwd_reg_kernel<N><<<nb, 256, 0, s>>>(rgb, sigma, z, zs, rd, n, S, white, comp, depth, acc, w)
+    if (S <= 32) TN_FWD(1); else if (S <= 64) TN_FWD(2); else if (S <= 128) TN_FWD(4); else if (S <= 256) TN_FWD(8);
+    else composite_fwd_kernel<<<nb, 256, 0, s>>>(rgb, sigma, z, zs, rd, n, S, white, comp, depth, acc, w);
+#undef TN_FWD
     return count_launch();
 }
 int launch_composite_bwd(const float* rgb, const float* sigma, const float* z, long long zs, const float* rd, long long n,
                          int S, int white, const float* gC, const float* gD, const float* gA, const float* gW,
                          float* g_rgb, float* g_sigma, cudaStream_t s) {
     if (n <= 0) return 0;
-    composite_bwd_kernel<<<blocks_for(n * 32, 256), 256, 0, s>>>(rgb, sigma, z, zs, rd, n, S, white, gC, gD, gA, gW, g_rgb, g_sigma);
+    const unsigned nb = blocks_for(n * 32, 256);
+#define TN_BWD(N) composite_bwd_reg_kernel<N><<<nb, 256, 0, s>>>(rgb, sigma, z, zs, rd, n, S, white, gC, gD, gA, gW, g_rgb, g_sigma)
+    if (S <= 32) TN_BWD(1); else if (S <= 64) TN_BWD(2); else if (S <= 128) TN_BWD(4); else TN_BWD(8);    // S <= 256 on this path (host checks)
+#undef TN_BWD
     return count_launch();
 }
 int launch_mse_psnr(const float* a, const float* b, long long n, float* out2, cudaStream_t s) {

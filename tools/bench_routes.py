@@ -7,12 +7,14 @@ section 5 "second baseline"); BASELINE config 3 shape (4096 rays x 64 samples pe
   reference  the reference's UNMODIFIED train.py importing the reference's own modules (oracle/_ref/src): its stock PyTorch CUDA
              path (autocast fp16) on the same GPU
 
-Each route runs twice (K1 and K2 iterations, previews / checkpoints / logging pushed past the end) in a fresh process; it/s =
-(K2 - K1) / (wall(K2) - wall(K1)), which removes start-up, compilation-free warm-up and the final render.  Developer / evidence
+Each route runs in a fresh process (previews / checkpoints / logging pushed past the end) with tools/_timing_shims/tqdm in front
+of the real tqdm: the unmodified loop `for step in tqdm(range(...))` then reports its own steady-state rate (clock from iteration
+--warm to the end of the loop, device synchronised on both sides; start-up and the final render are outside).  Developer / evidence
 tool for the GPU box:  python tools/bench_routes.py [--out profiles/r2_routes.json]"""
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import tempfile
@@ -23,13 +25,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "tiny-nerf-pytorch_b200")
 SHIMS = os.path.join(PKG, "_shims")
+TIMING = os.path.join(ROOT, "tools", "_timing_shims")
 REF_SCRIPTS = os.path.join(ROOT, "baseline", "_ref", "src")
 REF_MODULES = os.path.join(ROOT, "oracle", "_ref", "src")
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--out", default=None)
-ap.add_argument("--k1", type=int, default=200)
-ap.add_argument("--k2", type=int, default=2200)
+ap.add_argument("--warm", type=int, default=200)
+ap.add_argument("--iters", type=int, default=3200)
 ap.add_argument("--rays", type=int, default=4096)
 ap.add_argument("--samples", type=int, default=64)
 args = ap.parse_args()
@@ -52,14 +55,14 @@ def run(route, iters):
     if route == "fused":
         code = (f"import train; train.main(train.Config(iters={iters}, n_rand={args.rays}, n_samples={args.samples}, log_every={far}, "
                 f"preview_every={far}, ckpt_every={far}, resume=False))")
-        path = [PKG, SHIMS]
+        path = [TIMING, PKG, SHIMS]
     else:
         script = os.path.join(REF_SCRIPTS, "train.py")
         code = (f"import sys, runpy; sys.argv=['train.py','--iters','{iters}','--n-rand','{args.rays}','--n-samples','{args.samples}',"
                 f"'--log-every','{far}','--preview-every','{far}','--ckpt-every','{far}','--no-resume'];"
                 f"runpy.run_path({script!r}, run_name='__main__')")
-        path = [PKG, SHIMS] if route == "dropin" else [REF_MODULES, SHIMS]
-    env = dict(os.environ, PYTHONPATH=os.pathsep.join(path))
+        path = [TIMING, PKG, SHIMS] if route == "dropin" else [TIMING, REF_MODULES, SHIMS]
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join(path), TNERF_TIMING_WARMUP=str(args.warm))
     for d in ("checkpoints", "outputs"):
         subprocess.run(["rm", "-rf", os.path.join(work, d)])
     t0 = time.time()
@@ -67,20 +70,24 @@ def run(route, iters):
     dt = time.time() - t0
     if r.returncode != 0 or f"[done] {iters} iters" not in r.stdout:
         raise RuntimeError(f"{route} ({iters} iters) failed:\n{r.stdout[-1500:]}\n{r.stderr[-2500:]}")
-    return dt
+    m = re.search(r"\[timing\] steps=(\d+) seconds=([0-9.]+)", r.stdout)
+    if not m:
+        raise RuntimeError(f"{route}: no timing line in the output:\n{r.stdout[-1500:]}")
+    return int(m.group(1)), float(m.group(2)), dt
 
 
 res = {"workload": f"train.py loop, {args.rays} rays x {args.samples} samples per step, 100 x 100 synthetic scene, one B200",
-       "method": f"it/s = ({args.k2} - {args.k1}) / (wall({args.k2}) - wall({args.k1})), fresh process per run", "routes": {}}
+       "method": f"{args.iters} iterations, clock from iteration {args.warm} to the end of the loop (device synchronised), fresh process per route",
+       "routes": {}}
 for route in ("fused", "dropin", "reference"):
     if route != "fused" and not os.path.exists(os.path.join(REF_SCRIPTS, "train.py")):
         res["routes"][route] = {"unavailable": "reference scripts not staged (tools/stage_reference.sh)"}
         continue
     try:
-        t1, t2 = run(route, args.k1), run(route, args.k2)
-        its = (args.k2 - args.k1) / max(t2 - t1, 1e-9)
+        steps, secs, wall = run(route, args.iters)
+        its = steps / secs
         res["routes"][route] = {"it_per_s": its, "ray_samples_per_s": its * args.rays * args.samples, "us_per_step": 1e6 / its,
-                                "wall_s": [t1, t2]}
+                                "timed_steps": steps, "process_wall_s": wall}
     except Exception as e:  # noqa: BLE001  (evidence tool: record the failure and go on)
         res["routes"][route] = {"error": str(e)[-1500:]}
     print(route, json.dumps(res["routes"][route]), flush=True)
