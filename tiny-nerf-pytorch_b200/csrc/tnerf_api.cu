@@ -320,7 +320,8 @@ int tnerf_render_fwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long lo
     if (!h || h->params.empty() || !comp_rgb || n_rays < 0 || n_samples < 1) return bad("tnerf_render_fwd: invalid argument / params not bound");
     if (int e = check_source(rays_host)) return e;
     const RaySource rs = to_device_source(rays_host);
-    if (precision == TNERF_PREC_F16_TC)
+    // tensor-core kernels where they cover the shape (n_samples a multiple of 32, ...); other shapes take the exact fp32 path
+    if (precision == TNERF_PREC_F16_TC && fused_render_shape_ok(h, n_samples, weights != nullptr))
         return fused_render_fwd(h, rs, n_rays, near_, far_, n_samples, jitter, white_bkgd, comp_rgb, depth, acc, weights, rays_d_out,
                                 (cudaStream_t)stream);
     F32Job job{};
@@ -341,7 +342,8 @@ int tnerf_render_frames(tnerf_handle* h, const float* poses, int n_poses, int H,
     rs.c2w = poses; rs.H = H; rs.W = W; rs.focal = focal; rs.first_ray = first_ray; rs.frame_rays = rays_per_pose;
     // one launch for the whole pose batch where the kernel indexes the pose per ray (role-split render kernels: n_samples % 32 == 0);
     // other shapes: one launch per pose from here
-    const bool one_launch = precision == TNERF_PREC_F16_TC && n_samples % 32 == 0 && total < (1ll << 31);
+    const bool tc = precision == TNERF_PREC_F16_TC && fused_render_shape_ok(h, n_samples, false);
+    const bool one_launch = tc && total < (1ll << 31);
     if (one_launch)
         return fused_render_fwd(h, rs, total, near_, far_, n_samples, nullptr, white_bkgd, comp_rgb, depth, acc, nullptr, nullptr, (cudaStream_t)stream);
     rs.frame_rays = 0;
@@ -351,7 +353,7 @@ int tnerf_render_frames(tnerf_handle* h, const float* poses, int n_poses, int H,
         float* d = depth ? depth + f * rays_per_pose : nullptr;
         float* a = acc ? acc + f * rays_per_pose : nullptr;
         int e;
-        if (precision == TNERF_PREC_F16_TC)
+        if (tc)
             e = fused_render_fwd(h, rs, rays_per_pose, near_, far_, n_samples, nullptr, white_bkgd, c, d, a, nullptr, nullptr, (cudaStream_t)stream);
         else {
             F32Job job{};

@@ -69,253 +69,7 @@ __global__ void pack_weights_kernel(PackArgs a, __half* __restrict__ img) {
     img[e] = __float2half_rn(v);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Fused forward kernel.  288 threads: warps 0-3 = warpgroup A, warps 4-7 = warpgroup B (each owns one
-// 128-row tile at a time: thread <-> sample row <-> TMEM lane), warp 8 = MMA issuer + weight loader.
-constexpr int FWD_THREADS = 320;   // 2 x 4 row warps + one MMA-issuer warp per warpgroup
-constexpr int TM_ACC = 0, TM_ACT = 128, TM_X = 192, TM_HEAD = 224, TM_ONES = 240, TM_WG_STRIDE = 256;
-constexpr int MAX_G = 8;
-
-struct FwdSmem {   // trailing part of dynamic smem (after the weight image)
-    float4 stage[2][MAX_G * 128];   // per warpgroup: (sigma, r, g, b) per sample of the current unit
-    float stage_z[2][MAX_G * 128];
-    uint64_t bar_w, bar_a[2], bar_acc[2];
-    uint32_t tmem_slot;
-};
-
-__device__ __forceinline__ void composite_unit(const FwdParams& p, const float4* st, const float* sz, long long ray0, int warp_q,
-                                               int lane) {
-    const int S = p.S;
-    for (int rr = warp_q; rr < p.R; rr += 4) {
-        const long long ray = ray0 + rr;
-        if (ray >= p.n_rays) break;
-        float o[3], d[3];
-        load_ray(p.rs, ray, o, d);
-        const float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-        const float4* s4 = st + rr * S;
-        const float* zz = sz + rr * S;
-        float T_carry = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, dsum = 0.f, asum = 0.f;
-        for (int base = 0; base < S; base += 32) {
-            const int i = base + lane;
-            const bool ok = i < S;
-            float zi = 0.f, alpha = 0.f, q = 1.f;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) {
-                v = s4[i];
-                zi = zz[i];
-                const float gap = ((i == S - 1) ? kLastDelta : (zz[i + 1] - zi)) * dn;
-                alpha = 1.f - expf(-v.x * gap);
-                q = 1.f - alpha + kEpsT;
-            }
-            float incl = q;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const float up = __shfl_up_sync(0xffffffffu, incl, off);
-                if (lane >= off) incl *= up;
-            }
-            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-            if (lane == 0) excl = 1.f;
-            const float w = alpha * (T_carry * excl);
-            if (ok) {
-                if (p.weights) p.weights[ray * S + i] = w;
-                cr += w * v.y; cg += w * v.z; cb += w * v.w;
-                dsum += w * zi; asum += w;
-            }
-            T_carry *= __shfl_sync(0xffffffffu, incl, 31);
-        }
-        cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); dsum = warp_sum(dsum); asum = warp_sum(asum);
-        if (lane == 0) {
-            const float bg = p.white ? 1.f - asum : 0.f;
-            p.comp[3 * ray] = cr + bg; p.comp[3 * ray + 1] = cg + bg; p.comp[3 * ray + 2] = cb + bg;
-            if (p.depth) p.depth[ray] = dsum;
-            if (p.acc) p.acc[ray] = asum;
-            if (p.rays_d_out) { p.rays_d_out[3 * ray] = d[0]; p.rays_d_out[3 * ray + 1] = d[1]; p.rays_d_out[3 * ray + 2] = d[2]; }
-        }
-    }
-}
-
-template <int KX>
-__global__ void __launch_bounds__(FWD_THREADS, 1) fused_fwd_kernel(const __grid_constant__ FwdParams p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem + ((p.plan.image_bytes + 1023u) & ~1023u));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_w = smem_u32(&sm.bar_w);
-
-    if (warp == 8 && lane == 0) {
-        mbar_init(bar_w, 1);
-        for (int w = 0; w < 2; ++w) { mbar_init(smem_u32(&sm.bar_a[w]), 128); mbar_init(smem_u32(&sm.bar_acc[w]), 1); }
-        fence_barrier_init();
-    }
-    if (warp == 0) { tmem_alloc(smem_u32(&sm.tmem_slot), 512); tmem_relinquish(); }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = sm.tmem_slot;
-    long long* dbg = (p.debug && blockIdx.x == 0 && warp != 9) ? p.debug : nullptr;
-    int dbg_n = 0;
-#define STAMP(base) do { if (dbg && dbg_n < 500) dbg[(base) + dbg_n++] = clock64(); } while (0)
-
-    // units are dealt round-robin: (cta, warpgroup) pair j takes units j, j + 2*grid, ...
-    const long long stride = 2LL * gridDim.x;
-
-    if (warp >= 8) {
-        // ------------------------------ MMA issuers: warp 8 serves warpgroup 0, warp 9 warpgroup 1 ------------------------------
-        const int w = warp - 8;
-        if (lane == 0) {
-            if (w == 0) {
-                mbar_expect_tx(bar_w, p.plan.image_bytes);
-                uint32_t off = 0;
-                while (off < p.plan.image_bytes) {
-                    const uint32_t n = min(32768u, p.plan.image_bytes - off);
-                    bulk_g2s(smem_u32(smem) + off, reinterpret_cast<const uint8_t*>(p.image) + off, n, bar_w);
-                    off += n;
-                }
-            }
-            mbar_wait(bar_w, 0);
-            uint32_t phase = 0;
-            const uint32_t wbase = smem_u32(smem);
-            const uint32_t tw = tmem + w * TM_WG_STRIDE;
-            const uint32_t bar_a = smem_u32(&sm.bar_a[w]), bar_acc = smem_u32(&sm.bar_acc[w]);
-            for (long long u = 2LL * blockIdx.x + w; u < p.n_units; u += stride) {
-                for (int g = 0; g < p.G; ++g) {
-                    for (int step = 0; step <= p.plan.depth; ++step) {
-                        const LayerPlan& lp = p.plan.layer[step];
-                        const uint32_t idesc = lp.idesc, N = lp.N;
-                        const uint32_t b_adv = (N * 32u) >> 4;
-                        uint32_t b_lo = (((wbase + lp.b_off) >> 4) & 0x3FFFu) | (((N * 16u) >> 4) << 16);
-                        const uint32_t b_hi = (128u >> 4) | (1u << 14);          // SBO | descriptor version
-                        const uint32_t d_t = tw + ((step == p.plan.depth) ? TM_HEAD : TM_ACC);
-                        const int nseg = lp.nseg;
-                        uint32_t seg_a[3];
-                        int seg_n[3];
-#pragma unroll
-                        for (int sgi = 0; sgi < 3; ++sgi) {
-                            const uint32_t kind = lp.seg_kind[sgi];
-                            seg_a[sgi] = tw + (kind == SEG_ACT ? TM_ACT : kind == SEG_X ? TM_X : TM_ONES);
-                            seg_n[sgi] = sgi < nseg ? lp.seg_steps[sgi] : 0;
-                        }
-                        mbar_wait(bar_a, phase);
-                        phase ^= 1;
-                        tc_fence_after();
-                        STAMP(512);
-                        uint32_t acc = 0;
-#pragma unroll
-                        for (int sgi = 0; sgi < 3; ++sgi) issue_ts_n(seg_n[sgi], d_t, seg_a[sgi], b_lo, b_hi, b_adv, idesc, acc);
-                        tc_commit(bar_acc);
-                        STAMP(512);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-    } else {
-        // ------------------------------ sample / epilogue warpgroups ------------------------------
-        const int wg = warp >> 2, q = warp & 3, row = q * 32 + lane;
-        const uint32_t tw = tmem + wg * TM_WG_STRIDE + ((uint32_t)(q * 32) << 16);
-        const uint32_t bar_a = smem_u32(&sm.bar_a[wg]), bar_acc = smem_u32(&sm.bar_acc[wg]);
-        float4* st = sm.stage[wg];
-        float* sz = sm.stage_z[wg];
-        {   // constant-one chunk used to add biases inside the GEMM: A[:,0] = A[:,1] = 1
-            uint32_t ones[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) ones[i] = 0u;
-            ones[0] = 0x3C003C00u;
-            tmem_st8(tw + TM_ONES, ones);
-        }
-        uint32_t phase = 0;
-        const bool jit = p.jitter != nullptr;
-        if (!(wg == 0 && row == 0)) dbg = nullptr;
-        for (long long u = 2LL * blockIdx.x + wg; u < p.n_units; u += stride) {
-            const long long ray0 = u * p.R;
-            for (int g = 0; g < p.G; ++g) {
-                STAMP(0);
-                const int urow = g * 128 + row;            // row inside the unit
-                const long long ray = ray0 + urow / p.S;
-                const int si = urow % p.S;
-                const bool valid = ray < p.n_rays;
-                float pt[3] = {0.f, 0.f, 0.f};
-                float z = 0.f;
-                if (valid) {
-                    float o[3], d[3];
-                    load_ray(p.rs, ray, o, d);
-                    z = depth_sample(si, p.S, p.near_, p.far_, jit ? p.jitter[ray * p.S + si] : 0.f, jit);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) pt[c] = __fadd_rn(o[c], __fmul_rn(d[c], z));
-                }
-                sz[urow] = z;
-                {
-                    uint32_t pk[KX / 2];
-                    if (p.plan.include_input) encode_point<KX, true>(pt, p.plan.L, pk);
-                    else encode_point<KX, false>(pt, p.plan.L, pk);
-#pragma unroll
-                    for (int c = 0; c < KX / 32; ++c) {
-                        uint32_t chunk[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) chunk[i] = pk[c * 16 + i];
-                        tmem_st16(tw + TM_X + c * 16, chunk);
-                    }
-                    if (KX % 32) {
-                        uint32_t chunk[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) chunk[i] = pk[(KX / 32) * 16 + i];
-                        tmem_st8(tw + TM_X + (KX / 32) * 16, chunk);
-                    }
-                }
-                tc_wait_st();
-                tc_fence_before();
-                mbar_arrive(bar_a);
-                STAMP(0);
-                for (int l = 0; l < p.plan.depth; ++l) {
-                    mbar_wait(bar_acc, phase);
-                    phase ^= 1;
-                    tc_fence_after();
-                    STAMP(0);
-#pragma unroll
-                    for (int c = 0; c < 4; c += 2) {
-                        uint32_t v0[32], v1[32];
-                        tmem_ld32(tw + TM_ACC + c * 32, v0);
-                        tmem_ld32(tw + TM_ACC + c * 32 + 32, v1);
-                        tc_wait_ld();
-                        uint32_t h0[16], h1[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) h0[i] = pack_relu_h2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
-                        tmem_st16(tw + TM_ACT + c * 16, h0);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) h1[i] = pack_relu_h2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
-                        tmem_st16(tw + TM_ACT + c * 16 + 16, h1);
-                    }
-                    tc_wait_st();
-                    tc_fence_before();
-                    mbar_arrive(bar_a);
-                    STAMP(0);
-                }
-                mbar_wait(bar_acc, phase);
-                phase ^= 1;
-                tc_fence_after();
-                STAMP(0);
-                {
-                    uint32_t v[4];
-                    tmem_ld4(tw + TM_HEAD, v);
-                    tc_wait_ld();
-                    float4 o4;
-                    o4.x = fmaxf(__uint_as_float(v[0]), 0.f);
-                    o4.y = 1.f / (1.f + __expf(-__uint_as_float(v[1])));
-                    o4.z = 1.f / (1.f + __expf(-__uint_as_float(v[2])));
-                    o4.w = 1.f / (1.f + __expf(-__uint_as_float(v[3])));
-                    st[urow] = o4;
-                }
-            }
-            STAMP(0);
-            bar_sync(1 + wg, 128);
-            composite_unit(p, st, sz, ray0, q, lane);
-            bar_sync(1 + wg, 128);
-            STAMP(0);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
-}
+constexpr int MAX_G = 8;       // tiles of 128 samples per work unit of the render kernels (lcm(n_samples, 128) rows)
 
 // ================================================================================================
 // UMMA self-test: D(128 x N) = A(128 x K) B(N x K)^T through the descriptor conventions above.
@@ -619,6 +373,15 @@ int fused_pack_weights(tnerf_handle* h, cudaStream_t s) {
 
 static long long gcd_ll(long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; }
 
+// shapes the tensor-core render kernels cover; everything else runs on the exact fp32 path (tnerf_api.cu)
+bool fused_render_shape_ok(const tnerf_handle* h, int S, bool want_weights) {
+    if (S < 1 || S % 32 != 0) return false;
+    const long long G = S / gcd_ll(S, 128);
+    if (wide_shape_supported(h)) return G <= 4 && !want_weights;
+    FusedPlan pl;
+    return build_plan(h, pl) && G <= MAX_G && !(want_weights && G > 1);
+}
+
 int fused_render_fwd(tnerf_handle* h, const RaySource& rs, long long n, float nr, float fr, int S, const float* jitter, int white,
                      float* comp, float* depth, float* acc, float* weights, float* rays_d_out, cudaStream_t s) {
     if (n <= 0) return 0;
@@ -633,15 +396,10 @@ int fused_render_fwd(tnerf_handle* h, const RaySource& rs, long long n, float nr
     p.jitter = jitter; p.comp = comp; p.depth = depth; p.acc = acc; p.weights = weights; p.rays_d_out = rays_d_out;
     p.image = reinterpret_cast<const __half*>(h->packed);
     p.debug = reinterpret_cast<long long*>(h->debug);
-    const size_t smem = ((p.plan.image_bytes + 1023u) & ~1023u) + sizeof(FwdSmem);
     long long grid = (p.n_units + 1) / 2;
     if (grid > h->sm_count) grid = h->sm_count;
-    if (S % 32 == 0 && !(weights && p.G > 1)) return fused_render_fwd_fast(p, (int)grid, s);
-    auto kern = p.plan.Kx == 64 ? fused_fwd_kernel<64> : p.plan.Kx == 48 ? fused_fwd_kernel<48> : p.plan.Kx == 32 ? fused_fwd_kernel<32> : fused_fwd_kernel<16>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("fused fwd: shared memory request rejected"); return (int)e; }
-    kern<<<(unsigned)grid, FWD_THREADS, smem, s>>>(p);
-    return count_launch();
+    if (!(S % 32 == 0 && !(weights && p.G > 1))) { set_error("fused path: shape not covered by the tensor-core render kernel"); return -5; }
+    return fused_render_fwd_fast(p, (int)grid, s);
 }
 
 }  // namespace tnerf

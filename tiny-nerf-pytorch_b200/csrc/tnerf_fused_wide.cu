@@ -677,7 +677,7 @@ int fused_render_fwd_wide(tnerf_handle* h, const RaySource& rs, long long n, flo
     while (b) { const long long t = a % b; a = b; b = t; }
     wide::Params p{};
     p.G = (int)(S / a); p.R = (int)(128 / a);
-    if (p.G * 4 > wide::MAX_CHUNKS) { set_error("wide fused path: n_samples/gcd(n_samples,128) must be <= 8"); return -4; }
+    if (p.G * 4 > wide::MAX_CHUNKS) { set_error("wide fused path: n_samples/gcd(n_samples,128) must be <= 4"); return -4; }
     p.rs = rs; p.n_rays = n; p.n_units = (n + p.R - 1) / p.R; p.S = S; p.white = white; p.near_ = nr; p.far_ = fr;
     p.jitter = jitter; p.comp = comp; p.depth = depth; p.acc = acc; p.rays_d_out = rays_d_out;
     p.image_bytes = wide_image_bytes(kx);

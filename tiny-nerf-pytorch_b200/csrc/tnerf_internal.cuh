@@ -94,6 +94,7 @@ int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, flo
 int launch_found_inf(const float* g, long long n, float* found, cudaStream_t s);
 // wide MLP (hidden = 256) on CTA pairs (tnerf_fused_wide.cu)
 bool wide_shape_supported(const tnerf_handle* h);
+bool fused_render_shape_ok(const tnerf_handle* h, int S, bool want_weights);   // tnerf_fused.cu
 int wide_pack_weights(tnerf_handle* h, cudaStream_t s);
 void wide_release(tnerf_handle* h);
 int fused_render_fwd_wide(tnerf_handle* h, const RaySource& rs, long long n, float nr, float fr, int S, const float* jitter, int white,

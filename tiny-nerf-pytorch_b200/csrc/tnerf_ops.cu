@@ -2,13 +2,27 @@
 // get_rays, ray gather, stratified_samples, PositionalEncoding, TinyNeRF (tiled FFMA GEMMs),
 // volume_render forward/backward, MSE/PSNR, Adam.  All are HBM- or FFMA-bound elementwise / scan /
 // SGEMM kernels; the tensor-core fused path lives in tnerf_fused.cu.
+#include <cstdlib>
 #include "tnerf_fused.cuh"
 
 namespace tnerf {
 
+// one ray direction (src/rays.py:21-31) with the divisions turned into multiplications by once-computed reciprocals and the
+// normalisation into a reciprocal square root (<= 3 ulp on the direction, inside the 1e-6 bar; the fused kernels use the same form):
+// the IEEE divisions made this kernel instruction-bound (90 instructions per ray) at half of the write bandwidth
+__device__ __forceinline__ void ray_dir(const float* __restrict__ c2w, float cxs, float cys, float inv_focal, float* d) {
+    const float cx = cxs * inv_focal, cy = -cys * inv_focal;
+    const float wx = fmaf(-1.f, c2w[2], fmaf(cy, c2w[1], cx * c2w[0]));
+    const float wy = fmaf(-1.f, c2w[6], fmaf(cy, c2w[5], cx * c2w[4]));
+    const float wz = fmaf(-1.f, c2w[10], fmaf(cy, c2w[9], cx * c2w[8]));
+    const float inv_n = rsqrtf(fmaxf(fmaf(wz, wz, fmaf(wy, wy, wx * wx)), 1e-24f));
+    d[0] = wx * inv_n; d[1] = wy * inv_n; d[2] = wz * inv_n;
+}
+
 // ------------------------------------------------------------------------------------------------
 // a1 get_rays (src/rays.py:3-33): 24 B written per ray.  One thread = 4 consecutive rays = three 16-byte stores per output
-// (a thread per ray would issue stride-12 scalar stores); the pixel row/column are divided out once and stepped.
+// (a thread per ray would issue stride-12 scalar stores; a flat float4-per-thread mapping evaluates every ray 1.5 times and measured
+// slower); the pixel row/column are divided out once and stepped.
 __global__ void get_rays_kernel(int H, int W, float focal, const float* __restrict__ c2w, long long first,
                                 long long n, float* __restrict__ ro, float* __restrict__ rd) {
     const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -16,20 +30,17 @@ __global__ void get_rays_kernel(int H, int W, float focal, const float* __restri
     if (i0 >= n) return;
     const float ox = c2w[3], oy = c2w[7], oz = c2w[11];
     const long long k0 = first + i0;
-    int row = (int)(k0 / W), col = (int)(k0 - (long long)row * W);
+    int row, col;
+    if (k0 < (1LL << 31)) { row = (int)((unsigned)k0 / (unsigned)W); col = (int)((unsigned)k0 - (unsigned)row * (unsigned)W); }
+    else { row = (int)(k0 / W); col = (int)(k0 - (long long)row * W); }
+    const float inv_focal = __frcp_rn(focal);
     float d[12];
     const int cnt = (n - i0 < 4) ? (int)(n - i0) : 4;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         d[3 * j] = d[3 * j + 1] = d[3 * j + 2] = 0.f;
         if (j < cnt) {
-            const float cx = __fdiv_rn((float)col - (float)W * 0.5f, focal);
-            const float cy = -__fdiv_rn((float)row - (float)H * 0.5f, focal);
-            const float wx = fmaf(-1.f, c2w[2], fmaf(cy, c2w[1], cx * c2w[0]));
-            const float wy = fmaf(-1.f, c2w[6], fmaf(cy, c2w[5], cx * c2w[4]));
-            const float wz = fmaf(-1.f, c2w[10], fmaf(cy, c2w[9], cx * c2w[8]));
-            const float nn = fmaxf(sqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx))), 1e-12f);
-            d[3 * j] = __fdiv_rn(wx, nn); d[3 * j + 1] = __fdiv_rn(wy, nn); d[3 * j + 2] = __fdiv_rn(wz, nn);
+            ray_dir(c2w, (float)col - (float)W * 0.5f, (float)row - (float)H * 0.5f, inv_focal, d + 3 * j);
             if (++col == W) { col = 0; ++row; }
         }
     }
@@ -46,47 +57,6 @@ __global__ void get_rays_kernel(int H, int W, float focal, const float* __restri
             rd[3 * (i0 + j)] = d[3 * j]; rd[3 * (i0 + j) + 1] = d[3 * j + 1]; rd[3 * (i0 + j) + 2] = d[3 * j + 2];
             if (ro) { ro[3 * (i0 + j)] = ox; ro[3 * (i0 + j) + 1] = oy; ro[3 * (i0 + j) + 2] = oz; }
         }
-    }
-}
-
-// Flat variant (16-byte aligned outputs): thread q writes float4 number q of the flat (n, 3) direction array -- consecutive
-// threads, consecutive 16 bytes, every store instruction of a warp one contiguous 512-byte run (the kernel above writes 16 bytes
-// every 48: each 32-byte sector is touched by two different store instructions).  Four consecutive floats span at most two rays; both
-// are evaluated (same operations in the same order as above: identical bits).
-__global__ void get_rays_flat_kernel(int H, int W, float focal, const float* __restrict__ c2w, long long first,
-                                     long long n, float* __restrict__ ro, float* __restrict__ rd) {
-    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long f0 = 4 * q, total = 3 * n;
-    if (f0 >= total) return;
-    const long long ray0 = f0 / 3;
-    const int c0 = (int)(f0 - 3 * ray0);
-    const long long k0 = first + ray0;
-    int row = (int)(k0 / W), col = (int)(k0 - (long long)row * W);
-    float d[6];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const float cx = __fdiv_rn((float)col - (float)W * 0.5f, focal);
-        const float cy = -__fdiv_rn((float)row - (float)H * 0.5f, focal);
-        const float wx = fmaf(-1.f, c2w[2], fmaf(cy, c2w[1], cx * c2w[0]));
-        const float wy = fmaf(-1.f, c2w[6], fmaf(cy, c2w[5], cx * c2w[4]));
-        const float wz = fmaf(-1.f, c2w[10], fmaf(cy, c2w[9], cx * c2w[8]));
-        const float nn = fmaxf(sqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx))), 1e-12f);
-        d[3 * j] = __fdiv_rn(wx, nn); d[3 * j + 1] = __fdiv_rn(wy, nn); d[3 * j + 2] = __fdiv_rn(wz, nn);
-        if (++col == W) { col = 0; ++row; }
-    }
-    const float o3[3] = {c2w[3], c2w[7], c2w[11]};
-    float v[4], w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = c0 + j;                   // 0 .. 5: component c of ray0, or component c - 3 of the next ray
-        v[j] = c == 0 ? d[0] : c == 1 ? d[1] : c == 2 ? d[2] : c == 3 ? d[3] : c == 4 ? d[4] : d[5];
-        w[j] = o3[c >= 3 ? c - 3 : c];
-    }
-    if (f0 + 4 <= total) {
-        *reinterpret_cast<float4*>(rd + f0) = make_float4(v[0], v[1], v[2], v[3]);
-        if (ro) *reinterpret_cast<float4*>(ro + f0) = make_float4(w[0], w[1], w[2], w[3]);
-    } else {
-        for (int j = 0; f0 + j < total; ++j) { rd[f0 + j] = v[j]; if (ro) ro[f0 + j] = w[j]; }
     }
 }
 
@@ -754,9 +724,7 @@ static inline unsigned blocks_for(long long n, int per) { return (unsigned)((n +
 int launch_get_rays(int H, int W, float focal, const float* c2w, long long first, long long n, float* ro, float* rd,
                     cudaStream_t s) {
     if (n <= 0) return 0;
-    const bool al = ((reinterpret_cast<uintptr_t>(rd) | reinterpret_cast<uintptr_t>(ro)) & 15) == 0;      // ro may be NULL
-    if (al) get_rays_flat_kernel<<<blocks_for((3 * n + 3) / 4, 256), 256, 0, s>>>(H, W, focal, c2w, first, n, ro, rd);
-    else get_rays_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, s>>>(H, W, focal, c2w, first, n, ro, rd);
+    get_rays_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, s>>>(H, W, focal, c2w, first, n, ro, rd);
     return count_launch();
 }
 int launch_gather3(const long long* idx, long long n, long long n_src, const float* sa, float* da, const float* sb,
