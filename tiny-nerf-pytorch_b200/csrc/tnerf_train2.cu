@@ -188,12 +188,12 @@ struct StreamIssuer {
         } else if constexpr (OP == 3) {     // heads (samples on lanes)
             wait(bar_in, PH_IN);
             T2_ISSUE(gemm<8>(D, aQhead, bWH, i16tk, 0); tc_commit(T2_BAR(bar_head)););
-        } else if constexpr (OP == 4) {     // head wgrad: H3 . dZh
+        } else if constexpr (OP == 4) {     // head dgrad -> dH3 (the tile's serial chain continues through it)
             wait(T2_BAR(bar_dzh), PH_DZH);
-            T2_ISSUE(gemm<4>(D + 16, aQ, bDZHt, i16kt, 0); tc_commit(bar_d););
-        } else if constexpr (OP == 5) {     // head dgrad -> dH3
-            wait(bar_in, PH_IN);
             T2_ISSUE(gemm<1>(D, aWHt, bDZHk, i64tk, 0); tc_commit(bar_d););
+        } else if constexpr (OP == 5) {     // head wgrad: H3 . dZh -- behind the dgrad, into four columns of the accumulator the drain
+            wait(T2_BAR(bar_dread), PH_DR); // threads have just read dH3 out of: it runs while they turn dH3 into dZ3 (which they store
+            T2_ISSUE(gemm<4>(D + 16, aQ, bDZHt, i16kt, 0); tc_commit(bar_d););   // over H3 only after this GEMM has committed)
         } else if constexpr (OP == 6) {
             // layers 3 and 2: dgrad first on its own barrier, the wgrad GEMMs behind it -- the drain threads turn dH into the
             // packed dZ row while the wgrad still reads the slot, and store once the wgrad has committed
@@ -701,7 +701,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         //        0-3  forward drains H0->P, H1->Q (+ parked in registers), H2->P, H3->Q
         //        4    [staggered streams] the other stream's dW1 half: fixed rendezvous where this warpgroup would otherwise sleep
         //             through its own compositing; keeps the streams half a tile apart, blocking waits only
-        //        5    head weight gradient (4 columns)          6  dZ3 over H3 (Q), bias gradient of layer 3
+        //        5    (nothing)          6  dZ3 from the head input gradient; the head weight gradient (4 columns), issued behind it, is
+        //             collected before dZ3 replaces H3 (Q); bias gradient of layer 3
         //        7    dZ2 over H2 (P) once dW3 has committed, H1 back into Q
         //        8    dZ1 over H1 (Q) once dW2 has committed, bias gradient of layer 1; releases the accumulator early (H0 recompute)
         //        9    recomputed H0 -> P                         10  dW1 halves (own; in-phase mode also the other stream's, see below)
@@ -709,14 +710,15 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         //      after the last tile: the other stream's remaining dW1 halves.
         // In-phase mode (n_samples = 128, both streams in the same tile phase): the dW1 halves are drained where they are produced,
         // in the order stream 0 first half (WG0), stream 0 second half (WG1) | stream 1 first half (WG0), stream 1 second half (WG1).
-        enum { K_FWD = 0, K_G = 1, K_SMALL = 2, K_BWD = 3 };
+        enum { K_FWD = 0, K_G = 1, K_BWD = 3 };
 #define T2_SIGNAL(bar) do { fence_proxy_async(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar); } while (0)
         // one step of the tile program; returns 0 = next step, 1 = stay in this step (tail: more foreign halves), 2 = leave the tile.
         // ROLLED (default): called from a rolled loop, each drain body exists once (instruction-cache footprint: the two streams of a
         // CTA are half a tile apart and run different steps at the same time).  UNROLL: the twelve calls of a full tile are unrolled and
         // specialised per step: 15 % faster when the streams run in phase (n_samples = 128, BASELINE config 5); the host picks.
         auto do_step = [&](const int step, const bool tail, const long long t) __attribute__((always_inline)) -> int {
-                const int kind = (step == 4 || step == 10) ? K_G : (step == 5) ? K_SMALL : (step <= 3 || step == 9) ? K_FWD : K_BWD;
+                if (step == 5) return 0;                                // (the head weight gradient is collected inside step 6)
+                const int kind = (step == 4 || step == 10) ? K_G : (step <= 3 || step == 9) ? K_FWD : K_BWD;
                 uint8_t* slot = ((0x14A >> step) & 1) ? Q : P;          // Q for steps 1, 3, 6, 8
                 if (tail && step == 11) return 2;
                 if (kind == K_G) {
@@ -801,21 +803,24 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
 #pragma unroll
                         for (int i = 0; i < 32; ++i) stash[i] = o[i];
                     }
-                } else if (kind == K_SMALL) {
-                    uint32_t v[4];
-                    tmem_ld4(D_own + 16, v);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) dwh[k] += __uint_as_float(v[k]);
-                    T2_SIGNAL(bar_in);
                 } else {
                     // dZ = dH * (H > 0): computed into registers while the weight-gradient GEMM that still reads the slot runs,
                     // stored once that GEMM has committed (steps 7, 8); steps 6 and 11 store at once
                     uint32_t o[32];
                     const uint32_t ma = step == 6 ? mk3a : step == 7 ? mk2a : step == 8 ? mk1a : mk0a;
                     const uint32_t mb = step == 6 ? mk3b : step == 7 ? mk2b : step == 8 ? mk1b : mk0b;
-                    drain_bwd_compute(D_own, ma, mb, o, (step == 8 || step == 11) ? bar_dread : 0u);
+                    drain_bwd_compute(D_own, ma, mb, o, (step == 6 || step == 8 || step == 11) ? bar_dread : 0u);
                     if (step == 7 || step == 8) { T2_STAMP(); mbar_wait(bar_wg, ph_wg); ph_wg ^= 1; T2_STAMP(); }
+                    if (step == 6) {
+                        // the head weight-gradient GEMM was issued behind "dH3 read" and still reads H3 from the slot: wait for it,
+                        // collect its four columns, then dZ3 may replace H3
+                        T2_STAMP(); mbar_wait(bar_d, ph_d); ph_d ^= 1; tc_fence_after(); T2_STAMP();
+                        uint32_t v[4];
+                        tmem_ld4(D_own + 16, v);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) dwh[k] += __uint_as_float(v[k]);
+                    }
                     drain_store(slot, f, o);
                     if (step == 7) drain_store(Q, f, stash);                                         // H1 back into Q (dZ3 is dead)
                     T2_SIGNAL(step == 8 ? bar_in2 : bar_in);
