@@ -23,6 +23,9 @@
 namespace tnerf {
 namespace t2 {
 
+#ifndef T2_FLUSH_NBUF
+#define T2_FLUSH_NBUF 6
+#endif
 constexpr int THREADS = 512;
 constexpr int C_DW3 = 0, C_DW2 = 128, C_DW0 = 320, C_D = 384;   // tensor-memory columns; accumulator of stream s at C_D + 64 s
 constexpr uint32_t S_W0 = 0, S_W1 = 16384, S_W2 = 49152, S_W3 = 98304, S_WH = 131072;
@@ -31,7 +34,7 @@ constexpr uint32_t S_X0 = 200704, S_X1 = 208896, S_DZH0 = 217088, S_DZH1 = 21913
 
 struct Misc {
     float xch[2][48];          // cross-warp carries of the compositing scans (a ray spans 2 warps at 64 samples, all 4 at 128)
-    uint64_t bar_w, bar_x[2], bar_in[2], bar_d[2], bar_head[2], bar_dzh[2], bar_g[2][2], bar_gfree[2], bar_xfree[2], bar_wg[2], bar_dread[2], bar_in2[2], bar_xq[2], bar_qfree[2];
+    uint64_t bar_w, bar_x[2], bar_in[2], bar_d[2], bar_head[2], bar_dzh[2], bar_g[2][2], bar_gfree[2], bar_xfree[2], bar_wg[2], bar_dread[2], bar_in2[2], bar_xq[2], bar_qfree[2], bar_fin[2];
     uint32_t tmem_slot;
 };
 
@@ -246,6 +249,11 @@ __device__ __forceinline__ void run_ops2(StreamIssuer<KX, 0>& a, StreamIssuer<KX
     if constexpr (OP < N_OPS) {
         a.template op<OP>(sb, t, n0);
         if (t < n1) b.template op<OP>(sb, t, n1);
+        // last tile: everything that adds into dW3 (operation 6) / dW2 (operation 7) has been issued by this thread -- one commit
+        // tells the sample warps that the accumulator is final (early gradient flush, see the end of their role)
+        if constexpr (OP == 6 || OP == 7) {
+            if (t == n0 - 1) { if (elect_one()) tc_commit(a.mb + (uint32_t)offsetof(Misc, bar_fin) + 8u * (OP - 6)); __syncwarp(); }
+        }
         run_ops2<OP + 1>(a, b, sb, t, n0, n1);
     }
 }
@@ -298,6 +306,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             mbar_init(smem_u32(&ms.bar_in2[s]), 4);
             mbar_init(smem_u32(&ms.bar_xq[s]), 2);
             mbar_init(smem_u32(&ms.bar_qfree[s]), 1);
+            mbar_init(smem_u32(&ms.bar_fin[s]), 1);
         }
         fence_barrier_init();
     }
@@ -338,6 +347,13 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
     }
 #endif
     float* slab = p.slabs + (size_t)blockIdx.x * p.sm.total;
+    // early gradient flush (dW3 / dW2 by the sample warps under the last tile's tail): needs the single issuer warp (its commits tell
+    // when the accumulators are final) and the one-vector flush
+#if defined(T2_NO_MERGE) || defined(T2_NO_EARLY)
+    const bool early_flush = false;
+#else
+    const bool early_flush = UNROLL && (p.S == 128 || p.sync_streams > 0) && p.bulk_reduce && n_my[0] > 0;
+#endif
 
     if (wg == 3) {
         TN_SETMAXNREG_DEC(32);
@@ -642,20 +658,59 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             T2_STAMP();
             if (more) encode(tile + nstreams, z_next, gap_next);
             T2_STAMP();
+            if (!more) break;                                    // last tile: nothing to store (and the early gradient flush is waiting)
             if (t >= 0) {
                 mbar_wait(bar_qfree, ph_qfree); ph_qfree ^= 1;   // dH0 has completed: the Q slot is free
                 T2_STAMP();
             }
-            if (more) store_x(XQ, bar_xq);                       // early copy for layer 0 of the next tile
+            store_x(XQ, bar_xq);                                 // early copy for layer 0 of the next tile
             if (t >= 0) {
                 mbar_wait(bar_xfree, ph_xfree); ph_xfree ^= 1;   // last GEMM of the tile has completed: X may be replaced
                 T2_STAMP();
             }
-            if (more) { store_x(X, bar_x); z_cur = z_next; gap_cur = gap_next; }
+            store_x(X, bar_x); z_cur = z_next; gap_cur = gap_next;
         }
         loss_acc = warp_sum(loss_acc);
 #pragma unroll
         for (int k = 0; k < 4; ++k) hb[k] = warp_sum(hb[k]);
+        if (early_flush) {
+            // ---- early gradient flush: dW3 and dW2 (160 of the CTA's 265 KB) are final well before the last tile ends (after its
+            //      operations 6 / 7) and these four warps -- one per lane quadrant -- have nothing left to do.  The bulk-reduction
+            //      engine moves ~23 B/clk per SM, so the flush after the last GEMM was 6.4 us of every launch; started here it runs
+            //      under the rest of the last tile.  Staging: the W3 weight matrix (32 KB = two 32-column chunks) -- its last reader
+            //      is operation 6 of the last tile, the very event that makes dW3 final.  (Two 4 KB buffers in the spare 10 KB were
+            //      tried first: 8 KB in flight against the engine's ~1 k-cycle latency is 8 B/clk -- slower than no early flush.) ----
+            const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+            const int f = (warp & 3) * 32 + lane;
+            float* stage = reinterpret_cast<float*>(smem + S_W3);
+            const bool issuer_thread = warp == 8 && lane == 0;
+            int nchunk = 0;
+            auto push = [&](int tcol, int ncols, int off) {       // ncols is a multiple of 16
+                for (int c0 = 0; c0 < ncols; c0 += 32) {
+                    const int nc = ncols - c0 < 32 ? ncols - c0 : 32;
+                    if (nchunk >= 2) { if (issuer_thread) bulk_wait_group_read<1>(); bar_sync(3, 128); }
+                    float* st = stage + (nchunk & 1) * 4096;
+                    for (int c1 = 0; c1 < nc; c1 += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(tl + tcol + c0 + c1, v);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) st[(c1 + k) * 128 + f] = __uint_as_float(v[k]);
+                    }
+                    fence_proxy_async();
+                    bar_sync(3, 128);
+                    if (issuer_thread) { bulk_reduce_add_f32(p.slabs + off + c0 * 128, smem_u32(st), (uint32_t)nc * 512u); bulk_commit_group(); }
+                    ++nchunk;
+                }
+            };
+            mbar_wait(smem_u32(&ms.bar_fin[0]), 0);
+            tc_fence_after();
+            push(C_DW3, 128, p.sm.dw3);
+            mbar_wait(smem_u32(&ms.bar_fin[1]), 0);
+            tc_fence_after();
+            push(C_DW2, 128 + KX, p.sm.dw2);
+            if (issuer_thread) bulk_wait_group<0>();
+        }
         tc_fence_before();
         __syncthreads();                                          // (A) every GEMM of both streams has completed
         if (lane == 0) {
@@ -863,17 +918,21 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             //      in L2, no 39 MB of slabs, no reduce kernel).  Two staging halves per warpgroup; the issuing thread waits for
             //      the engine to have READ a half before it is refilled. ----
             float* G = p.slabs;
-            float* stage = reinterpret_cast<float*>(smem + (s ? S_P1 : S_P0));       // P and Q slot of this stream: 2 x 16 KB
+            // every GEMM has completed: the whole shared memory is free.  NBUF staging chunks of 16 KB per warpgroup (weights and
+            // slots region): a bulk reduction has a latency of a few thousand cycles, its throughput grows with the bytes in flight
+            constexpr int NBUF = T2_FLUSH_NBUF;
+            static_assert(2 * NBUF * 16384 <= S_MISC, "staging exceeds the shared memory below Misc");
+            float* stage = reinterpret_cast<float*>(smem + s * NBUF * 16384);
             const bool issuer_thread = (warp & 3) == 0 && lane == 0;
             int nchunk = 0;
             auto begin_chunk = [&]() -> float* {
-                if (nchunk >= 2) { if (issuer_thread) bulk_wait_group_read<1>(); bar_sync(4 + s, 128); }
-                return stage + (nchunk & 1) * 4096;
+                if (nchunk >= NBUF) { if (issuer_thread) bulk_wait_group_read<NBUF - 1>(); bar_sync(4 + s, 128); }
+                return stage + (nchunk % NBUF) * 4096;
             };
             auto end_chunk = [&](int off, int ncols) {
                 fence_proxy_async();
                 bar_sync(4 + s, 128);
-                if (issuer_thread) { bulk_reduce_add_f32(G + off, smem_u32(stage + (nchunk & 1) * 4096), (uint32_t)ncols * 512u); bulk_commit_group(); }
+                if (issuer_thread) { bulk_reduce_add_f32(G + off, smem_u32(stage + (nchunk % NBUF) * 4096), (uint32_t)ncols * 512u); bulk_commit_group(); }
                 ++nchunk;
             };
             auto push_tmem = [&](int tcol, int ncols, int off) {           // ncols is a multiple of 16
@@ -890,7 +949,11 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                     end_chunk(off + c0 * 128, nc);
                 }
             };
-            if (s == 0) { push_tmem(C_DW3, 128, p.sm.dw3); push_tmem(C_DW0, KX, p.sm.dw0); }
+            if (early_flush) {               // dW3 / dW2 are already on their way (sample warps); dW0 is split between the warpgroups
+                constexpr int N0 = KX >= 32 ? ((KX / 2 + 15) & ~15) : KX;
+                if (s == 0) push_tmem(C_DW0, N0, p.sm.dw0);
+                else if (KX > N0) push_tmem(C_DW0 + N0, KX - N0, p.sm.dw0 + N0 * 128);
+            } else if (s == 0) { push_tmem(C_DW3, 128, p.sm.dw3); push_tmem(C_DW0, KX, p.sm.dw0); }
             else push_tmem(C_DW2, 128 + KX, p.sm.dw2);
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
