@@ -34,7 +34,7 @@ constexpr uint32_t S_X0 = 200704, S_X1 = 208896, S_DZH0 = 217088, S_DZH1 = 21913
 
 struct Misc {
     float xch[2][48];          // cross-warp carries of the compositing scans (a ray spans 2 warps at 64 samples, all 4 at 128)
-    uint64_t bar_w, bar_x[2], bar_in[2], bar_d[2], bar_head[2], bar_dzh[2], bar_g[2][2], bar_gfree[2], bar_xfree[2], bar_wg[2], bar_dread[2], bar_in2[2], bar_xq[2], bar_qfree[2], bar_fin[2];
+    uint64_t bar_w, bar_x[2], bar_in[2], bar_d[2], bar_head[2], bar_dzh[2], bar_g[2][2], bar_gfree[2], bar_xfree[2], bar_wg[2], bar_dread[2], bar_xq[2], bar_qfree[2], bar_fin[2];
     uint32_t tmem_slot;
 };
 
@@ -132,7 +132,7 @@ struct StreamIssuer {
     static constexpr int XS = KX / 16;
     static constexpr uint32_t P = S_P0, Q = S_Q0, X = S_X0, DZH = S_DZH0;   // byte offsets of stream 0; the stream enters through the bases
     static_assert(S_P1 - S_P0 == 32768 && S_Q1 - S_Q0 == 32768 && S_X1 - S_X0 == 8192 && S_DZH1 - S_DZH0 == 2048, "stream strides");
-    enum { PH_X = 1, PH_IN = 2, PH_DZH = 4, PH_GF = 8, PH_DR = 16, PH_IN2 = 32, PH_XQ = 64 };
+    enum { PH_X = 1, PH_IN = 2, PH_DZH = 4, PH_GF = 8, PH_DR = 16, PH_XQ = 64 };
     uint32_t mb, tmem, ph = 0;      // shared-memory address of Misc, tensor-memory base, phase bits of the barriers this warp waits on
     long long* dbg;
     int dbg_n = 0;
@@ -212,9 +212,9 @@ struct StreamIssuer {
             wait(T2_BAR(bar_dread), PH_DR);                                                             // dH1 has been read out
             T2_ISSUE(gemm<XS>(D, aW0, bXk, i64kk, 0); tc_commit(bar_d););
         } else if constexpr (OP == 9) {     // dW1[:, :64] partial
-            // "dZ1 stored" has its own barrier: with the H0 recompute already in flight the drain threads can complete this phase AND
-            // the next one (H0 stored) before this warp looks -- two unobserved phases of ONE mbarrier alias to "not complete" (deadlock)
-            wait(T2_BAR(bar_in2), PH_IN2);                                                              // dZ1 stored
+            // dZ1 stored (step 8) AND the recomputed H0 stored (step 9): step 8 does not signal at all -- the same threads store H0
+            // afterwards and signal once.  (Two signals on ONE mbarrier here would let two phases complete unobserved, which alias
+            // to "not complete": a deadlock found by tools/stress_train.py in round 1; a second barrier cost a wait per tile.)
             wait(bar_in, PH_IN);
             T2_ISSUE(gemm<4>(D, aQ, bP_lo, i64kk, 0); tc_commit(mb + (uint32_t)offsetof(Misc, bar_g) + 16u * SS););
         } else if constexpr (OP == 10) {    // dW1[:, 64:] partial
@@ -225,8 +225,7 @@ struct StreamIssuer {
             T2_ISSUE(gemm<8>(D, aW1t, bQ, i64tt, 0); tc_commit(bar_d); tc_commit(T2_BAR(bar_qfree)););
         } else if constexpr (OP == 12) {    // F0 of the NEXT tile
             if (t + 1 < n) {
-                wait(T2_BAR(bar_dread), PH_DR);                                                         // dH0 has been read out
-                wait(T2_BAR(bar_xq), PH_XQ);                                                            // next tile's features staged in Q
+                wait(T2_BAR(bar_xq), PH_XQ);        // next tile's features staged in Q (2 sample warps) AND dH0 read out of the accumulator (4 drain warps)
                 T2_ISSUE(gemm<XS>(D, aW0, bXq, i64kk, 0); tc_commit(bar_d););
             }
         } else {                            // dW0 += dZ0 . X^T ; tile done
@@ -303,8 +302,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             mbar_init(smem_u32(&ms.bar_xfree[s]), 1);
             mbar_init(smem_u32(&ms.bar_wg[s]), 1);
             mbar_init(smem_u32(&ms.bar_dread[s]), 4);
-            mbar_init(smem_u32(&ms.bar_in2[s]), 4);
-            mbar_init(smem_u32(&ms.bar_xq[s]), 2);
+            mbar_init(smem_u32(&ms.bar_xq[s]), 6);            // 2 sample warps (features staged) + 4 drain warps (accumulator read; once up front for the first tile)
             mbar_init(smem_u32(&ms.bar_qfree[s]), 1);
             mbar_init(smem_u32(&ms.bar_fin[s]), 1);
         }
@@ -731,7 +729,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         const uint32_t D_own = tl + C_D + 64 * s, D_oth = tl + C_D + 64 * (1 - s);
         uint8_t* P = smem + (s ? S_P1 : S_P0);
         uint8_t* Q = smem + (s ? S_Q1 : S_Q0);
-        const uint32_t bar_in = smem_u32(&ms.bar_in[s]), bar_d = smem_u32(&ms.bar_d[s]), bar_wg = smem_u32(&ms.bar_wg[s]), bar_dread = smem_u32(&ms.bar_dread[s]), bar_in2 = smem_u32(&ms.bar_in2[s]), bar_xfree = smem_u32(&ms.bar_xfree[s]);
+        const uint32_t bar_in = smem_u32(&ms.bar_in[s]), bar_d = smem_u32(&ms.bar_d[s]), bar_wg = smem_u32(&ms.bar_wg[s]), bar_dread = smem_u32(&ms.bar_dread[s]), bar_xfree = smem_u32(&ms.bar_xfree[s]), bar_xq = smem_u32(&ms.bar_xq[s]);
         const uint32_t bar_g_own = smem_u32(&ms.bar_g[s][s]), bar_g_oth = smem_u32(&ms.bar_g[1 - s][s]);
         const uint32_t bar_gfree_own = smem_u32(&ms.bar_gfree[s]), bar_gfree_oth = smem_u32(&ms.bar_gfree[1 - s]);
         float dw1[64];                  // dW1[f][64 s + j]: this warpgroup's half of the columns, BOTH streams
@@ -864,7 +862,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                     uint32_t o[32];
                     const uint32_t ma = step == 6 ? mk3a : step == 7 ? mk2a : step == 8 ? mk1a : mk0a;
                     const uint32_t mb = step == 6 ? mk3b : step == 7 ? mk2b : step == 8 ? mk1b : mk0b;
-                    drain_bwd_compute(D_own, ma, mb, o, (step == 6 || step == 8 || step == 11) ? bar_dread : 0u);
+                    drain_bwd_compute(D_own, ma, mb, o, (step == 6 || step == 8) ? bar_dread : step == 11 ? bar_xq : 0u);
                     if (step == 7 || step == 8) { T2_STAMP(); mbar_wait(bar_wg, ph_wg); ph_wg ^= 1; T2_STAMP(); }
                     if (step == 6) {
                         // the head weight-gradient GEMM was issued behind "dH3 read" and still reads H3 from the slot: wait for it,
@@ -878,7 +876,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                     }
                     drain_store(slot, f, o);
                     if (step == 7) drain_store(Q, f, stash);                                         // H1 back into Q (dZ3 is dead)
-                    T2_SIGNAL(step == 8 ? bar_in2 : bar_in);
+                    if (step != 8) T2_SIGNAL(bar_in);          // dZ1 (step 8) is covered by the signal of step 9: same threads, stored before
                     if (step == 6 || step == 8) {                     // bias gradient of layer 3 / 1 = row sum of dZ3 / dZ1 (after the hand-off)
                         float sum = 0.f;
 #pragma unroll
@@ -889,6 +887,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                 }
                 return 0;
         };
+        if (lane == 0) mbar_arrive(bar_xq);       // the first tile's layer 0 has no accumulator to wait for
 #pragma unroll 1
         for (long long t = 0; t <= n_my[s]; ++t) {
             const bool tail = t == n_my[s];
