@@ -156,6 +156,9 @@ struct StreamIssuer {
         wait(T2_BAR(bar_xq), PH_XQ);
         T2_ISSUE(gemm<XS>(D, kmaj(sb, S_W0, 128), kmaj(sb + SS * (32768u >> 4), Q, 64), make_idesc_f16(128, 64, 0, 0), 0); tc_commit(T2_BAR(bar_d)););
     }
+    // "X buffer refilled" (needed from layer 2 on) is looked at right after layer 1 has been issued for both streams: the issuer would
+    // wait for the layer-1 drain then anyway, so the ~70 cycles even a completed mbarrier costs are off the serial path
+    __device__ __forceinline__ void wait_x() { wait(T2_BAR(bar_x), PH_X); }
     template <int OP>
     __device__ __forceinline__ void op(uint32_t sb, long long t, long long n) {
         constexpr uint32_t i64kk = make_idesc_f16(128, 64, 0, 0), i64kt = make_idesc_f16(128, 64, 0, 1), i64tk = make_idesc_f16(128, 64, 1, 0),
@@ -181,9 +184,8 @@ struct StreamIssuer {
         if constexpr (OP == 0) {            // F1: H1 (F0 was issued early)
             wait(bar_in, PH_IN);
             T2_ISSUE(gemm<8>(D, aW1, bP, i64kt, 0); tc_commit(bar_d););
-        } else if constexpr (OP == 1) {     // F2: H2 (needs the refilled X buffer)
+        } else if constexpr (OP == 1) {     // F2: H2 (needs the refilled X buffer: wait_x() below)
             wait(bar_in, PH_IN);
-            wait(T2_BAR(bar_x), PH_X);
             T2_ISSUE(gemm<8>(D, aW2h, bQ, i64kt, 0); gemm<XS>(D, aW2x, bXk, i64kk, 1); tc_commit(bar_d););
         } else if constexpr (OP == 2) {     // F3: H3
             wait(bar_in, PH_IN);
@@ -240,6 +242,7 @@ template <int OP, int KX, int SS>
 __device__ __forceinline__ void run_ops(StreamIssuer<KX, SS>& a, uint32_t sb, long long t, long long n) {
     if constexpr (OP < N_OPS) {
         a.template op<OP>(sb, t, n);
+        if constexpr (OP == 0) a.wait_x();
         run_ops<OP + 1>(a, sb, t, n);
     }
 }
@@ -248,6 +251,7 @@ __device__ __forceinline__ void run_ops2(StreamIssuer<KX, 0>& a, StreamIssuer<KX
     if constexpr (OP < N_OPS) {
         a.template op<OP>(sb, t, n0);
         if (t < n1) b.template op<OP>(sb, t, n1);
+        if constexpr (OP == 0) { a.wait_x(); if (t < n1) b.wait_x(); }
         // last tile: everything that adds into dW3 (operation 6) / dW2 (operation 7) has been issued by this thread -- one commit
         // tells the sample warps that the accumulator is final (early gradient flush, see the end of their role)
         if constexpr (OP == 6 || OP == 7) {
