@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
 #if defined(T2_NO_MERGE) || defined(T2_NO_EARLY)
     const bool early_flush = false;
 #else
-    const bool early_flush = UNROLL && (p.S == 128 || p.sync_streams > 0) && p.bulk_reduce && n_my[0] > 0;
+    const bool early_flush = (p.S == 128 || p.sync_streams > 0) && p.bulk_reduce && n_my[0] > 0;
 #endif
 
     if (wg == 3) {
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
 #ifdef T2_NO_MERGE
         if (false) {
 #else
-        if (UNROLL && (p.S == 128 || p.sync_streams > 0)) {       // streams in phase: one warp issues for both (see StreamIssuer)
+        if (p.S == 128 || p.sync_streams > 0) {       // streams in phase: one warp issues for both (see StreamIssuer)
 #endif
             if (warp == 12) issuer_loop_merged<KX>(ms, sbase, tmem, n_my[0], n_my[1], idbg);
         } else {
