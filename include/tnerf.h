@@ -93,6 +93,8 @@ int  tnerf_set_encoding(tnerf_handle* h, int num_freqs, int include_input);
  *   "bulk_reduce" 1 = CTAs add their gradients into one vector with bulk async reductions, 0 = per-CTA slabs summed in order;
  *   "unroll_from" tiles per stream from which the unrolled tile program is used (tuning / tests). */
 int  tnerf_set_option(tnerf_handle* h, const char* name, int value);
+/* the value in EFFECT for an option ("train_sync", "bulk_reduce": 0 / 1 after defaults; "unroll_from": as set); -1 = unknown name */
+int  tnerf_get_option(const tnerf_handle* h, const char* name);
 /* Developer hook: a device buffer of 2048 int64 that receives clock64() phase stamps of CTA 0 of the fused
  * forward kernel (tools/trace_fwd.py); NULL disables it. */
 int  tnerf_set_debug_buffer(tnerf_handle* h, void* buf);
@@ -183,7 +185,10 @@ int tnerf_render_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, long lo
  * GradScaler semantics of src/train.py:81,126 (scaler.scale(loss).backward()) on the device: loss_scale_dev (1 device float, e.g.
  * tnerf_scaler.state) replaces the built-in power-of-two loss scale of the tensor-core path (NULL = built-in); found_inf (1 device
  * float or NULL) is SET TO 1 when the step overflowed -- a scaled head gradient beyond 2^10 (the fp16 operands of the backward chain
- * would saturate), or a non-finite loss / gradient.  It is never cleared here. */
+ * would saturate), or a non-finite loss / gradient.  It is never cleared here.
+ * grads = NULL (tensor-core path, "bulk_reduce" in effect): the gradient is LEFT in the handle as the training kernel's one sum
+ * vector (already divided by the loss scale, accumulating over calls) and the next tnerf_optimizer_step with bit 1 of `repack` set
+ * gathers it from there -- the gradient scatter launch disappears from the step. */
 int tnerf_train_fwd_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, const float* target,
                         long long n_rays, float near_, float far_, int n_samples, const float* jitter,
                         int white_bkgd, int precision, float loss_denom, float* comp_rgb, float* loss_sum,
@@ -220,8 +225,10 @@ typedef struct tnerf_scaler {
 
 /* a9 + (f) N1: the optimiser step of the training loop as ONE launch: Adam as above (inv_scale = 1) on the flat parameter
  * vector, the gradient vector cleared for the next step (grads[0 .. n_clear), n_clear >= n so a trailing loss slot is cleared
- * too; their old values go to tail_out if non-NULL) and -- repack != 0 -- the fp16 operand image of the tensor-core kernels refreshed in place (replaces memset +
+ * too; their old values go to tail_out if non-NULL) and -- bit 0 of repack -- the fp16 operand image of the tensor-core kernels refreshed in place (replaces memset +
  * tnerf_adam_step + tnerf_pack_weights; needs the handle's parameters bound as views of `params` in state_dict order).
+ * Bit 1 of repack: grads[0 .. n) is NOT read -- the gradient is gathered from the sum vector a preceding tnerf_train_fwd_bwd with
+ * grads = NULL left in the handle (and cleared there); grads[n .. n_clear), e.g. the loss slot, is read and cleared as usual.
  * scaler_host (HOST struct, may be NULL): GradScaler semantics as described at tnerf_scaler; `step` is then only used when
  * scaler_host is NULL. */
 int tnerf_optimizer_step(tnerf_handle* h, float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n,

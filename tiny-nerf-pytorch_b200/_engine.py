@@ -55,6 +55,7 @@ _SIGS = {
     "tnerf_param_count": (_ll, [_p]),
     "tnerf_set_encoding": (_i, [_p, _i, _i]),
     "tnerf_set_option": (_i, [_p, C.c_char_p, _i]),
+    "tnerf_get_option": (_i, [_p, C.c_char_p]),
     "tnerf_set_debug_buffer": (_i, [_p, _p]),
     "tnerf_fused_supported": (_i, [_p]),
     "tnerf_pack_weights": (_i, [_p, _p]),
@@ -199,6 +200,10 @@ class ModelHandle:
     def set_option(self, name: str, value: int) -> None:
         """schedule options of the fused training kernel (include/tnerf.h, tnerf_set_option); -1 = built-in choice"""
         check(lib().tnerf_set_option(self.h, name.encode(), int(value)), "tnerf_set_option")
+
+    def get_option(self, name: str) -> int:
+        """the value in effect (defaults resolved); -1 = unknown option"""
+        return int(lib().tnerf_get_option(self.h, name.encode()))
 
     def ensure_packed(self, force: bool = False) -> None:
         ps = self.bind()

@@ -234,6 +234,7 @@ void tnerf_destroy(tnerf_handle* h) {
     if (h->packed) cudaFree(h->packed);
     if (h->slabs) cudaFree(h->slabs);
     if (h->auto_scale) cudaFree(h->auto_scale);
+    if (h->gather_map) cudaFree(h->gather_map);
     if (h->jitter_scratch) cudaFree(h->jitter_scratch);
     delete h;
 }
@@ -251,6 +252,15 @@ int tnerf_set_option(tnerf_handle* h, const char* name, int value) {
     else if (n == "unroll_from") h->opt_unroll_from = value;
     else return bad("tnerf_set_option: unknown option");
     return 0;
+}
+int tnerf_get_option(const tnerf_handle* h, const char* name) {
+    if (!h || !name) return -1;
+    const std::string n(name);
+    const int sync = h->opt_train_sync >= 0 ? (h->opt_train_sync != 0) : 1;
+    if (n == "train_sync") return sync;
+    if (n == "bulk_reduce") return h->opt_bulk_reduce >= 0 ? (h->opt_bulk_reduce != 0) : sync;
+    if (n == "unroll_from") return h->opt_unroll_from;
+    return -1;
 }
 int tnerf_set_debug_buffer(tnerf_handle* h, void* buf) {
     if (!h) return bad("NULL handle");
@@ -386,8 +396,9 @@ int tnerf_train_fwd_bwd(tnerf_handle* h, const tnerf_ray_source* rays_host, cons
                         float* comp_rgb, float* loss_sum, float* grads, const float* loss_scale_dev, float* found_inf, void* stream) {
     TN_ON_DEVICE(h);
     if (n_rays == 0) return 0;
-    if (!h || h->params.empty() || !target || !grads || !loss_sum || n_rays < 0 || n_samples < 1 || !(loss_denom > 0.f))
+    if (!h || h->params.empty() || !target || !loss_sum || n_rays < 0 || n_samples < 1 || !(loss_denom > 0.f))
         return bad("tnerf_train_fwd_bwd: invalid argument");
+    if (!grads && precision != TNERF_PREC_F16_TC) return bad("tnerf_train_fwd_bwd: grads = NULL (gradient left for the gathering optimiser launch) is a tensor-core path feature");
     if (int e = check_source(rays_host)) return e;
     const RaySource rs = to_device_source(rays_host);
     if (precision == TNERF_PREC_F16_TC)
@@ -459,6 +470,14 @@ int tnerf_optimizer_step(tnerf_handle* h, float* params, float* grads, float* ex
                          const tnerf_scaler* scaler_host, void* stream) {
     DeviceGuard device_guard_(h ? h->device : device_of(params));
     if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || n_clear < n || step < 1) return bad("tnerf_optimizer_step: invalid argument");
+    const int* gmap = nullptr;
+    float* gsum = nullptr;
+    if (repack & 2) {        // the gradient is the handle's pending sum (tnerf_train_fwd_bwd with grads = NULL), gathered by the optimiser launch
+        if (!h || !h->gather_map || h->gather_n != n || !h->slabs) return bad("tnerf_optimizer_step: no pending gradient sum (call tnerf_train_fwd_bwd with grads = NULL first)");
+        gmap = h->gather_map; gsum = reinterpret_cast<float*>(h->slabs);
+        h->slab_pending = false; h->slab0_zero = true;      // every element the training kernel writes is read and cleared by this launch
+    }
+    repack &= 1;
     RepackMap mp{};
     if (repack) {
         if (!params_are_flat(h, params) || n != h->param_count) return bad("tnerf_optimizer_step: repack needs the handle's parameters bound as one flat vector");
@@ -466,7 +485,7 @@ int tnerf_optimizer_step(tnerf_handle* h, float* params, float* grads, float* ex
     }
     ScalerArgs sc;
     if (int e = to_scaler_args(scaler_host, sc)) return e;
-    return launch_adam_fused(params, grads, exp_avg, exp_avg_sq, n, n_clear, step, lr, beta1, beta2, eps, tail_out, mp, sc, (cudaStream_t)stream);
+    return launch_adam_fused(params, grads, exp_avg, exp_avg_sq, n, n_clear, step, lr, beta1, beta2, eps, tail_out, mp, sc, gmap, gsum, (cudaStream_t)stream);
 }
 int tnerf_allreduce_adam_step(tnerf_handle* h, float* params, float* exp_avg, float* exp_avg_sq, long long n, const float* const* peer_grads,
                               unsigned int* const* peer_flags, int world, int rank, unsigned int epoch, int step, float lr,

@@ -47,6 +47,9 @@ struct tnerf_handle {
     void* packed = nullptr; size_t packed_bytes = 0;   // fp16 operand image (device)
     void* slabs = nullptr;  size_t slab_bytes = 0;     // per-CTA partial weight gradients
     bool slab0_zero = false;                           // slab 0 is all zeros (it is the accumulation target of the bulk-reduction mode)
+    bool slab_pending = false;                         // slab 0 holds an unscaled gradient sum waiting for the gathering optimiser launch
+    int* gather_map = nullptr; long long gather_n = 0; // parameter i <- slab element gather_map[i] (tnerf_train_fwd_bwd with grads = NULL;
+                                                       // bit 30: the sum of four elements 4 apart -- head biases), tnerf_train.cu
     int sm_count = 0;
     long long wide_version = 0;           // bumped by every pack of the hidden=256 image (the kernel's constant table follows it)
     bool fused_ok = false;

@@ -577,7 +577,8 @@ __device__ __forceinline__ void scaler_decide(const ScalerArgs& sc, bool skip, b
 // carries GradScaler.step()/update(): an overflowed step leaves parameters and moments untouched and halves the loss scale.
 __global__ void adam_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                   long long n, long long n_clear, float lr_over_bc1, float inv_sqrt_bc2, float lr, float b1, float b2, float eps,
-                                  float* __restrict__ tail_out, const __grid_constant__ RepackMap mp, const ScalerArgs sc) {
+                                  float* __restrict__ tail_out, const __grid_constant__ RepackMap mp, const ScalerArgs sc,
+                                  const int* __restrict__ gmap, float* __restrict__ gsum) {
     __shared__ float dec[3];
     asm volatile("griddepcontrol.wait;" ::: "memory");       // programmatic stream serialisation: set up under the previous kernel's tail
     if (sc.state) {
@@ -588,8 +589,17 @@ __global__ void adam_fused_kernel(float* __restrict__ p, float* __restrict__ g, 
     const bool skip = sc.state && dec[0] != 0.f;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n_clear) return;
-    const float gi = g[i];
-    g[i] = 0.f;
+    float gi;
+    if (gmap && i < n) {
+        // the gradient straight from the training kernel's ONE sum vector (tensor-memory order, already divided by the loss scale):
+        // parameter i <- element gmap[i]; no scatter kernel in between.  The elements read are cleared for the next step.
+        int e = gmap[i];
+        if (e & (1 << 30)) {             // head biases: four per-warp partial sums, 4 elements apart
+            e &= ~(1 << 30);
+            gi = (gsum[e] + gsum[e + 4]) + (gsum[e + 8] + gsum[e + 12]);
+            gsum[e] = 0.f; gsum[e + 4] = 0.f; gsum[e + 8] = 0.f; gsum[e + 12] = 0.f;
+        } else { gi = gsum[e]; gsum[e] = 0.f; }
+    } else { gi = g[i]; g[i] = 0.f; }
     if (i >= n) { if (tail_out) tail_out[i - n] = gi; return; }      // e.g. the loss slot behind the gradient
     if (skip) return;
     const float mi = fmaf(1.f - b1, gi - m[i], m[i]);
@@ -823,7 +833,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, int s
     return count_launch();
 }
 int launch_adam_fused(float* p, float* g, float* m, float* v, long long n, long long n_clear, int step, float lr, float b1, float b2,
-                      float eps, float* tail_out, const RepackMap& mp, const ScalerArgs& sc, cudaStream_t s) {
+                      float eps, float* tail_out, const RepackMap& mp, const ScalerArgs& sc, const int* gmap, float* gsum, cudaStream_t s) {
     if (n_clear <= 0) return 0;
     const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
     cudaLaunchConfig_t cfg{};
@@ -831,7 +841,7 @@ int launch_adam_fused(float* p, float* g, float* m, float* v, long long n, long 
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 4) ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, adam_fused_kernel, p, g, m, v, n, n_clear, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), lr, b1, b2, eps, tail_out, mp, sc);
+    cudaLaunchKernelEx(&cfg, adam_fused_kernel, p, g, m, v, n, n_clear, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), lr, b1, b2, eps, tail_out, mp, sc, gmap, gsum);
     return count_launch();
 }
 int launch_allreduce_adam(float* p, float* m, float* v, long long n, const float* const* peer_grads, unsigned int* const* peer_flags,

@@ -3,6 +3,7 @@
 // src/train.py:114-126 in ONE launch) followed by the gradient scatter below.  Also here: the device-side choice of the loss
 // scale for upstream-gradient calls and the overflow flag of the GradScaler semantics (src/train.py:81,126-128).
 #include <cstdlib>
+#include <vector>
 #include "tnerf_train.cuh"
 
 namespace tnerf {
@@ -93,6 +94,45 @@ int launch_found_inf(const float* g, long long n, float* found, cudaStream_t s) 
     return count_launch();
 }
 
+// parameter index -> element of the tensor-memory-ordered sum vector: the inverse of reduce_slabs_kernel's scatter, built once per
+// handle on the host and kept on the device (tnerf_train_fwd_bwd with grads = NULL leaves the gradient in that vector; the optimiser
+// launch gathers through this map).  Bit 30 marks the head biases: the sum of four per-warp partials, 4 elements apart.
+static int build_gather_map(tnerf_handle* h, const SlabMap& sm, int D, int Kx, cudaStream_t s) {
+    if (h->gather_map && h->gather_n == h->param_count) return 0;
+    std::vector<int> map((size_t)h->param_count, -1);
+    const long long* off = h->offsets.data();
+    const int fan2 = 128 + D;
+    auto put = [&](long long dst, int e) { if (dst >= 0 && dst < h->param_count) map[(size_t)dst] = e; };
+    for (int c = 0; c < Kx; ++c)
+        for (int m = 0; m < 128; ++m) {
+            const int e = sm.dw0 + c * 128 + m;
+            if (c < D) put(off[0] + (long long)m * D + c, e);
+            else if (c == Kx - 1) put(off[1] + m, e);
+        }
+    for (int c = 0; c < 128; ++c)
+        for (int m = 0; m < 128; ++m) {
+            put(off[2] + (long long)m * 128 + c, sm.dw1 + c * 128 + m);
+            put(off[6] + (long long)m * 128 + c, sm.dw3 + c * 128 + m);
+        }
+    for (int c = 0; c < 128 + Kx; ++c)
+        for (int m = 0; m < 128; ++m) {
+            const int e = sm.dw2 + c * 128 + m;
+            if (c < 128 || c - 128 < D) put(off[4] + (long long)m * fan2 + c, e);
+            else if (c - 128 == Kx - 1) put(off[5] + m, e);
+        }
+    for (int o = 0; o < 4; ++o)
+        for (int f = 0; f < 128; ++f) put(o == 0 ? off[8] + f : off[10] + (long long)(o - 1) * 128 + f, sm.dwh + o * 128 + f);
+    for (int f = 0; f < 128; ++f) { put(off[3] + f, sm.db1 + f); put(off[7] + f, sm.db3 + f); }
+    for (int o = 0; o < 4; ++o) put(o == 0 ? off[9] : off[11] + (o - 1), (sm.hb + o) | (1 << 30));
+    for (int v : map) if (v < 0) { set_error("fused train: gather map incomplete (unexpected parameter layout)"); return -6; }
+    if (h->gather_map) cudaFree(h->gather_map);
+    cudaError_t e = cudaMalloc(&h->gather_map, map.size() * sizeof(int));
+    if (e != cudaSuccess) { set_error("cudaMalloc(gather map) failed"); h->gather_map = nullptr; return (int)e; }
+    cudaMemcpyAsync(h->gather_map, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice, s);   // pageable source: staged before the call returns
+    h->gather_n = h->param_count;
+    return 0;
+}
+
 int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, float fr, int S, const float* jitter, int white,
                 const float* target, float loss_denom, const float* gC, const float* gD, const float* gA, const float* gW,
                 float grad_scale, const float* grad_scale_dev, float* found, float* comp, float* loss_sum, float* grads, cudaStream_t s) {
@@ -166,8 +206,17 @@ int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, flo
     const long long grid = (p.n_tiles + 1) / 2 < h->sm_count ? (p.n_tiles + 1) / 2 : h->sm_count;
     p.bulk_reduce = bulk ? 1 : 0;
     p.sync_streams = sync;
-    if (bulk && !h->slab0_zero) cudaMemsetAsync(h->slabs, 0, (size_t)sm.total * sizeof(float), s);
+    // grads == NULL: leave the (unscaled) sum in the ONE vector for the optimiser launch to gather from -- no scatter kernel
+    const bool leave = grads == nullptr;
+    if (leave) {
+        if (!bulk) { set_error("fused train: grads = NULL needs the one-vector gradient flush (option bulk_reduce)"); return -7; }
+        if (int rc = build_gather_map(h, sm, fp.D, Kx, s)) return rc;
+        p.unscale = 1;
+    }
+    if (!leave && h->slab_pending) { set_error("fused train: a gradient sum is pending (tnerf_train_fwd_bwd with grads = NULL): run the gathering tnerf_optimizer_step first"); return -8; }
+    if (bulk && !h->slab0_zero && !h->slab_pending) cudaMemsetAsync(h->slabs, 0, (size_t)sm.total * sizeof(float), s);
     if (int rc = fused_train2(h, fp, p, Kx, (int)grid, s)) return rc;
+    if (leave) { h->slab0_zero = false; h->slab_pending = true; return 0; }     // pending: cleared element by element by the gathering optimiser launch
     h->slab0_zero = bulk;               // the scatter kernel leaves slab 0 cleared in bulk mode; otherwise it holds a CTA's partial sums
     ReduceArgs ra{};
     ra.slabs = p.slabs; ra.n_slabs = bulk ? 1 : (int)grid; ra.zero_after = bulk ? 1 : 0; ra.sm = sm; ra.D = fp.D; ra.Kx = Kx; ra.inv_scale = 1.f / p.scale; ra.scale_dev = p.scale_dev; ra.grads = grads;

@@ -27,6 +27,8 @@ struct TrainParams {
     long long* debug;          // optional clock64 phase stamps of CTA 0 (tools/trace_train.py)
     int bulk_reduce;           // two-stream kernel: add the CTA's gradients into ONE vector (slabs[0 .. sm.total)) with bulk async reductions
     int sync_streams;          // the two streams of a CTA keep the same tile phase (dW1 halves drained where they are produced); -1 = host default
+    int unscale;               // bulk-reduction flush only: the flush divides by the loss scale, so the ONE gradient vector holds unscaled sums
+                               // (the optimiser launch then gathers from it directly: no scatter kernel, tnerf_train_fwd_bwd with grads = NULL)
     float* found;              // optional overflow flag (GradScaler's found_inf): set to 1 when a head gradient leaves the fp16-safe range or is not finite
 };
 

@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         const bool jit_rng = p.jitter == nullptr && p.rs.jitter_seed != 0;       // stratified jitter drawn in-kernel (Philox)
         const bool jit = p.jitter != nullptr || jit_rng;
         const float gscale = p.scale_dev ? *p.scale_dev : p.scale;
+        const float inv_g = p.unscale ? __frcp_rn(gscale) : 1.f;      // power-of-two scales: exact
         const float bs = p.b_sigma[0], br = p.b_rgb[0], bg = p.b_rgb[1], bb = p.b_rgb[2];
         float hb[4] = {0.f, 0.f, 0.f, 0.f}, loss_acc = 0.f;
         bool overflow = false;          // a scaled head gradient left the fp16-safe range (or is not finite): GradScaler's found_inf
@@ -697,7 +698,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                         tmem_ld16(tl + tcol + c0 + c1, v);
                         tc_wait_ld();
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) st[(c1 + k) * 128 + f] = __uint_as_float(v[k]);
+                        for (int k = 0; k < 16; ++k) st[(c1 + k) * 128 + f] = __uint_as_float(v[k]) * inv_g;
                     }
                     fence_proxy_async();
                     bar_sync(3, 128);
@@ -718,7 +719,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (p.bulk_reduce) atomicAdd(p.slabs + p.sm.hb + (warp - 8) * 4 + k, hb[k]);
+                if (p.bulk_reduce) atomicAdd(p.slabs + p.sm.hb + (warp - 8) * 4 + k, hb[k] * inv_g);
                 else slab[p.sm.hb + (warp - 8) * 4 + k] = hb[k];
             }
             if (p.loss_sum && loss_acc != 0.f) atomicAdd(p.loss_sum, loss_acc);
@@ -745,6 +746,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
         uint32_t mk0a = 0u, mk0b = 0u, mk1a = 0u, mk1b = 0u, mk2a = 0u, mk2b = 0u, mk3a = 0u, mk3b = 0u;   // ReLU masks of H0 (recomputed), H1, H2, H3
         float dwh[4] = {0.f, 0.f, 0.f, 0.f}, db1 = 0.f, db3 = 0.f;
         const float b1 = p.b1[f], b3 = p.b3[f];
+        const float inv_g = p.unscale ? __frcp_rn(p.scale_dev ? *p.scale_dev : p.scale) : 1.f;
         uint32_t ph_d = 0, ph_g_own = 0, ph_g_oth = 0, ph_wg = 0, ph_xf = 0;
         long long g_oth_left = n_my[1 - s];
         const bool inphase = p.S == 128 || p.sync_streams > 0;
@@ -947,7 +949,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                         tmem_ld16(tl + tcol + c0 + c1, v);
                         tc_wait_ld();
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) st[(c1 + k) * 128 + f] = __uint_as_float(v[k]);
+                        for (int k = 0; k < 16; ++k) st[(c1 + k) * 128 + f] = __uint_as_float(v[k]) * inv_g;
                     }
                     end_chunk(off + c0 * 128, nc);
                 }
@@ -962,13 +964,13 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
             for (int h2 = 0; h2 < 2; ++h2) {
                 float* st = begin_chunk();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) st[j * 128 + f] = dw1[h2 * 32 + j];
+                for (int j = 0; j < 32; ++j) st[j * 128 + f] = dw1[h2 * 32 + j] * inv_g;
                 end_chunk(p.sm.dw1 + (64 * s + 32 * h2) * 128, 32);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) atomicAdd(G + p.sm.dwh + k * 128 + f, dwh[k]);
-            atomicAdd(G + p.sm.db1 + f, db1);
-            atomicAdd(G + p.sm.db3 + f, db3);
+            for (int k = 0; k < 4; ++k) atomicAdd(G + p.sm.dwh + k * 128 + f, dwh[k] * inv_g);
+            atomicAdd(G + p.sm.db1 + f, db1 * inv_g);
+            atomicAdd(G + p.sm.db3 + f, db3 * inv_g);
             if (issuer_thread) bulk_wait_group<0>();
             __syncthreads();                                      // (B)
             if (dbg) { dbg[255] = clock64(); dbg[252] = gtimer(); }

@@ -167,6 +167,12 @@ def render_weights(model, ro, o_stride, rd, n, S, near, far, jitter, white, prec
     return w
 
 
+# TNERF_GATHER=1: the optimiser launch gathers the gradient straight from the training kernel's sum vector (no scatter launch).  Off by
+# default: the gather is strided (parameter (f, k) <- element k * 128 + f) and the launch takes 22 us against 8.5 + 4.7 us for
+# Adam + scatter (cold, ncu) -- 157.6 instead of 149.2 us per step; it needs a transposing optimiser kernel to pay.
+_GATHER = os.environ.get("TNERF_GATHER", "0") == "1"
+
+
 class Trainer:
     """The training-step host path (src/train.py:106-128) on the fused kernels: one tnerf_train_fwd_bwd call (rays generated
     in-kernel from pose + pixel ids, MSE inside; training kernel + gradient scatter) and ONE optimiser launch (Adam + clearing
@@ -292,7 +298,7 @@ class Trainer:
         self.reduced = torch.zeros(self.P + 2, dtype=torch.float32, device=self.device)
 
     # ---- one optimisation step ------------------------------------------------------------------
-    def _finish(self):
+    def _finish(self, gather=False):
         """optimiser step: ONE launch (Adam + clearing of the next step's gradient vector + in-place refresh of the fp16
         operand image); with several ranks the same launch first all-reduces the gradient over NVLink peer memory"""
         call = self.steps                # parity of THIS call: selects the overflow flag / beta-power slots
@@ -318,7 +324,7 @@ class Trainer:
         sc = self._scaler_struct(self.gbuf[P + 1 + (call & 1):], self.gbuf[P + 1 + ((call + 1) & 1):], call)
         E.check(E.lib().tnerf_optimizer_step(self.h.h, E.ptr(self.flat), E.ptr(self.gbuf), E.ptr(self.exp_avg), E.ptr(self.exp_avg_sq), P,
                                              P + 1, self.steps, self.lr, self.betas[0], self.betas[1], self.eps, E.ptr(self.loss_out),
-                                             repack, sc, st),
+                                             repack | (2 if gather else 0), sc, st),
                 "tnerf_optimizer_step")
         return self.loss_out
 
@@ -334,10 +340,14 @@ class Trainer:
                 self.scaler_state[0] = self._scale_init
             scale = self.scaler_state
             found = gbuf[P + 1:] if self.comm == "p2p" else gbuf[P + 1 + (self.steps & 1):]
+        # one process, tensor-core path, one-vector flush: the gradient stays in the training kernel's sum vector and the optimiser
+        # launch gathers it from there (no scatter launch); otherwise it is scattered into gbuf (the exchange vector of a multi-rank step)
+        gather = self.world == 1 and self.prec == E.PREC_F16_TC and _GATHER and self.h.get_option("bulk_reduce") == 1
         E.check(E.lib().tnerf_train_fwd_bwd(self.h.h, C.byref(rs), E.ptr(target), n, self.near, self.far, self.S, E.ptr(jitter),
-                                            int(self.white), self.prec, denom, None, E.ptr(gbuf[P:]), E.ptr(gbuf), E.ptr(scale), E.ptr(found), st),
+                                            int(self.white), self.prec, denom, None, E.ptr(gbuf[P:]), None if gather else E.ptr(gbuf),
+                                            E.ptr(scale), E.ptr(found), st),
                 "tnerf_train_fwd_bwd")
-        return self._finish()
+        return self._finish(gather)
 
     def step_pixels(self, c2w, H, W, focal, pixel_index, target, jitter=None, global_rays=None):
         """rays are generated in-kernel from the pose and the pixel ids (a1+a2 fused in); returns the loss (device, shape (1,)).
