@@ -432,6 +432,40 @@ def test_trainer_steps_match_oracle_adam(dev):
     opt.load_state_dict(sd)                                    # interchangeable with torch.optim.Adam (checkpoints)
 
 
+def test_gathering_optimizer_step_matches_the_scatter_path(dev, monkeypatch):
+    """tnerf_train_fwd_bwd with grads = NULL leaves the (unscaled) gradient in the training kernel's sum vector and
+    tnerf_optimizer_step (repack bit 1) gathers it: same parameters as the default path (scatter kernel + Adam) after a few steps --
+    reproducible accumulation order is not available in that mode, so the comparison carries the last-bit tolerance of the sums --
+    and an overflowed step leaves nothing behind in the vector."""
+    import engine
+    from encoding import PositionalEncoding
+    enc = PositionalEncoding(10, True).to(dev)
+    H, W, focal, n, S = 40, 40, 60.0, 2048, 64
+    pose = O.look_at_pose(0.7, 0.45).to(dev)
+    g = torch.Generator().manual_seed(77)
+    batches = [(torch.randint(0, H * W, (n,), generator=g).to(dev), torch.rand(n, 3, generator=g).to(dev), torch.rand(n, S, generator=g).to(dev))
+               for _ in range(4)]
+
+    def run(gather):
+        monkeypatch.setattr(engine, "_GATHER", gather)
+        model, _ = make_model((63, 128, 4, 2), 78, dev, 1.5)
+        tr = engine.Trainer(model, enc, n_samples=S)
+        losses = []
+        for k, (pix, tgt, jit) in enumerate(batches):
+            if k == 2:      # a poisoned batch in between: skipped, and the sum vector must come out clean
+                bad = tgt.clone(); bad[3, 0] = float("nan")
+                tr.step_pixels(pose, H, W, focal, pix, bad, jit)
+            losses.append(float(tr.step_pixels(pose, H, W, focal, pix, tgt, jit)))
+        assert tr.applied_steps() == len(batches)
+        return tr.flat.clone(), losses
+
+    p_scatter, l_scatter = run(False)
+    p_gather, l_gather = run(True)
+    d = (p_scatter - p_gather).abs()
+    assert d.max().item() <= 2e-4 and d.mean().item() <= 2e-6, (d.max().item(), d.mean().item())
+    assert max(abs(a - b) for a, b in zip(l_scatter, l_gather)) < 1e-4
+
+
 def test_optimizer_step_refreshes_operand_image_like_a_full_repack(dev):
     """tnerf_optimizer_step (Adam + clear gradient vector + in-place fp16 image refresh, one launch) against
     tnerf_adam_step followed by tnerf_pack_weights: same parameters, same moments, byte-identical image, cleared gradients."""

@@ -648,8 +648,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
                 T2_STAMP();
                 hb[0] += s0; hb[1] += s1; hb[2] += s2; hb[3] += s3;      // head bias gradients: per-thread partials, reduced at the end
                 // the hidden layers amplify |dZ| by a few units per layer at most: 2^10 at the heads keeps every fp16 operand of the
-                // backward chain far from 65504 (cvt.satfinite would clip silently); NaN fails the comparison too
-                overflow |= !(fmaxf(fmaxf(fabsf(s0), fabsf(s1)), fmaxf(fabsf(s2), fabsf(s3))) <= 1024.f);
+                // backward chain far from 65504 (cvt.satfinite would clip silently); a NaN fails its comparison too
+                overflow |= !(fabsf(s0) <= 1024.f) || !(fabsf(s1) <= 1024.f) || !(fabsf(s2) <= 1024.f) || !(fabsf(s3) <= 1024.f);   // (fmaxf would drop a NaN)
             };
             if (S == 64) composite(std::integral_constant<int, 64>{});
             else if (S == 128) composite(std::integral_constant<int, 128>{});
