@@ -627,7 +627,12 @@ static int kx_of(const tnerf_handle* h, int& L, int& inc) {
 
 // The constant table belongs to one (handle, pack version) at a time per device.  A launch for another owner first waits (on its
 // stream) for the last kernel that read the table, then uploads its own 6 KB: stream ordered, no host synchronisation.
-struct TableState { const tnerf_handle* owner = nullptr; long long version = -1; cudaEvent_t last_use = nullptr; };
+struct TableState {
+    const tnerf_handle* owner = nullptr; long long version = -1;
+    cudaEvent_t last_use = nullptr;       // last kernel that read the table (a new owner's upload waits for it)
+    cudaEvent_t uploaded = nullptr;       // the current owner's upload; a launch on ANOTHER stream waits for it (same owner, same version)
+    cudaStream_t upload_stream = nullptr;
+};
 static std::mutex g_table_mu;
 static TableState g_table[64];
 void wide_release(tnerf_handle* h) {
@@ -694,11 +699,16 @@ int fused_render_fwd_wide(tnerf_handle* h, const RaySource& rs, long long n, flo
     std::lock_guard<std::mutex> lk(g_table_mu);
     TableState& t = g_table[h->device & 63];
     if (!t.last_use && cudaEventCreateWithFlags(&t.last_use, cudaEventDisableTiming) != cudaSuccess) { set_error("wide fused fwd: cudaEventCreate failed"); return -6; }
+    if (!t.uploaded && cudaEventCreateWithFlags(&t.uploaded, cudaEventDisableTiming) != cudaSuccess) { set_error("wide fused fwd: cudaEventCreate failed"); return -6; }
     if (t.owner != h || t.version != h->wide_version) {
         if (t.owner) cudaStreamWaitEvent(s, t.last_use, 0);
         e = cudaMemcpyToSymbolAsync(wide::c_tail, p.image + 2ull * p.image_bytes, wide::TAIL_FLOATS * sizeof(float), 0, cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) { set_error("wide fused fwd: constant-bank upload failed"); return (int)e; }
         t.owner = h; t.version = h->wide_version;
+        cudaEventRecord(t.uploaded, s);
+        t.upload_stream = s;
+    } else if (t.upload_stream != s) {
+        cudaStreamWaitEvent(s, t.uploaded, 0);        // same table, other stream: the upload was only ordered on the stream that made it
     }
     kern<<<(unsigned)(2 * pairs), wide::THREADS, smem, s>>>(p);
     cudaEventRecord(t.last_use, s);
