@@ -234,7 +234,6 @@ void tnerf_destroy(tnerf_handle* h) {
     if (h->packed) cudaFree(h->packed);
     if (h->slabs) cudaFree(h->slabs);
     if (h->auto_scale) cudaFree(h->auto_scale);
-    if (h->gather_map) cudaFree(h->gather_map);
     if (h->jitter_scratch) cudaFree(h->jitter_scratch);
     delete h;
 }
@@ -470,13 +469,9 @@ int tnerf_optimizer_step(tnerf_handle* h, float* params, float* grads, float* ex
                          const tnerf_scaler* scaler_host, void* stream) {
     DeviceGuard device_guard_(h ? h->device : device_of(params));
     if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || n_clear < n || step < 1) return bad("tnerf_optimizer_step: invalid argument");
-    const int* gmap = nullptr;
-    float* gsum = nullptr;
-    if (repack & 2) {        // the gradient is the handle's pending sum (tnerf_train_fwd_bwd with grads = NULL), gathered by the optimiser launch
-        if (!h || !h->gather_map || h->gather_n != n || !h->slabs) return bad("tnerf_optimizer_step: no pending gradient sum (call tnerf_train_fwd_bwd with grads = NULL first)");
-        gmap = h->gather_map; gsum = reinterpret_cast<float*>(h->slabs);
-        h->slab_pending = false; h->slab0_zero = true;      // every element the training kernel writes is read and cleared by this launch
-    }
+    const bool gather = (repack & 2) != 0;      // the gradient is the handle's pending sum (tnerf_train_fwd_bwd with grads = NULL)
+    if (gather && (!h || !h->gplan.valid || h->gplan.n != n || !h->slabs || n_clear > n + 64))
+        return bad("tnerf_optimizer_step: no pending gradient sum (call tnerf_train_fwd_bwd with grads = NULL first)");
     repack &= 1;
     RepackMap mp{};
     if (repack) {
@@ -485,7 +480,12 @@ int tnerf_optimizer_step(tnerf_handle* h, float* params, float* grads, float* ex
     }
     ScalerArgs sc;
     if (int e = to_scaler_args(scaler_host, sc)) return e;
-    return launch_adam_fused(params, grads, exp_avg, exp_avg_sq, n, n_clear, step, lr, beta1, beta2, eps, tail_out, mp, sc, gmap, gsum, (cudaStream_t)stream);
+    if (gather) {
+        h->slab_pending = false; h->slab0_zero = true;      // every element the training kernel writes is read and cleared by this launch
+        return launch_adam_gather(params, grads, exp_avg, exp_avg_sq, n, n_clear, step, lr, beta1, beta2, eps, tail_out, mp, sc, h->gplan,
+                                  reinterpret_cast<float*>(h->slabs), (cudaStream_t)stream);
+    }
+    return launch_adam_fused(params, grads, exp_avg, exp_avg_sq, n, n_clear, step, lr, beta1, beta2, eps, tail_out, mp, sc, (cudaStream_t)stream);
 }
 int tnerf_allreduce_adam_step(tnerf_handle* h, float* params, float* exp_avg, float* exp_avg_sq, long long n, const float* const* peer_grads,
                               unsigned int* const* peer_flags, int world, int rank, unsigned int epoch, int step, float lr,

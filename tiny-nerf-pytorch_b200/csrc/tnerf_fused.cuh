@@ -185,7 +185,9 @@ struct ScalerArgs {
     unsigned int call;
 };
 int launch_adam_fused(float* p, float* g, float* m, float* v, long long n, long long n_clear, int step, float lr, float b1, float b2,
-                      float eps, float* tail_out, const RepackMap& mp, const ScalerArgs& sc, const int* gmap, float* gsum, cudaStream_t s);
+                      float eps, float* tail_out, const RepackMap& mp, const ScalerArgs& sc, cudaStream_t s);
+int launch_adam_gather(float* p, float* g, float* m, float* v, long long n, long long n_clear, int step, float lr, float b1, float b2,
+                       float eps, float* tail_out, const RepackMap& mp, const ScalerArgs& sc, const GatherPlan& plan, float* gsum, cudaStream_t s);
 int launch_allreduce_adam(float* p, float* m, float* v, long long n, const float* const* peer_grads, unsigned int* const* peer_flags,
                           int world, int rank, unsigned int epoch, int step, float lr, float b1, float b2, float eps, float* reduced_out,
                           float* zero_next, const RepackMap& mp, const ScalerArgs& sc, long long timeout_cycles, cudaStream_t s);

@@ -27,6 +27,18 @@ void set_error(const std::string& msg);
 // records a launch, returns the pending cudaError_t (0 if none)
 int count_launch();
 
+// How the optimiser launch reads the gradient straight out of the training kernel's sum vector (tensor-memory order: element
+// (column c, row m) of a block at c * 128 + m) -- tnerf_train_fwd_bwd with grads = NULL, tnerf_optimizer_step with repack bit 1.
+struct GatherSeg { int sb, C, ld, tile0; long long pb; };   // weight block: param[pb + m * ld + c] <- sum[sb + c * 128 + m], c < C, m < 128; 32 x 32 tiles
+struct GatherVec { int sb, n, first; long long pb; };       // vector: param[pb + j] <- sum[sb + j], j < n (biases, head weights); `first` = position in the vector pass
+struct GatherPlan {
+    int valid = 0, n_seg = 0, n_vec = 0, n_tiles = 0, n_vec_elems = 0, hb = 0;
+    GatherSeg seg[6];
+    GatherVec vec[8];
+    long long pb_hb[4];                                     // head biases: param[pb_hb[o]] <- sum[hb + o] + sum[hb + o + 4] + sum[hb + o + 8] + sum[hb + o + 12]
+    long long n = 0;
+};
+
 struct Workspace {   // grow-only device scratch owned by a handle
     void* ptr = nullptr; size_t bytes = 0;
     int reserve(size_t need);
@@ -48,8 +60,7 @@ struct tnerf_handle {
     void* slabs = nullptr;  size_t slab_bytes = 0;     // per-CTA partial weight gradients
     bool slab0_zero = false;                           // slab 0 is all zeros (it is the accumulation target of the bulk-reduction mode)
     bool slab_pending = false;                         // slab 0 holds an unscaled gradient sum waiting for the gathering optimiser launch
-    int* gather_map = nullptr; long long gather_n = 0; // parameter i <- slab element gather_map[i] (tnerf_train_fwd_bwd with grads = NULL;
-                                                       // bit 30: the sum of four elements 4 apart -- head biases), tnerf_train.cu
+    tnerf::GatherPlan gplan;                           // built by tnerf_train_fwd_bwd with grads = NULL (tnerf_train.cu)
     int sm_count = 0;
     long long wide_version = 0;           // bumped by every pack of the hidden=256 image (the kernel's constant table follows it)
     bool fused_ok = false;

@@ -577,8 +577,7 @@ __device__ __forceinline__ void scaler_decide(const ScalerArgs& sc, bool skip, b
 // carries GradScaler.step()/update(): an overflowed step leaves parameters and moments untouched and halves the loss scale.
 __global__ void adam_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                   long long n, long long n_clear, float lr_over_bc1, float inv_sqrt_bc2, float lr, float b1, float b2, float eps,
-                                  float* __restrict__ tail_out, const __grid_constant__ RepackMap mp, const ScalerArgs sc,
-                                  const int* __restrict__ gmap, float* __restrict__ gsum) {
+                                  float* __restrict__ tail_out, const __grid_constant__ RepackMap mp, const ScalerArgs sc) {
     __shared__ float dec[3];
     asm volatile("griddepcontrol.wait;" ::: "memory");       // programmatic stream serialisation: set up under the previous kernel's tail
     if (sc.state) {
@@ -589,17 +588,8 @@ __global__ void adam_fused_kernel(float* __restrict__ p, float* __restrict__ g, 
     const bool skip = sc.state && dec[0] != 0.f;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n_clear) return;
-    float gi;
-    if (gmap && i < n) {
-        // the gradient straight from the training kernel's ONE sum vector (tensor-memory order, already divided by the loss scale):
-        // parameter i <- element gmap[i]; no scatter kernel in between.  The elements read are cleared for the next step.
-        int e = gmap[i];
-        if (e & (1 << 30)) {             // head biases: four per-warp partial sums, 4 elements apart
-            e &= ~(1 << 30);
-            gi = (gsum[e] + gsum[e + 4]) + (gsum[e + 8] + gsum[e + 12]);
-            gsum[e] = 0.f; gsum[e + 4] = 0.f; gsum[e + 8] = 0.f; gsum[e + 12] = 0.f;
-        } else { gi = gsum[e]; gsum[e] = 0.f; }
-    } else { gi = g[i]; g[i] = 0.f; }
+    const float gi = g[i];
+    g[i] = 0.f;
     if (i >= n) { if (tail_out) tail_out[i - n] = gi; return; }      // e.g. the loss slot behind the gradient
     if (skip) return;
     const float mi = fmaf(1.f - b1, gi - m[i], m[i]);
@@ -609,6 +599,78 @@ __global__ void adam_fused_kernel(float* __restrict__ p, float* __restrict__ g, 
     const float pn = p[i] - lr_over_bc1 * (mi / denom);
     p[i] = pn;
     if (mp.valid) repack_param(mp, i, pn);
+}
+
+// The same optimiser launch with the gradient GATHERED from the training kernel's sum vector (tensor-memory order, already divided
+// by the loss scale) instead of read from a flat vector: the gradient-scatter launch disappears from the step.  A weight block sits
+// there as [column c][row m] while the parameter is [m][c]: 32 x 32 tiles go through shared memory, so the reads of the sum vector
+// (and its clearing) are coalesced along m and the parameter / moment traffic along c.  Blocks beyond the tiles handle the vectors
+// (biases, head weights), the four head biases (four per-warp partials each) and the tail of `g` (the loss slot).
+__device__ __forceinline__ void adam_apply(long long i, float gi, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                           float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps, const RepackMap& mp) {
+    const float mi = fmaf(1.f - b1, gi - m[i], m[i]);
+    const float vi = fmaf(v[i], b2, (1.f - b2) * gi * gi);
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    const float pn = p[i] - lr_over_bc1 * (mi / denom);
+    p[i] = pn;
+    if (mp.valid) repack_param(mp, i, pn);
+}
+__global__ void __launch_bounds__(256) adam_gather_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                   long long n, long long n_clear, float lr_over_bc1, float inv_sqrt_bc2, float lr, float b1, float b2, float eps,
+                                   float* __restrict__ tail_out, const __grid_constant__ RepackMap mp, const ScalerArgs sc,
+                                   const __grid_constant__ GatherPlan plan, float* __restrict__ gsum) {
+    __shared__ float dec[3];
+    __shared__ float tile[32][33];
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (sc.state) {
+        if (threadIdx.x == 0) scaler_decide(sc, sc.found && !(*sc.found == 0.f), blockIdx.x == 0, lr, b1, b2, dec);
+        __syncthreads();
+        lr_over_bc1 = dec[1]; inv_sqrt_bc2 = dec[2];
+    }
+    const bool skip = sc.state && dec[0] != 0.f;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if ((int)blockIdx.x < plan.n_tiles) {
+        int si = 0;
+        while (si + 1 < plan.n_seg && (int)blockIdx.x >= plan.seg[si + 1].tile0) ++si;
+        const GatherSeg sg = plan.seg[si];
+        const int t = (int)blockIdx.x - sg.tile0, c0 = (t >> 2) * 32, m0 = (t & 3) * 32;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {                 // rows of the sum vector: c fixed, m consecutive
+            const int c = c0 + ty + 8 * r;
+            float x = 0.f;
+            if (c < sg.C) { float* q = gsum + sg.sb + c * 128 + m0 + tx; x = *q; *q = 0.f; }
+            tile[ty + 8 * r][tx] = x;
+        }
+        __syncthreads();
+        if (skip) return;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {                 // rows of the parameter: m fixed, c consecutive
+            const int mm = m0 + ty + 8 * r, c = c0 + tx;
+            if (c < sg.C) adam_apply(sg.pb + (long long)mm * sg.ld + c, tile[tx][ty + 8 * r], p, m, v, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps, mp);
+        }
+        return;
+    }
+    const long long j = ((long long)blockIdx.x - plan.n_tiles) * 256 + threadIdx.x;
+    if (j < plan.n_vec_elems) {
+        int vi = 0;
+        while (vi + 1 < plan.n_vec && j >= plan.vec[vi + 1].first) ++vi;
+        const GatherVec vc = plan.vec[vi];
+        float* q = gsum + vc.sb + (j - vc.first);
+        const float gi = *q; *q = 0.f;
+        if (!skip) adam_apply(vc.pb + (j - vc.first), gi, p, m, v, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps, mp);
+    } else if (j < plan.n_vec_elems + 4) {
+        const int o = (int)(j - plan.n_vec_elems);
+        float* q = gsum + plan.hb + o;
+        const float gi = (q[0] + q[4]) + (q[8] + q[12]);
+        q[0] = 0.f; q[4] = 0.f; q[8] = 0.f; q[12] = 0.f;
+        if (!skip) adam_apply(plan.pb_hb[o], gi, p, m, v, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps, mp);
+    } else if (j < plan.n_vec_elems + 4 + (n_clear - n)) {   // the tail of the flat vector (loss slot): handed out and cleared
+        const long long i = n + (j - plan.n_vec_elems - 4);
+        const float gi = g[i];
+        g[i] = 0.f;
+        if (tail_out) tail_out[i - n] = gi;
+    }
 }
 
 // (e) ray-sharded data parallel: one-shot all-reduce of the flat [gradient | loss (| overflow flag)] vectors over NVLink peer memory,
@@ -833,7 +895,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, int s
     return count_launch();
 }
 int launch_adam_fused(float* p, float* g, float* m, float* v, long long n, long long n_clear, int step, float lr, float b1, float b2,
-                      float eps, float* tail_out, const RepackMap& mp, const ScalerArgs& sc, const int* gmap, float* gsum, cudaStream_t s) {
+                      float eps, float* tail_out, const RepackMap& mp, const ScalerArgs& sc, cudaStream_t s) {
     if (n_clear <= 0) return 0;
     const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
     cudaLaunchConfig_t cfg{};
@@ -841,7 +903,20 @@ int launch_adam_fused(float* p, float* g, float* m, float* v, long long n, long 
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 4) ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, adam_fused_kernel, p, g, m, v, n, n_clear, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), lr, b1, b2, eps, tail_out, mp, sc, gmap, gsum);
+    cudaLaunchKernelEx(&cfg, adam_fused_kernel, p, g, m, v, n, n_clear, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), lr, b1, b2, eps, tail_out, mp, sc);
+    return count_launch();
+}
+int launch_adam_gather(float* p, float* g, float* m, float* v, long long n, long long n_clear, int step, float lr, float b1, float b2,
+                       float eps, float* tail_out, const RepackMap& mp, const ScalerArgs& sc, const GatherPlan& plan, float* gsum, cudaStream_t s) {
+    const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+    const long long nvec = plan.n_vec_elems + 4 + (n_clear - n);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(plan.n_tiles + blocks_for(nvec, 256))); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 4) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, adam_gather_kernel, p, g, m, v, n, n_clear, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), lr, b1, b2, eps, tail_out, mp, sc,
+                       plan, gsum);
     return count_launch();
 }
 int launch_allreduce_adam(float* p, float* m, float* v, long long n, const float* const* peer_grads, unsigned int* const* peer_flags,

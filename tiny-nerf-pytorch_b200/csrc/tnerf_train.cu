@@ -94,42 +94,42 @@ int launch_found_inf(const float* g, long long n, float* found, cudaStream_t s) 
     return count_launch();
 }
 
-// parameter index -> element of the tensor-memory-ordered sum vector: the inverse of reduce_slabs_kernel's scatter, built once per
-// handle on the host and kept on the device (tnerf_train_fwd_bwd with grads = NULL leaves the gradient in that vector; the optimiser
-// launch gathers through this map).  Bit 30 marks the head biases: the sum of four per-warp partials, 4 elements apart.
-static int build_gather_map(tnerf_handle* h, const SlabMap& sm, int D, int Kx, cudaStream_t s) {
-    if (h->gather_map && h->gather_n == h->param_count) return 0;
-    std::vector<int> map((size_t)h->param_count, -1);
+// where every parameter's gradient sits in the tensor-memory-ordered sum vector: the inverse of reduce_slabs_kernel's scatter as a
+// short list of blocks and vectors (tnerf_train_fwd_bwd with grads = NULL leaves the gradient there; the gathering optimiser launch
+// transposes the weight blocks through shared memory so that both sides are coalesced)
+static int build_gather_plan(tnerf_handle* h, const SlabMap& sm, int D, int Kx) {
+    GatherPlan& g = h->gplan;
+    if (g.valid && g.n == h->param_count) return 0;
+    g = GatherPlan{};
     const long long* off = h->offsets.data();
-    const int fan2 = 128 + D;
-    auto put = [&](long long dst, int e) { if (dst >= 0 && dst < h->param_count) map[(size_t)dst] = e; };
-    for (int c = 0; c < Kx; ++c)
-        for (int m = 0; m < 128; ++m) {
-            const int e = sm.dw0 + c * 128 + m;
-            if (c < D) put(off[0] + (long long)m * D + c, e);
-            else if (c == Kx - 1) put(off[1] + m, e);
-        }
-    for (int c = 0; c < 128; ++c)
-        for (int m = 0; m < 128; ++m) {
-            put(off[2] + (long long)m * 128 + c, sm.dw1 + c * 128 + m);
-            put(off[6] + (long long)m * 128 + c, sm.dw3 + c * 128 + m);
-        }
-    for (int c = 0; c < 128 + Kx; ++c)
-        for (int m = 0; m < 128; ++m) {
-            const int e = sm.dw2 + c * 128 + m;
-            if (c < 128 || c - 128 < D) put(off[4] + (long long)m * fan2 + c, e);
-            else if (c - 128 == Kx - 1) put(off[5] + m, e);
-        }
-    for (int o = 0; o < 4; ++o)
-        for (int f = 0; f < 128; ++f) put(o == 0 ? off[8] + f : off[10] + (long long)(o - 1) * 128 + f, sm.dwh + o * 128 + f);
-    for (int f = 0; f < 128; ++f) { put(off[3] + f, sm.db1 + f); put(off[7] + f, sm.db3 + f); }
-    for (int o = 0; o < 4; ++o) put(o == 0 ? off[9] : off[11] + (o - 1), (sm.hb + o) | (1 << 30));
-    for (int v : map) if (v < 0) { set_error("fused train: gather map incomplete (unexpected parameter layout)"); return -6; }
-    if (h->gather_map) cudaFree(h->gather_map);
-    cudaError_t e = cudaMalloc(&h->gather_map, map.size() * sizeof(int));
-    if (e != cudaSuccess) { set_error("cudaMalloc(gather map) failed"); h->gather_map = nullptr; return (int)e; }
-    cudaMemcpyAsync(h->gather_map, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice, s);   // pageable source: staged before the call returns
-    h->gather_n = h->param_count;
+    int tiles = 0;
+    auto seg = [&](int sb, int C, int ld, long long pb) {
+        g.seg[g.n_seg++] = GatherSeg{sb, C, ld, tiles, pb};
+        tiles += ((C + 31) / 32) * 4;
+    };
+    seg(sm.dw0, D, D, off[0]);
+    seg(sm.dw1, 128, 128, off[2]);
+    seg(sm.dw2, 128, 128 + D, off[4]);
+    seg(sm.dw2 + 128 * 128, D, 128 + D, off[4] + 128);
+    seg(sm.dw3, 128, 128, off[6]);
+    g.n_tiles = tiles;
+    int first = 0;
+    auto vec = [&](int sb, int n, long long pb) { g.vec[g.n_vec++] = GatherVec{sb, n, first, pb}; first += n; };
+    vec(sm.dw0 + (Kx - 1) * 128, 128, off[1]);            // layer-0 bias = the encoding's constant-1 column
+    vec(sm.db1, 128, off[3]);
+    vec(sm.dw2 + (128 + Kx - 1) * 128, 128, off[5]);      // layer-2 bias likewise
+    vec(sm.db3, 128, off[7]);
+    vec(sm.dwh, 128, off[8]);                             // sigma weight
+    vec(sm.dwh + 128, 384, off[10]);                      // rgb weight, [3][128]
+    g.n_vec_elems = first;
+    g.hb = sm.hb;
+    g.pb_hb[0] = off[9]; g.pb_hb[1] = off[11]; g.pb_hb[2] = off[11] + 1; g.pb_hb[3] = off[11] + 2;
+    long long covered = 4;
+    for (int i = 0; i < g.n_seg; ++i) covered += 128LL * g.seg[i].C;
+    for (int i = 0; i < g.n_vec; ++i) covered += g.vec[i].n;
+    if (covered != h->param_count) { set_error("fused train: gather plan does not cover the parameter vector (unexpected layout)"); return -6; }
+    g.n = h->param_count;
+    g.valid = 1;
     return 0;
 }
 
@@ -210,7 +210,7 @@ int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, flo
     const bool leave = grads == nullptr;
     if (leave) {
         if (!bulk) { set_error("fused train: grads = NULL needs the one-vector gradient flush (option bulk_reduce)"); return -7; }
-        if (int rc = build_gather_map(h, sm, fp.D, Kx, s)) return rc;
+        if (int rc = build_gather_plan(h, sm, fp.D, Kx)) return rc;
         p.unscale = 1;
     }
     if (!leave && h->slab_pending) { set_error("fused train: a gradient sum is pending (tnerf_train_fwd_bwd with grads = NULL): run the gathering tnerf_optimizer_step first"); return -8; }

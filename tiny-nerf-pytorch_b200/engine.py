@@ -167,10 +167,10 @@ def render_weights(model, ro, o_stride, rd, n, S, near, far, jitter, white, prec
     return w
 
 
-# TNERF_GATHER=1: the optimiser launch gathers the gradient straight from the training kernel's sum vector (no scatter launch).  Off by
-# default: the gather is strided (parameter (f, k) <- element k * 128 + f) and the launch takes 22 us against 8.5 + 4.7 us for
-# Adam + scatter (cold, ncu) -- 157.6 instead of 149.2 us per step; it needs a transposing optimiser kernel to pay.
-_GATHER = os.environ.get("TNERF_GATHER", "0") == "1"
+# One process on the tensor-core path: the gradient stays in the training kernel's sum vector (tnerf_train_fwd_bwd with grads = NULL)
+# and the optimiser launch gathers it from there, transposing the weight blocks through shared memory -- the gradient-scatter launch
+# disappears from the step (150.7 -> 148.4 us).  TNERF_GATHER=0: always scatter into the flat vector (developer A/B).
+_GATHER = os.environ.get("TNERF_GATHER", "1") != "0"
 
 
 class Trainer:
