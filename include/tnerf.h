@@ -95,6 +95,12 @@ int  tnerf_set_encoding(tnerf_handle* h, int num_freqs, int include_input);
 int  tnerf_set_option(tnerf_handle* h, const char* name, int value);
 /* the value in EFFECT for an option ("train_sync", "bulk_reduce": 0 / 1 after defaults; "unroll_from": as set); -1 = unknown name */
 int  tnerf_get_option(const tnerf_handle* h, const char* name);
+/* The sum vector of the fused training kernel (hidden 128, depth 4 models): tnerf_sum_elems = its length in floats (-1: no such kernel for
+ * this model); tnerf_set_sum_buffer = let tnerf_train_fwd_bwd (grads = NULL) accumulate into a CALLER-owned vector of that length
+ * (16-byte aligned, zero on entry, e.g. peer-mapped memory of a multi-rank step: tnerf_allreduce_adam_step with bit 1 of `repack`
+ * then sums the ranks' vectors [sum | loss | overflow flag] directly); NULL = the handle's own vector again. */
+long long tnerf_sum_elems(tnerf_handle* h);
+int  tnerf_set_sum_buffer(tnerf_handle* h, float* buf);
 /* Developer hook: a device buffer of 2048 int64 that receives clock64() phase stamps of CTA 0 of the fused
  * forward kernel (tools/trace_fwd.py); NULL disables it. */
 int  tnerf_set_debug_buffer(tnerf_handle* h, void* buf);
@@ -244,7 +250,9 @@ int tnerf_optimizer_step(tnerf_handle* h, float* params, float* grads, float* ex
  * must be double-buffered by epoch parity.  The sum is formed in rank order, so every rank computes bit-identical parameters.
  * With scaler_host the vectors are [gradient(n) | loss | overflow flag]: the flags are summed too, so every rank takes the same
  * skip / apply decision.  reduced_out (vector length or NULL) receives the reduced vector; zero_next (same length or NULL) = this
- * rank's OTHER-parity vector, cleared here for the next step; repack as in tnerf_optimizer_step (h may be NULL when 0).  A peer
+ * rank's OTHER-parity vector, cleared here for the next step; repack bit 0 as in tnerf_optimizer_step (h may be NULL when 0); bit 1:
+ * peer_grads[r] are the ranks' SUM vectors [sum(tnerf_sum_elems) | loss | overflow flag] left by tnerf_train_fwd_bwd (grads = NULL,
+ * tnerf_set_sum_buffer) -- no gradient-scatter launch; reduced_out still receives [gradient(n) | loss | flag] in parameter order.  A peer
  * that has not arrived after TNERF_PEER_TIMEOUT_S seconds (environment, default 60, 0 = wait forever) traps instead of hanging
  * the device. */
 int tnerf_allreduce_adam_step(tnerf_handle* h, float* params, float* exp_avg, float* exp_avg_sq, long long n,

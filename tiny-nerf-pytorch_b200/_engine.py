@@ -56,6 +56,8 @@ _SIGS = {
     "tnerf_set_encoding": (_i, [_p, _i, _i]),
     "tnerf_set_option": (_i, [_p, C.c_char_p, _i]),
     "tnerf_get_option": (_i, [_p, C.c_char_p]),
+    "tnerf_sum_elems": (_ll, [_p]),
+    "tnerf_set_sum_buffer": (_i, [_p, _p]),
     "tnerf_set_debug_buffer": (_i, [_p, _p]),
     "tnerf_fused_supported": (_i, [_p]),
     "tnerf_pack_weights": (_i, [_p, _p]),

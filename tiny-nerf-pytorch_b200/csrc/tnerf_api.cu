@@ -252,6 +252,13 @@ int tnerf_set_option(tnerf_handle* h, const char* name, int value) {
     else return bad("tnerf_set_option: unknown option");
     return 0;
 }
+long long tnerf_sum_elems(tnerf_handle* h) { return h ? fused_train_sum_elems(h) : -1; }
+int tnerf_set_sum_buffer(tnerf_handle* h, float* buf) {
+    if (!h) return bad("tnerf_set_sum_buffer: NULL handle");
+    if (buf && (reinterpret_cast<uintptr_t>(buf) & 15)) return bad("tnerf_set_sum_buffer: the vector must be 16-byte aligned");
+    h->ext_sum = buf;
+    return 0;
+}
 int tnerf_get_option(const tnerf_handle* h, const char* name) {
     if (!h || !name) return -1;
     const std::string n(name);
@@ -496,6 +503,10 @@ int tnerf_allreduce_adam_step(tnerf_handle* h, float* params, float* exp_avg, fl
     if (world < 1 || world > 8 || rank < 0 || rank >= world || epoch == 0) return bad("tnerf_allreduce_adam_step: need 1 <= world <= 8, 0 <= rank < world, epoch >= 1");
     for (int r = 0; r < world; ++r)
         if (!peer_grads[r] || !peer_flags[r] || (reinterpret_cast<uintptr_t>(peer_grads[r]) & 15)) return bad("tnerf_allreduce_adam_step: NULL or unaligned (16 B) peer pointer");
+    const bool gather = (repack & 2) != 0;      // peer_grads[r] are the ranks' SUM vectors [sum | loss | flag] (tnerf_set_sum_buffer + grads = NULL)
+    if (gather && (!h || !h->gplan.valid || h->gplan.n != n || h->sum_total <= 0))
+        return bad("tnerf_allreduce_adam_step: gather mode needs a preceding tnerf_train_fwd_bwd with grads = NULL on this handle");
+    repack &= 1;
     RepackMap mp{};
     if (repack) {
         if (!params_are_flat(h, params) || n != h->param_count) return bad("tnerf_allreduce_adam_step: repack needs the handle's parameters bound as one flat vector");
@@ -510,6 +521,9 @@ int tnerf_allreduce_adam_step(tnerf_handle* h, float* params, float* exp_avg, fl
         const double sec = e ? atof(e) : 60.0;
         return sec > 0.0 ? (long long)(sec * 2.0e9) : 0LL;
     }();
+    if (gather)
+        return launch_allreduce_adam_gather(params, exp_avg, exp_avg_sq, n, peer_grads, peer_flags, world, rank, epoch, step, lr, beta1, beta2, eps,
+                                            reduced_out, zero_next, mp, sc, h->gplan, h->sum_total, timeout_cycles, (cudaStream_t)stream);
     return launch_allreduce_adam(params, exp_avg, exp_avg_sq, n, peer_grads, peer_flags, world, rank, epoch, step, lr, beta1, beta2, eps,
                                  reduced_out, zero_next, mp, sc, timeout_cycles, (cudaStream_t)stream);
 }

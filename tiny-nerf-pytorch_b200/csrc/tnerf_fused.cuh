@@ -192,6 +192,10 @@ int launch_allreduce_adam(float* p, float* m, float* v, long long n, const float
                           int world, int rank, unsigned int epoch, int step, float lr, float b1, float b2, float eps, float* reduced_out,
                           float* zero_next, const RepackMap& mp, const ScalerArgs& sc, long long timeout_cycles, cudaStream_t s);
 
+int launch_allreduce_adam_gather(float* p, float* m, float* v, long long n, const float* const* peer_sums, unsigned int* const* peer_flags,
+                                 int world, int rank, unsigned int epoch, int step, float lr, float b1, float b2, float eps, float* reduced_out,
+                                 float* zero_next, const RepackMap& mp, const ScalerArgs& sc, const GatherPlan& plan, int sum_total,
+                                 long long timeout_cycles, cudaStream_t s);
 bool build_plan(const tnerf_handle* h, FusedPlan& pl);
 int fused_render_fwd_fast(const FwdParams& p, int grid, cudaStream_t s);   // tnerf_fused_fast.cu (n_samples % 32 == 0)
 

@@ -61,6 +61,8 @@ struct tnerf_handle {
     bool slab0_zero = false;                           // slab 0 is all zeros (it is the accumulation target of the bulk-reduction mode)
     bool slab_pending = false;                         // slab 0 holds an unscaled gradient sum waiting for the gathering optimiser launch
     tnerf::GatherPlan gplan;                           // built by tnerf_train_fwd_bwd with grads = NULL (tnerf_train.cu)
+    float* ext_sum = nullptr;                          // caller-owned sum vector (tnerf_set_sum_buffer: peer-mapped memory of a multi-rank step)
+    int sum_total = 0;                                 // elements of the sum vector for this model (0 until known)
     int sm_count = 0;
     long long wide_version = 0;           // bumped by every pack of the hidden=256 image (the kernel's constant table follows it)
     bool fused_ok = false;
@@ -109,6 +111,7 @@ int launch_found_inf(const float* g, long long n, float* found, cudaStream_t s);
 // wide MLP (hidden = 256) on CTA pairs (tnerf_fused_wide.cu)
 bool wide_shape_supported(const tnerf_handle* h);
 bool fused_render_shape_ok(const tnerf_handle* h, int S, bool want_weights);   // tnerf_fused.cu
+int fused_train_sum_elems(tnerf_handle* h);                                    // tnerf_train.cu
 int wide_pack_weights(tnerf_handle* h, cudaStream_t s);
 void wide_release(tnerf_handle* h);
 int fused_render_fwd_wide(tnerf_handle* h, const RaySource& rs, long long n, float nr, float fr, int S, const float* jitter, int white,

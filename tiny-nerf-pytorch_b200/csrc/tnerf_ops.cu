@@ -635,12 +635,15 @@ __global__ void __launch_bounds__(256) adam_gather_kernel(float* __restrict__ p,
         while (si + 1 < plan.n_seg && (int)blockIdx.x >= plan.seg[si + 1].tile0) ++si;
         const GatherSeg sg = plan.seg[si];
         const int t = (int)blockIdx.x - sg.tile0, c0 = (t >> 2) * 32, m0 = (t & 3) * 32;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {                 // rows of the sum vector: c fixed, m consecutive
-            const int c = c0 + ty + 8 * r;
-            float x = 0.f;
-            if (c < sg.C) { float* q = gsum + sg.sb + c * 128 + m0 + tx; x = *q; *q = 0.f; }
-            tile[ty + 8 * r][tx] = x;
+        {   // rows of the sum vector (c fixed, m consecutive): one 16-byte load per thread, row = thread / 8
+            const int cl = threadIdx.x >> 3, q = threadIdx.x & 7, c = c0 + cl;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < sg.C) {
+                float4* src = reinterpret_cast<float4*>(gsum + sg.sb + c * 128 + m0 + 4 * q);
+                x = *src;
+                *src = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            tile[cl][4 * q] = x.x; tile[cl][4 * q + 1] = x.y; tile[cl][4 * q + 2] = x.z; tile[cl][4 * q + 3] = x.w;
         }
         __syncthreads();
         if (skip) return;
@@ -766,6 +769,102 @@ __global__ void allreduce_adam_kernel(PeerSet ps, int world, int rank, unsigned 
         const float pn = p[i] - lr_over_bc1 * (mi / denom);
         p[i] = pn;
         if (mp.valid) repack_param(mp, i, pn);
+    }
+}
+
+// The exchange kernel with the gradient GATHERED from the ranks' sum vectors (tensor-memory order) instead of their flat vectors: with
+// several ranks, too, the training kernel's one-vector flush is the last thing that touches the gradient before the optimiser --
+// no scatter launch.  Vectors: [sum(total) | loss | overflow flag]; tiles / vectors as in adam_gather_kernel, every element summed
+// over the ranks in rank order (bit-identical replicas), this rank's other-parity vector cleared on the way.
+__device__ __forceinline__ float peer_sum(const PeerSet& ps, int world, long long idx) {
+    float g = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) if (r < world) g += __ldcv(ps.grads[r] + idx);
+    return g;
+}
+__global__ void __launch_bounds__(256) allreduce_adam_gather_kernel(PeerSet ps, int world, int rank, unsigned int epoch, float* __restrict__ p,
+                                      float* __restrict__ m, float* __restrict__ v, long long n, float lr_over_bc1, float inv_sqrt_bc2, float lr,
+                                      float b1, float b2, float eps, float* __restrict__ reduced_out, float* __restrict__ zero_next,
+                                      const __grid_constant__ RepackMap mp, const ScalerArgs sc, const __grid_constant__ GatherPlan plan,
+                                      int sum_total, long long timeout_cycles) {
+    __shared__ int timed_out;
+    __shared__ float dec[3];
+    __shared__ float tile[32][33];
+    if (threadIdx.x == 0) timed_out = 0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(ps.flags[threadIdx.x] + rank, epoch);
+    if (threadIdx.x < world) {
+        const unsigned int* mine = ps.flags[rank] + threadIdx.x;
+        const long long t0 = clock64();
+        unsigned int spins = 0;
+        while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
+            if (timeout_cycles > 0 && clock64() - t0 > timeout_cycles) { timed_out = 1; break; }
+            if (++spins > 64) __nanosleep(32);
+        }
+    }
+    __syncthreads();
+    if (timed_out) { __trap(); }
+    if (sc.state) {
+        if (threadIdx.x == 0) scaler_decide(sc, !(peer_sum(ps, world, sum_total + 1) == 0.f), blockIdx.x == 0, lr, b1, b2, dec);
+        __syncthreads();
+        lr_over_bc1 = dec[1]; inv_sqrt_bc2 = dec[2];
+    }
+    const bool skip = sc.state && dec[0] != 0.f;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if ((int)blockIdx.x < plan.n_tiles) {
+        int si = 0;
+        while (si + 1 < plan.n_seg && (int)blockIdx.x >= plan.seg[si + 1].tile0) ++si;
+        const GatherSeg sg = plan.seg[si];
+        const int t = (int)blockIdx.x - sg.tile0, c0 = (t >> 2) * 32, m0 = (t & 3) * 32;
+        {   // one 16-byte load per rank and thread: row (c) = thread / 8, four consecutive m
+            const int cl = threadIdx.x >> 3, q = threadIdx.x & 7, c = c0 + cl;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < sg.C) {
+                const long long idx = sg.sb + c * 128 + m0 + 4 * q;
+                float4 y[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) if (r < world) y[r] = ld_cv4(ps.grads[r] + idx);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) if (r < world) { x.x += y[r].x; x.y += y[r].y; x.z += y[r].z; x.w += y[r].w; }   // rank order
+                if (zero_next) *reinterpret_cast<float4*>(zero_next + idx) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            tile[cl][4 * q] = x.x; tile[cl][4 * q + 1] = x.y; tile[cl][4 * q + 2] = x.z; tile[cl][4 * q + 3] = x.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int mm = m0 + ty + 8 * r, c = c0 + tx;
+            if (c < sg.C) {
+                const long long i = sg.pb + (long long)mm * sg.ld + c;
+                const float gi = tile[tx][ty + 8 * r];
+                if (reduced_out) reduced_out[i] = gi;
+                if (!skip) adam_apply(i, gi, p, m, v, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps, mp);
+            }
+        }
+        return;
+    }
+    const long long j = ((long long)blockIdx.x - plan.n_tiles) * 256 + threadIdx.x;
+    if (j < plan.n_vec_elems) {
+        int vi = 0;
+        while (vi + 1 < plan.n_vec && j >= plan.vec[vi + 1].first) ++vi;
+        const GatherVec vc = plan.vec[vi];
+        const long long idx = vc.sb + (j - vc.first), i = vc.pb + (j - vc.first);
+        const float gi = peer_sum(ps, world, idx);
+        if (zero_next) zero_next[idx] = 0.f;
+        if (reduced_out) reduced_out[i] = gi;
+        if (!skip) adam_apply(i, gi, p, m, v, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps, mp);
+    } else if (j < plan.n_vec_elems + 4) {
+        const int o = (int)(j - plan.n_vec_elems);
+        const long long idx = plan.hb + o;
+        const float gi = (peer_sum(ps, world, idx) + peer_sum(ps, world, idx + 4)) + (peer_sum(ps, world, idx + 8) + peer_sum(ps, world, idx + 12));
+        if (zero_next) { zero_next[idx] = 0.f; zero_next[idx + 4] = 0.f; zero_next[idx + 8] = 0.f; zero_next[idx + 12] = 0.f; }
+        if (reduced_out) reduced_out[plan.pb_hb[o]] = gi;
+        if (!skip) adam_apply(plan.pb_hb[o], gi, p, m, v, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps, mp);
+    } else if (j < plan.n_vec_elems + 4 + (sc.state ? 2 : 1)) {     // loss (and overflow flag) behind the sum
+        const long long k = j - plan.n_vec_elems - 4;
+        const float x = peer_sum(ps, world, sum_total + k);
+        if (zero_next) zero_next[sum_total + k] = 0.f;
+        if (reduced_out) reduced_out[n + k] = x;
     }
 }
 
@@ -934,6 +1033,24 @@ int launch_allreduce_adam(float* p, float* m, float* v, long long n, const float
     cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 4) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, allreduce_adam_kernel, ps, world, rank, epoch, p, m, v, n, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), lr, b1, b2,
                        eps, reduced_out, zero_next, mp, sc, timeout_cycles);
+    return count_launch();
+}
+int launch_allreduce_adam_gather(float* p, float* m, float* v, long long n, const float* const* peer_sums, unsigned int* const* peer_flags,
+                                 int world, int rank, unsigned int epoch, int step, float lr, float b1, float b2, float eps, float* reduced_out,
+                                 float* zero_next, const RepackMap& mp, const ScalerArgs& sc, const GatherPlan& plan, int sum_total,
+                                 long long timeout_cycles, cudaStream_t s) {
+    if (n <= 0) return 0;
+    PeerSet ps{};
+    for (int r = 0; r < world; ++r) { ps.grads[r] = peer_sums[r]; ps.flags[r] = peer_flags[r]; }
+    const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+    const long long nvec = plan.n_vec_elems + 4 + 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(plan.n_tiles + blocks_for(nvec, 256))); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (pdl_mask() & 4) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, allreduce_adam_gather_kernel, ps, world, rank, epoch, p, m, v, n, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), lr, b1,
+                       b2, eps, reduced_out, zero_next, mp, sc, plan, sum_total, timeout_cycles);
     return count_launch();
 }
 int launch_check_finite(const float* g, long long n, int* flag, cudaStream_t s) {

@@ -94,6 +94,28 @@ int launch_found_inf(const float* g, long long n, float* found, cudaStream_t s) 
     return count_launch();
 }
 
+static void make_slab_map(int Kx, SlabMap& sm) {
+    int off = 0;
+    sm.dw0 = off; off += Kx * 128;
+    sm.dw1 = off; off += 128 * 128;
+    sm.dw2 = off; off += (128 + Kx) * 128;
+    sm.dw3 = off; off += 128 * 128;
+    sm.dwh = off; off += 4 * 128;
+    sm.db1 = off; off += 128;
+    sm.db3 = off; off += 128;
+    sm.hb = off; off += 16;
+    sm.total = off;
+}
+// elements of the training kernel's sum vector for this model, and the gather plan (tnerf_sum_elems: callers that provide the vector)
+int fused_train_sum_elems(tnerf_handle* h) {
+    FusedPlan fp;
+    if (!build_plan(h, fp) || fp.depth != 4 || fp.H != 128) return -1;
+    SlabMap sm;
+    make_slab_map(fp.Kx, sm);
+    h->sum_total = sm.total;
+    return sm.total;
+}
+
 // where every parameter's gradient sits in the tensor-memory-ordered sum vector: the inverse of reduce_slabs_kernel's scatter as a
 // short list of blocks and vectors (tnerf_train_fwd_bwd with grads = NULL leaves the gradient there; the gathering optimiser launch
 // transposes the weight blocks through shared memory so that both sides are coalesced)
@@ -175,16 +197,8 @@ int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, flo
     }
     const int Kx = fp.Kx;
     SlabMap& sm = p.sm;
-    int off = 0;
-    sm.dw0 = off; off += Kx * 128;
-    sm.dw1 = off; off += 128 * 128;
-    sm.dw2 = off; off += (128 + Kx) * 128;
-    sm.dw3 = off; off += 128 * 128;
-    sm.dwh = off; off += 4 * 128;
-    sm.db1 = off; off += 128;
-    sm.db3 = off; off += 128;
-    sm.hb = off; off += 16;
-    sm.total = off;
+    make_slab_map(Kx, sm);
+    h->sum_total = sm.total;
     const size_t need = (size_t)h->sm_count * sm.total * sizeof(float);
     if (h->slab_bytes < need) {
         if (h->slabs) cudaFree(h->slabs);
@@ -195,6 +209,8 @@ int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, flo
         h->slab0_zero = true;
     }
     p.slabs = reinterpret_cast<float*>(h->slabs);
+    const bool ext = grads == nullptr && h->ext_sum != nullptr;      // caller-owned sum vector (zero on entry, cleared by the caller's exchange)
+    if (ext) p.slabs = h->ext_sum;
     // Default mode: streams in phase + gradients added into ONE vector by bulk async reductions (fastest; fp32 sums differ in the last
     // bits between runs).  Option train_sync = 0 (tnerf_set_option / TNERF_TRAIN_SYNC at handle creation) = the run-to-run reproducible mode: streams half a tile apart, per-CTA slabs summed in a
     // fixed order.  Option bulk_reduce = 0/1 overrides the flush alone.
@@ -213,9 +229,10 @@ int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, flo
         if (int rc = build_gather_plan(h, sm, fp.D, Kx)) return rc;
         p.unscale = 1;
     }
-    if (!leave && h->slab_pending) { set_error("fused train: a gradient sum is pending (tnerf_train_fwd_bwd with grads = NULL): run the gathering tnerf_optimizer_step first"); return -8; }
-    if (bulk && !h->slab0_zero && !h->slab_pending) cudaMemsetAsync(h->slabs, 0, (size_t)sm.total * sizeof(float), s);
+    if (!leave && h->slab_pending && !ext) { set_error("fused train: a gradient sum is pending (tnerf_train_fwd_bwd with grads = NULL): run the gathering tnerf_optimizer_step first"); return -8; }
+    if (bulk && !ext && !h->slab0_zero && !h->slab_pending) cudaMemsetAsync(h->slabs, 0, (size_t)sm.total * sizeof(float), s);
     if (int rc = fused_train2(h, fp, p, Kx, (int)grid, s)) return rc;
+    if (ext) return 0;
     if (leave) { h->slab0_zero = false; h->slab_pending = true; return 0; }     // pending: cleared element by element by the gathering optimiser launch
     h->slab0_zero = bulk;               // the scatter kernel leaves slab 0 cleared in bulk mode; otherwise it holds a CTA's partial sums
     ReduceArgs ra{};

@@ -234,6 +234,7 @@ class Trainer:
             if init_scale is not None:
                 self.scaler_state[0] = float(init_scale)
         self.h.bind()
+        E.check(E.lib().tnerf_set_sum_buffer(self.h.h, None), "tnerf_set_sum_buffer")     # (a multi-rank trainer of the same model may have lent it one)
         if self.prec == E.PREC_F16_TC:
             self.h.ensure_packed(force=True)
         # gradient exchange of ray-sharded data parallel: "p2p" = one kernel that all-reduces over NVLink peer memory and
@@ -282,7 +283,9 @@ class Trainer:
         import torch.distributed._symmetric_memory as symm_mem
         group = self.pg if self.pg is not None else dist.group.WORLD
         self.rank = dist.get_rank(group)
-        stride = (self.P + 2 + 63) // 64 * 64
+        # sum-vector exchange (no gradient-scatter launch): the ranks' [sum | loss | flag] vectors in the training kernel's own order
+        self._sum_elems = int(E.lib().tnerf_sum_elems(self.h.h)) if self.prec == E.PREC_F16_TC else -1
+        stride = (max(self.P, self._sum_elems) + 2 + 63) // 64 * 64
         self._sym_stride = stride
         self.sym = symm_mem.empty(2 * stride + 64, dtype=torch.float32, device=self.device)
         self.sym.zero_()
@@ -295,6 +298,7 @@ class Trainer:
         self._peer_grads = [VP(*[b + 4 * k * stride for b in bases]) for k in range(2)]
         self._peer_flags = VP(*[b + 4 * 2 * stride for b in bases])
         self._gviews = [self.sym[k * stride:k * stride + self.P + 2] for k in range(2)]
+        self._sviews = [self.sym[k * stride:k * stride + self._sum_elems + 2] for k in range(2)] if self._sum_elems > 0 else None
         self.reduced = torch.zeros(self.P + 2, dtype=torch.float32, device=self.device)
 
     # ---- one optimisation step ------------------------------------------------------------------
@@ -313,10 +317,11 @@ class Trainer:
         if self.comm == "p2p":
             k = self.steps & 1
             sc = self._scaler_struct(None, None, call)
+            nxt = self._sviews[k ^ 1] if gather else self._gviews[k ^ 1]
             E.check(E.lib().tnerf_allreduce_adam_step(self.h.h, E.ptr(self.flat), E.ptr(self.exp_avg), E.ptr(self.exp_avg_sq), P,
                                                       self._peer_grads[k], self._peer_flags, self.world, self.rank, self.steps, self.steps,
                                                       self.lr, self.betas[0], self.betas[1], self.eps, E.ptr(self.reduced),
-                                                      E.ptr(self._gviews[k ^ 1]), repack, sc, st), "tnerf_allreduce_adam_step")
+                                                      E.ptr(nxt), repack | (2 if gather else 0), sc, st), "tnerf_allreduce_adam_step")
             return self.reduced[P:P + 1]
         if self.world > 1:
             torch.distributed.all_reduce(self.gbuf, group=self.pg)
@@ -342,9 +347,18 @@ class Trainer:
             found = gbuf[P + 1:] if self.comm == "p2p" else gbuf[P + 1 + (self.steps & 1):]
         # one process, tensor-core path, one-vector flush: the gradient stays in the training kernel's sum vector and the optimiser
         # launch gathers it from there (no scatter launch); otherwise it is scattered into gbuf (the exchange vector of a multi-rank step)
-        gather = self.world == 1 and self.prec == E.PREC_F16_TC and _GATHER and self.h.get_option("bulk_reduce") == 1
+        gather = self.prec == E.PREC_F16_TC and _GATHER and self.h.get_option("bulk_reduce") == 1 and \
+            (self.world == 1 or (self.comm == "p2p" and self._sviews is not None))
+        loss_slot = gbuf[P:]
+        if gather and self.comm == "p2p":
+            # several ranks: the kernel's sum vector IS this rank's exchange vector (peer-mapped), loss and overflow flag behind it
+            sbuf = self._sviews[(self.steps + 1) & 1]
+            E.check(E.lib().tnerf_set_sum_buffer(self.h.h, E.ptr(sbuf)), "tnerf_set_sum_buffer")
+            loss_slot = sbuf[self._sum_elems:]
+            if found is not None:
+                found = sbuf[self._sum_elems + 1:]
         E.check(E.lib().tnerf_train_fwd_bwd(self.h.h, C.byref(rs), E.ptr(target), n, self.near, self.far, self.S, E.ptr(jitter),
-                                            int(self.white), self.prec, denom, None, E.ptr(gbuf[P:]), None if gather else E.ptr(gbuf),
+                                            int(self.white), self.prec, denom, None, E.ptr(loss_slot), None if gather else E.ptr(gbuf),
                                             E.ptr(scale), E.ptr(found), st),
                 "tnerf_train_fwd_bwd")
         return self._finish(gather)
