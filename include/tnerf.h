@@ -100,6 +100,8 @@ int  tnerf_get_option(const tnerf_handle* h, const char* name);
  * (16-byte aligned, zero on entry, e.g. peer-mapped memory of a multi-rank step: tnerf_allreduce_adam_step with bit 1 of `repack`
  * then sums the ranks' vectors [sum | loss | overflow flag] directly); NULL = the handle's own vector again. */
 long long tnerf_sum_elems(tnerf_handle* h);
+/* drop a gradient sum left in the handle's own vector by tnerf_train_fwd_bwd(grads = NULL) without applying it */
+int  tnerf_clear_sum(tnerf_handle* h, void* stream);
 int  tnerf_set_sum_buffer(tnerf_handle* h, float* buf);
 /* Developer hook: a device buffer of 2048 int64 that receives clock64() phase stamps of CTA 0 of the fused
  * forward kernel (tools/trace_fwd.py); NULL disables it. */

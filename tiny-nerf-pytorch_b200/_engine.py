@@ -58,6 +58,7 @@ _SIGS = {
     "tnerf_get_option": (_i, [_p, C.c_char_p]),
     "tnerf_sum_elems": (_ll, [_p]),
     "tnerf_set_sum_buffer": (_i, [_p, _p]),
+    "tnerf_clear_sum": (_i, [_p, _p]),
     "tnerf_set_debug_buffer": (_i, [_p, _p]),
     "tnerf_fused_supported": (_i, [_p]),
     "tnerf_pack_weights": (_i, [_p, _p]),

@@ -259,6 +259,13 @@ int tnerf_set_sum_buffer(tnerf_handle* h, float* buf) {
     h->ext_sum = buf;
     return 0;
 }
+int tnerf_clear_sum(tnerf_handle* h, void* stream) {
+    TN_ON_DEVICE(h);
+    if (!h) return bad("tnerf_clear_sum: NULL handle");
+    if (h->slabs && h->sum_total > 0) cudaMemsetAsync(h->slabs, 0, (size_t)h->sum_total * sizeof(float), (cudaStream_t)stream);
+    h->slab_pending = false; h->slab0_zero = h->slabs != nullptr;
+    return 0;
+}
 int tnerf_get_option(const tnerf_handle* h, const char* name) {
     if (!h || !name) return -1;
     const std::string n(name);

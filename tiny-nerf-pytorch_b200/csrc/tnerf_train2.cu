@@ -1,5 +1,5 @@
-// Fused training kernel, two-stream variant (sm_100a).  Same contract as tnerf_train.cu (forward recompute +
-// composite + loss gradient + full backward of src/train.py:114-126 in ONE launch), different schedule:
+// Fused training kernel (sm_100a): forward recompute + composite + loss gradient + full backward of src/train.py:114-126 in ONE
+// launch.  Design (DESIGN.md sections 5.2 and 5.5):
 //
 //   * feature-major ("transposed") GEMMs: every layer is  D[feature x sample] = W[feature x k] . H[k x sample],
 //     so the weights are the M=128 operand and a tile may hold any number of samples.  A tile is 64 samples
@@ -7,15 +7,21 @@
 //     per CTA: while one stream's accumulator is being drained the other stream's GEMM owns the tensor pipe.
 //   * the fp16 weight image (132 KB) is RESIDENT in shared memory (one bulk copy per CTA), nothing is streamed;
 //   * per stream: X (8 KB) + two 16 KB activation slots; H1 is parked in registers of the drain threads between
-//     its two uses, H0 is recomputed (K = 64), dZ_l overwrites H_l in place;
+//     its two uses, H0 is recomputed (K = 64), dZ_l overwrites H_l in place; layer 0 of the next tile is issued early from a
+//     second copy of its features staged in the Q slot;
 //   * biases of layers 1/3 are added in fp32 by the drain threads (thread <-> feature row), their gradients are
 //     row sums of the same threads; layers 0/2 keep their bias in the constant-1 column of the encoding;
 //   * tensor memory: dW3 (128 cols) + dW2 (128+Kx) + dW0 (Kx) stay resident, one 64-column accumulator per
-//     stream; dW1 lives in registers, half of its columns in each drain warpgroup.
+//     stream; dW1 lives in registers, half of its columns in each drain warpgroup;
+//   * gradient flush: bulk async reductions into ONE vector (divided by the loss scale on the way when the optimiser launch
+//     gathers from it); dW3 / dW2 leave early, from the sample warps, while the last tile finishes.
 //
 // Warp roles (512 threads): warpgroup 0/1 = drain threads of stream 0/1 (thread <-> feature <-> TMEM lane);
-// warps 8-9 / 10-11 = sample threads of stream 0/1 (rays, depths, Fourier features, compositing fwd+bwd);
-// warp 12/13 lane 0 = MMA issuer of stream 0/1; warp 14 loads the weights.
+// warps 8-9 / 10-11 = sample threads of stream 0/1 (rays, depths, jitter, Fourier features, compositing fwd+bwd, early flush);
+// warp 12 = MMA issuer of BOTH streams (default schedule; warps 12/13 one stream each in the reproducible schedule); warp 14 lane 0
+// loads the weights.
+// Developer switches (compile time, tools/build_variant.sh): T2_SOLO (stream 1 idle: length of one stream's chain), T2_NO_MERGE (an
+// issuer warp per stream in every schedule), T2_NO_EARLY (no early flush), T2_FLUSH_NBUF (staging chunks of the final flush).
 #include <cstdlib>
 #include <type_traits>
 #include "tnerf_train.cuh"
