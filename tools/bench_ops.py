@@ -56,6 +56,17 @@ def f_rays():
 
 t = timed(f_rays)
 res["get_rays"] = {"units": n, "bytes_per_unit": 24, "seconds": t}
+
+
+# reference for a WRITE-ONLY stream of the same size and launch pattern: torch's fill of the same two alternating 100 MB pairs
+# (the roofline denominator is a copy, read + write; a pure write stream does not reach it)
+def f_fill():
+    i = k[0] & 1; k[0] += 1
+    ro[i].fill_(1.0); rd[i].fill_(2.0)
+
+
+t = timed(f_fill)
+res["write_only_reference_fill"] = {"units": n, "bytes_per_unit": 24, "seconds": t}
 # stratified: n2 rays x 64 samples: in 24 + 4S (jitter), out 16 S (z + pts)
 n2 = 1 << 18
 jit = torch.rand(n2, S, device=dev)
