@@ -15,6 +15,9 @@ Parity status: the reference ships no tests, golden vectors or fixtures for this
 ``tests/golden/make_golden.py`` imports the unmodified reference modules from
 ``/root/reference/src`` in the build container and stores input/output vectors in
 ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` replays them through this file.
+The one stage the reference delegates to a third-party generator -- the stratified jitter, ``torch.rand_like`` on the device,
+src/sampling.py:24 -- is restated as Philox4x32-10 with the engine's documented keying and pinned against the published
+Random123 known-answer vectors (bottom of this file).
 
 Every function cites the reference lines it restates (paths relative to /root/reference).
 The arithmetic is deliberately written in a different shape from the reference (functional,
@@ -363,3 +366,36 @@ def render_rays_last_flipped(p: Params, rays_o: Tensor, rays_d: Tensor, near, fa
     s = s.reshape(n, n_samples, 1).clone()
     s[:, -1, 0] = torch.where(s[:, -1, 0] > 0, torch.zeros_like(s[:, -1, 0]), torch.ones_like(s[:, -1, 0]))
     return composite(c.reshape(n, n_samples, 3), s, z, rays_d, white_bkgd)
+
+
+# --------------------------------------------------------------------------------------
+# stratified jitter drawn in-kernel  (src/sampling.py:24: torch.rand_like on the device)
+# --------------------------------------------------------------------------------------
+# The reference draws its jitter from torch's device generator, whose stream depends on launch geometry and cannot be reproduced
+# outside torch.  The engine draws from the same FAMILY of generator (Philox4x32-10, Salmon et al., "Parallel random numbers: as
+# easy as 1, 2, 3", SC'11 -- third-party algorithm, not part of /root/reference) with its own documented keying
+# (include/tnerf.h, tnerf_ray_source): key = (seed.lo, seed.hi ^ step.hi), counter = (sample, ray.lo, ray.hi, step.lo), first output
+# word, top 24 bits -> [0, 1).  Restated here in numpy integer arithmetic and pinned against the published known-answer vectors of
+# the Random123 distribution (tests/test_oracle_golden.py::test_philox_known_answers); tnerf_jitter_fill is compared with it bit for bit.
+def philox4x32_10(counter, key):
+    """counter: 4 arrays of uint32 (broadcastable), key: 2 arrays of uint32 -> the 4 output words (uint32 arrays)."""
+    import numpy as np
+    c = [np.asarray(x, dtype=np.uint64) & np.uint64(0xFFFFFFFF) for x in counter]
+    c = list(np.broadcast_arrays(*c))
+    k0, k1 = (int(x) & 0xFFFFFFFF for x in key)
+    m0, m1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = m0 * c[0], m1 * c[2]                       # 32 x 32 -> 64 bit products
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ np.uint64(k0), p1 & mask, (p0 >> np.uint64(32)) ^ c[3] ^ np.uint64(k1), p0 & mask]
+        k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return [x.astype(np.uint32) for x in c]
+
+
+def jitter_uniform(seed: int, step: int, n_rays: int, n_samples: int, first_ray: int = 0) -> Tensor:
+    """(n_rays, n_samples) fp32 uniform [0, 1): the numbers the training kernel draws for (jitter_seed, jitter_step)."""
+    import numpy as np
+    ray = np.arange(first_ray, first_ray + n_rays, dtype=np.uint64)[:, None]
+    smp = np.arange(n_samples, dtype=np.uint64)[None, :]
+    x = philox4x32_10((smp, ray & np.uint64(0xFFFFFFFF), ray >> np.uint64(32), step & 0xFFFFFFFF),
+                      (seed & 0xFFFFFFFF, ((seed >> 32) ^ (step >> 32)) & 0xFFFFFFFF))[0]
+    return torch.from_numpy((x >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24))

@@ -561,6 +561,18 @@ def test_in_kernel_jitter_equals_the_explicit_tensor_and_is_uniform(dev, prec):
     assert abs(l_k - l_ref.item()) < (1e-5 if prec == "f32" else 2e-3 * max(1.0, l_ref.item()))
 
 
+@pytest.mark.parametrize("case", [(1234567, 0, 257, 64), (0x9E3779B97F4A7C15, 3, 100, 128), (1, (1 << 32) + 17, 33, 24), ((1 << 63) + 5, 2 ** 40, 64, 1)])
+def test_jitter_fill_is_philox_bit_for_bit(dev, case):
+    """tnerf_jitter_fill (= the numbers the training kernel draws, previous test) against the oracle's Philox4x32-10 restatement,
+    which is pinned to the published known-answer vectors (tests/test_oracle_golden.py::test_philox_known_answers): bit exact,
+    including 64-bit seeds and step counts beyond 2^32."""
+    import _engine as E
+    seed, step, n, S = case
+    out = torch.full((n, S), -1.0, device=dev)
+    E.check(E.lib().tnerf_jitter_fill(seed, step, n, S, E.ptr(out), E.stream(dev)), "tnerf_jitter_fill")
+    assert torch.equal(out.cpu(), O.jitter_uniform(seed, step, n, S))
+
+
 # ------------------------------------------------------------------------------------------ GradScaler semantics
 @pytest.mark.parametrize("prec", ["f16", "f32"])
 def test_grad_scaler_skips_an_overflowed_step_and_recovers(dev, prec):

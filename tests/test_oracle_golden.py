@@ -179,3 +179,33 @@ def test_config4_chain_against_reference(golden_c4):
     close(depth, g["c4_depth"], atol=1e-4)
     close(acc, g["c4_acc"], atol=2e-5)
     close(w, g["c4_weights"], atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------ in-kernel jitter generator
+def test_philox_known_answers():
+    """The stratified jitter of the training kernel is Philox4x32-10 (third-party algorithm: Salmon et al., SC'11; not part of the
+    reference, which calls torch.rand_like, src/sampling.py:24).  The oracle's restatement against the known-answer vectors published
+    with the Random123 distribution (kat_vectors: counter, key -> output)."""
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+            ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+            ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0), (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1))]
+    for ctr, key, want in kats:
+        assert [int(x) for x in O.philox4x32_10(ctr, key)] == list(want)
+    # vectorised evaluation = element-wise evaluation
+    c0 = np.arange(7, dtype=np.uint64)
+    vec = O.philox4x32_10((c0, 5, 0, 9), (11, 13))[0]
+    assert [int(O.philox4x32_10((int(i), 5, 0, 9), (11, 13))[0]) for i in c0] == [int(x) for x in vec]
+
+
+def test_jitter_uniform_is_a_pure_function_of_seed_step_ray_sample():
+    """u(seed, step, ray, sample): 24-bit uniform in [0, 1); a shard of the rays sees the numbers of the same rays in the full batch
+    (ray-sharded data parallel draws per global ray id only through the per-rank seed -- the function itself is geometry-free)."""
+    u = O.jitter_uniform(0x1234567887654321, (1 << 32) + 5, 96, 64)
+    assert u.dtype == torch.float32 and u.shape == (96, 64)
+    assert 0.0 <= float(u.min()) and float(u.max()) < 1.0
+    assert torch.equal(u * 2 ** 24, (u * 2 ** 24).round())                 # 24-bit grid
+    assert torch.equal(O.jitter_uniform(0x1234567887654321, (1 << 32) + 5, 40, 64, first_ray=56), u[56:])
+    assert not torch.equal(O.jitter_uniform(0x1234567887654321, (1 << 32) + 6, 96, 64), u)      # next step: new numbers
+    assert not torch.equal(O.jitter_uniform(0x1234567887654322, (1 << 32) + 5, 96, 64), u)      # other seed (rank): new numbers
+    big = O.jitter_uniform(7, 1, 4096, 64)
+    assert abs(float(big.mean()) - 0.5) < 5e-3 and abs(float(big.var()) - 1 / 12) < 2e-3
