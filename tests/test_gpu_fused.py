@@ -681,6 +681,37 @@ def test_reference_call_sequence_is_fused(dev):
     assert ((w + 0).cpu() - ow)[keep].abs().max() < 2e-3
 
 
+def test_deferred_weights_refuse_to_describe_a_modified_model(dev):
+    """The 4th output of a fused volume_render (per-sample weights) is recomputed on demand.  Asked for AFTER the parameters were
+    modified in place it must fail loudly (as autograd does for a modified saved tensor), not describe the new network; asked for
+    before, it is the oracle's weights."""
+    from encoding import PositionalEncoding
+    from sampling import stratified_samples
+    from volume import volume_render
+    enc = PositionalEncoding(10, True).to(dev)
+    model, p = make_model((63, 128, 4, 2), 71, dev, 1.5)
+    n, S = 64, 32
+    ro, rd = random_rays(n, 72)
+    ro_d, rd_d = ro.to(dev), rd.to(dev)
+
+    def render():
+        z_vals, pts = stratified_samples(2.0, 6.0, S, ro_d, rd_d, randomized=False)
+        rgb, sigma = model(enc(pts.reshape(-1, 3)))
+        return volume_render(rgb.reshape(n, S, 3), sigma.reshape(n, S, 1), z_vals, rd_d)
+    with torch.no_grad():
+        comp, _, _, w = render()
+        comp = comp + 0
+        w_now = w + 0                                      # read before the update: fine
+        comp2, _, _, w2 = render()
+        comp2 = comp2 + 0
+        model.layers[0].bias.add_(0.01)                    # what optimizer.step() does
+        with pytest.raises(RuntimeError, match="modified in place"):
+            w2 + 0
+    ow = O.render_rays(p, ro, rd, 2.0, 6.0, S, None)[3]
+    clear = O.last_sample_sigma_pre(p, ro, rd, 2.0, 6.0, S, None).abs() > 4e-3
+    assert w_now.shape == (n, S) and (w_now.cpu() - ow)[clear].abs().max() < 2e-3
+
+
 def test_deferred_falls_back_when_chain_is_broken(dev):
     from encoding import PositionalEncoding
     from sampling import stratified_samples
