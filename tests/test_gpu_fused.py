@@ -712,6 +712,24 @@ def test_deferred_weights_refuse_to_describe_a_modified_model(dev):
     assert w_now.shape == (n, S) and (w_now.cpu() - ow)[clear].abs().max() < 2e-3
 
 
+def test_fused_backward_refuses_parameters_modified_since_the_forward(dev):
+    """The fused backward recomputes the activations from the parameters; the reference's autograd graph raises when a parameter it
+    needs was modified in place between forward and backward -- so does this one (instead of differentiating another network)."""
+    import engine
+    from encoding import PositionalEncoding
+    enc = PositionalEncoding(10, True).to(dev)
+    model, _ = make_model((63, 128, 4, 2), 73, dev, 1.5)
+    ro, rd = random_rays(128, 74)
+    comp, _, _ = engine.render_rays(model, enc, ro.to(dev), rd.to(dev), 2.0, 6.0, 64)
+    with torch.no_grad():
+        model.layers[1].weight.mul_(1.01)
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        comp.sum().backward()
+    comp, _, _ = engine.render_rays(model, enc, ro.to(dev), rd.to(dev), 2.0, 6.0, 64)     # a fresh forward differentiates fine
+    comp.sum().backward()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters())
+
+
 def test_deferred_falls_back_when_chain_is_broken(dev):
     from encoding import PositionalEncoding
     from sampling import stratified_samples

@@ -163,6 +163,7 @@ class ModelHandle:
         self._bound = None
         self._packed_versions = None
         self.generation = 0          # bumped by writers that change the parameters without touching their version counters
+        self.param_writes = 0        # every raw-kernel parameter update (engine.Trainer), whether or not the operand image was refreshed with it
         self.param_count = int(lib().tnerf_param_count(h))
         self.fused_ok = bool(lib().tnerf_fused_supported(h))
 

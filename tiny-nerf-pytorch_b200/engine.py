@@ -59,11 +59,13 @@ class _FusedRender(torch.autograd.Function):
         E.check(E.lib().tnerf_render_fwd(h.h, C.byref(rs), n, near, far, S, E.ptr(jitter), int(white), prec, E.ptr(comp),
                                          E.ptr(depth), E.ptr(acc), None, None, E.stream(dev)), "tnerf_render_fwd")
         ctx.args = (module, ro, o_stride, rd, n, S, near, far, jitter, white, bwd_prec)
+        ctx.save_for_backward(*params)      # backward recomputes from the parameters: autograd's in-place-modification check guards them
         return comp, depth, acc
 
     @staticmethod
     def backward(ctx, gC, gD, gA):
         module, ro, o_stride, rd, n, S, near, far, jitter, white, prec = ctx.args
+        ctx.saved_tensors                   # raises like the reference's autograd graph if a parameter was modified in place since the forward
         dev = rd.device
         h = E.handle_for(module, dev)
         ps = h.bind()
@@ -307,6 +309,7 @@ class Trainer:
         operand image); with several ranks the same launch first all-reduces the gradient over NVLink peer memory"""
         call = self.steps                # parity of THIS call: selects the overflow flag / beta-power slots
         self.steps += 1
+        self.h.param_writes += 1         # (deferred outputs of earlier renders notice that the network has changed)
         st = E.stream(self.device)
         repack = 1 if self.prec == E.PREC_F16_TC else 0
         if not repack:

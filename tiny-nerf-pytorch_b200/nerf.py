@@ -22,14 +22,14 @@ class _MLP(torch.autograd.Function):
         acts = torch.empty((module.depth, n, module.hidden), dtype=torch.float32, device=dev) if need_grad else None
         E.check(E.lib().tnerf_mlp_fwd(h.h, E.ptr(xc), n, E.ptr(rgb), E.ptr(sigma), E.ptr(acts), E.stream(dev)), "tnerf_mlp_fwd")
         if need_grad:
-            ctx.save_for_backward(xc, acts, rgb, sigma)
+            ctx.save_for_backward(xc, acts, rgb, sigma, *params)      # parameters: guarded by autograd's in-place-modification check
             ctx.module = module
             ctx.x_grad = x.requires_grad
         return rgb, sigma
 
     @staticmethod
     def backward(ctx, g_rgb, g_sigma):
-        xc, acts, rgb, sigma = ctx.saved_tensors
+        xc, acts, rgb, sigma = ctx.saved_tensors[:4]
         module, dev, n = ctx.module, xc.device, xc.shape[0]
         h = E.handle_for(module, dev)
         ps = h.bind()

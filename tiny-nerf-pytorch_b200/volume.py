@@ -50,13 +50,18 @@ class _LazyWeights:
     def __init__(self, args):
         self.args, self.cache = args, {}
         self.spec, self.encoder, self.model = None, None, None
-        self.versions = tuple(p._version for p in args[0]._params())
+        self.versions = self._state()
+
+    def _state(self):
+        """version counters of the parameters + the count of raw-kernel updates (engine.Trainer writes them without bumping versions)"""
+        model, rd = self.args[0], self.args[3]
+        return tuple(p._version for p in model._params()) + (E.handle_for(model, rd.device).param_writes,)
 
     def value(self, kind):
         if "w" not in self.cache:
             # the weights are recomputed on demand from the model: if an optimiser step has changed the parameters in place since the
             # render, the recomputation would silently describe ANOTHER network -- fail like autograd does for a modified saved tensor
-            if tuple(p._version for p in self.args[0]._params()) != self.versions:
+            if self._state() != self.versions:
                 raise RuntimeError("volume_render: the per-sample `weights` of a fused render were requested after the model's parameters "
                                    "were modified in place; read them (e.g. `weights + 0`) before the optimiser step")
             self.cache["w"] = engine.render_weights(*self.args)
