@@ -699,6 +699,8 @@ def main():
         detail = {"precision": prec_text(tr.prec), "kernels_per_fwd_bwd_call": b["kernels_per_call"], "exchange": tr.comm,
                   "rounds": R, "round_ms": {"median": ms_round, "min": float(b["t_dev"].min()), "max": float(b["t_dev"].max())},
                   "remeasured": bool(b.get("remeasured", False))}
+        if tr.tile_order is not None:                       # SM-speed-aware tile dealing (engine.Trainer.calibrate_tile_order)
+            detail["tile_order"] = engine._TILE_ORDERS[local][1]
         if adam:
             detail["round_ms_e2e"] = {"median": ms_round_e2e, "min": float(b["t_e2e"].min()), "max": float(b["t_e2e"].max())}
         if args.workload == "c5":

@@ -103,6 +103,14 @@ long long tnerf_sum_elems(tnerf_handle* h);
 /* drop a gradient sum left in the handle's own vector by tnerf_train_fwd_bwd(grads = NULL) without applying it */
 int  tnerf_clear_sum(tnerf_handle* h, void* stream);
 int  tnerf_set_sum_buffer(tnerf_handle* h, float* buf);
+/* Tile dealing of the fused training kernel.  The kernel deals its 64-sample tiles round-robin over (CTA, stream) pairs, so when the
+ * tile count is not a multiple of 2 x CTAs the pairs with the highest indices run one tile less.  SMs of one GPU do not run at exactly
+ * the same speed (a few per cent, stable per device); `order_dev` (caller-owned DEVICE array of n int32, a permutation of 0..n-1, kept
+ * alive by the caller) gives CTA b the dealing index order_dev[b]: a caller that has timed the CTAs (tnerf_set_debug_buffer: stamps
+ * 1024 + 4 b = start, 1025 + 4 b = end of the tile loop of CTA b, globaltimer ns) hands the shorter allotments to the slowest SMs.
+ * Used only when n equals the launch's CTA count and the schedule is not the reproducible one (train_sync = 0); any permutation
+ * gives the same gradient up to fp32 summation order.  n = 0 restores the identity. */
+int  tnerf_set_tile_order(tnerf_handle* h, const int* order_dev, int n);
 /* Developer hook: a device buffer of 2048 int64 that receives clock64() phase stamps of CTA 0 of the fused
  * forward kernel (tools/trace_fwd.py); NULL disables it. */
 int  tnerf_set_debug_buffer(tnerf_handle* h, void* buf);

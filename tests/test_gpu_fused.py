@@ -487,6 +487,45 @@ def test_fp32_trainer_does_not_leave_a_stale_operand_image(dev):
     assert (after - first).abs().max() > 1e-3            # the weights did move
 
 
+def test_tile_order_is_only_a_permutation_of_the_dealing(dev):
+    """tnerf_set_tile_order / engine.Trainer.calibrate_tile_order (SM-speed-aware tile dealing): the calibration hands out a
+    permutation of the CTAs, and ANY permutation -- the tiles of a step reach other CTAs, nothing else changes -- gives the same
+    gradient and loss up to fp32 summation order, on a batch whose tiles do not divide evenly over the (CTA, stream) pairs."""
+    import ctypes as C
+    import _engine as E
+    import engine
+    from encoding import PositionalEncoding
+    enc = PositionalEncoding(10, True).to(dev)
+    model, _ = make_model((63, 128, 4, 2), 83, dev, 1.5)
+    tr = engine.Trainer(model, enc, n_samples=64)
+    summary = tr.calibrate_tile_order(force=True)
+    sms = int(torch.cuda.get_device_properties(dev).multi_processor_count)
+    assert sorted(tr.tile_order.cpu().tolist()) == list(range(sms))
+    assert summary["ctas"] == sms and 0 < summary["loop_ns_min"] <= summary["loop_ns_median"] <= summary["loop_ns_max"]
+    n, S = 4096 + 37, 64
+    g = torch.Generator().manual_seed(84)
+    pose = O.look_at_pose(0.7, 0.45).to(dev)
+    pix = torch.randint(0, 100 * 100, (n,), generator=g).to(dev)
+    tgt, jit = torch.rand(n, 3, generator=g).to(dev), torch.rand(n, S, generator=g).to(dev)
+    rs = engine.ray_source(c2w=pose, H=100, W=100, focal=138.9, pixel_index=pix)
+
+    def grad_and_loss(order):
+        E.check(E.lib().tnerf_set_tile_order(tr.h.h, E.ptr(order), 0 if order is None else int(order.numel())), "tnerf_set_tile_order")
+        out = torch.zeros(tr.P + 3, device=dev)
+        loss_slot = out[tr.P:]
+        E.check(E.lib().tnerf_train_fwd_bwd(tr.h.h, C.byref(rs), E.ptr(tgt), n, 2.0, 6.0, S, E.ptr(jit), 1, tr.prec, 3.0 * n, None,
+                                            E.ptr(loss_slot), E.ptr(out), None, None, E.stream(dev)), "tnerf_train_fwd_bwd")
+        torch.cuda.synchronize()
+        return out[:tr.P + 1].clone()
+    base = grad_and_loss(None)
+    assert float(base[:-1].norm()) > 0 and float(base[-1]) > 0
+    orders = [torch.arange(sms - 1, -1, -1, dtype=torch.int32, device=dev), torch.randperm(sms, generator=g).to(torch.int32).to(dev), tr.tile_order]
+    for order in orders:
+        got = grad_and_loss(order)
+        assert float((got[:-1] - base[:-1]).norm() / base[:-1].norm()) < 1e-4
+        assert abs(float(got[-1] - base[-1])) < 1e-4 * max(1.0, abs(float(base[-1])))
+
+
 def test_optimizer_step_refreshes_operand_image_like_a_full_repack(dev):
     """tnerf_optimizer_step (Adam + clear gradient vector + in-place fp16 image refresh, one launch) against
     tnerf_adam_step followed by tnerf_pack_weights: same parameters, same moments, byte-identical image, cleared gradients."""

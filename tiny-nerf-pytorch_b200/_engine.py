@@ -60,6 +60,7 @@ _SIGS = {
     "tnerf_set_sum_buffer": (_i, [_p, _p]),
     "tnerf_clear_sum": (_i, [_p, _p]),
     "tnerf_set_debug_buffer": (_i, [_p, _p]),
+    "tnerf_set_tile_order": (_i, [_p, _p, _i]),
     "tnerf_fused_supported": (_i, [_p]),
     "tnerf_pack_weights": (_i, [_p, _p]),
     "tnerf_mlp_fwd": (_i, [_p, _p, _ll, _p, _p, _p, _p]),

@@ -275,6 +275,12 @@ int tnerf_get_option(const tnerf_handle* h, const char* name) {
     if (n == "unroll_from") return h->opt_unroll_from;
     return -1;
 }
+int tnerf_set_tile_order(tnerf_handle* h, const int* order_dev, int n) {
+    if (!h || n < 0 || (n > 0 && !order_dev)) return bad("tnerf_set_tile_order: NULL handle / negative length / NULL table");
+    h->tile_order = n > 0 ? order_dev : nullptr;
+    h->tile_order_n = n;
+    return 0;
+}
 int tnerf_set_debug_buffer(tnerf_handle* h, void* buf) {
     if (!h) return bad("NULL handle");
     h->debug = buf;

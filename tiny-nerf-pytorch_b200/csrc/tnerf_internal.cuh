@@ -68,6 +68,7 @@ struct tnerf_handle {
     bool fused_ok = false;
     int num_freqs = 0;                    // (in_dim-3)/6 when in_dim = 3+6L
     void* debug = nullptr;                // optional device buffer (1024 int64) for kernel phase stamps
+    const int* tile_order = nullptr; int tile_order_n = 0;   // caller-owned device permutation of the training kernel's CTAs (tnerf_set_tile_order)
     // training-kernel schedule (tnerf_set_option; defaults from TNERF_TRAIN_SYNC / TNERF_BULK_REDUCE / TNERF_TRAIN_UNROLL_FROM, read
     // ONCE when the handle is created): -1 = built-in choice
     int opt_train_sync = -1, opt_bulk_reduce = -1, opt_unroll_from = -1;

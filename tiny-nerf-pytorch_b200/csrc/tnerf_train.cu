@@ -222,6 +222,8 @@ int fused_train(tnerf_handle* h, const RaySource& rs, long long n, float nr, flo
     const long long grid = (p.n_tiles + 1) / 2 < h->sm_count ? (p.n_tiles + 1) / 2 : h->sm_count;
     p.bulk_reduce = bulk ? 1 : 0;
     p.sync_streams = sync;
+    // measured SM speeds (tnerf_set_tile_order): the slowest SMs get the shorter allotments; not in the reproducible schedule
+    p.tile_order = (sync && h->tile_order && h->tile_order_n == (int)grid) ? h->tile_order : nullptr;
     // grads == NULL: leave the (unscaled) sum in the ONE vector for the optimiser launch to gather from -- no scatter kernel
     const bool leave = grads == nullptr;
     if (leave) {

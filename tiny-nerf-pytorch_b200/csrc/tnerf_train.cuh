@@ -29,6 +29,7 @@ struct TrainParams {
     int sync_streams;          // the two streams of a CTA keep the same tile phase (dW1 halves drained where they are produced); -1 = host default
     int unscale;               // bulk-reduction flush only: the flush divides by the loss scale, so the ONE gradient vector holds unscaled sums
                                // (the optimiser launch then gathers from it directly: no scatter kernel, tnerf_train_fwd_bwd with grads = NULL)
+    const int* tile_order;     // optional permutation of the CTAs for the tile dealing (tnerf_set_tile_order); NULL = identity
     float* found;              // optional overflow flag (GradScaler's found_inf): set to 1 when a head gradient leaves the fp16-safe range or is not finite
 };
 

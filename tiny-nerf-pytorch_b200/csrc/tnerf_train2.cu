@@ -348,9 +348,12 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
 #else
     const long long nstreams = 2LL * gridDim.x;
     long long n_my[2];
+    // dealing index of this CTA: the identity, or the caller's permutation (the slowest SMs take the highest indices = one tile less
+    // when the tiles do not divide evenly, tnerf_set_tile_order); a constant table, not written by the previous kernel
+    const long long vb = p.tile_order ? (long long)__ldg(p.tile_order + blockIdx.x) : (long long)blockIdx.x;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-        const long long j = 2LL * blockIdx.x + s;
+        const long long j = 2LL * vb + s;
         n_my[s] = (j < p.n_tiles) ? (p.n_tiles - j + nstreams - 1) / nstreams : 0;
     }
 #endif
@@ -420,7 +423,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_train2_kernel(const __grid_c
 #ifdef T2_SOLO
         const long long j0 = blockIdx.x;
 #else
-        const long long j0 = 2LL * blockIdx.x + s;
+        const long long j0 = 2LL * vb + s;
 #endif
         const int S = p.S, W = S < 32 ? S : 32, sl = lane & (W - 1);
         const bool camera = p.rs.rays_d == nullptr;

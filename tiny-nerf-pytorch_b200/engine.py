@@ -169,6 +169,15 @@ def render_weights(model, ro, o_stride, rd, n, S, near, far, jitter, white, prec
     return w
 
 
+# SM-speed-aware tile dealing (include/tnerf.h, tnerf_set_tile_order): the SMs of one GPU differ by a few per cent in speed, stably per
+# device.  The first Trainer on a device times the CTAs of the training kernel on a balanced batch (a handful of launches, once per
+# process and device) and hands the resulting permutation to every handle it trains: when the tiles of a step do not divide evenly
+# over the (CTA, stream) pairs, the slowest SMs run the shorter allotments.  TNERF_TILE_ORDER=0 keeps the identity.
+_TILE_ORDER = os.environ.get("TNERF_TILE_ORDER", "1") != "0"
+_TILE_ORDERS = {}        # device index -> (int32 device tensor: dealing index per CTA, summary dict)
+_TILE_TABLES = []        # every table ever handed to a handle stays allocated (handles keep the bare pointer; a table is 592 bytes)
+
+
 # One process on the tensor-core path: the gradient stays in the training kernel's sum vector (tnerf_train_fwd_bwd with grads = NULL)
 # and the optimiser launch gathers it from there, transposing the weight blocks through shared memory -- the gradient-scatter launch
 # disappears from the step (150.7 -> 148.4 us).  TNERF_GATHER=0: always scatter into the flat vector (developer A/B).
@@ -253,6 +262,56 @@ class Trainer:
                     if comm == "p2p":
                         raise
                     print(f"[tnerf] peer-memory gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL", flush=True)
+
+        self.tile_order = None
+        if _TILE_ORDER and self.prec == E.PREC_F16_TC:
+            self.calibrate_tile_order()
+
+    # ---- SM-speed-aware tile dealing ---------------------------------------------------------------
+    def calibrate_tile_order(self, reps: int = 3, force: bool = False):
+        """time the training kernel's CTAs on a balanced batch (every (CTA, stream) pair gets the same number of tiles) and give the
+        handle the dealing order fastest SM first; cached per device.  Returns the summary (CTA loop times in ns)."""
+        dev = self.device
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        lib = E.lib()
+        if force or key not in _TILE_ORDERS:
+            sms = int(torch.cuda.get_device_properties(dev).multi_processor_count)
+            tiles = 2 * sms * 8
+            n = tiles * (64 // self.S) if self.S <= 64 else tiles // 2
+            pose = torch.eye(4, device=dev)
+            pose[2, 3] = 4.0
+            pix = torch.arange(n, device=dev, dtype=torch.int64) % 10000
+            tgt = torch.full((n, 3), 0.5, dtype=torch.float32, device=dev)
+            scratch = torch.zeros(self.P + 3, dtype=torch.float32, device=dev)
+            loss_slot = scratch[self.P:self.P + 1]
+            dbg = torch.zeros(2048, dtype=torch.int64, device=dev)
+            rs = ray_source(c2w=pose, H=100, W=100, focal=138.9, pixel_index=pix, jitter_seed=1)
+            total = torch.zeros(sms, dtype=torch.float64)
+            E.check(lib.tnerf_set_tile_order(self.h.h, None, 0), "tnerf_set_tile_order")
+            E.check(lib.tnerf_set_debug_buffer(self.h.h, E.ptr(dbg)), "tnerf_set_debug_buffer")
+            try:
+                for r in range(reps + 1):                  # the first launch warms up
+                    E.check(lib.tnerf_train_fwd_bwd(self.h.h, C.byref(rs), E.ptr(tgt), n, self.near, self.far, self.S, None, int(self.white),
+                                                    self.prec, 3.0 * n, None, E.ptr(loss_slot), E.ptr(scratch), None, None, E.stream(dev)),
+                            "tnerf_train_fwd_bwd (tile-order calibration)")
+                    d = dbg.cpu()                          # synchronises
+                    if r:
+                        total += (d[1025:1025 + 4 * sms:4] - d[1024:1024 + 4 * sms:4]).double()
+            finally:
+                E.check(lib.tnerf_set_debug_buffer(self.h.h, None), "tnerf_set_debug_buffer")
+            t = total / reps
+            fastest_first = torch.argsort(t)
+            perm = torch.empty(sms, dtype=torch.int32)
+            perm[fastest_first] = torch.arange(sms, dtype=torch.int32)
+            ts = t.sort().values
+            summary = {"ctas": sms, "loop_ns_min": float(ts[0]), "loop_ns_median": float(ts[sms // 2]), "loop_ns_max": float(ts[-1]),
+                       "slowest_ctas": [int(i) for i in fastest_first[-8:].flip(0)]}
+            _TILE_ORDERS[key] = (perm.to(dev), summary)
+            _TILE_TABLES.append(_TILE_ORDERS[key][0])
+        table, summary = _TILE_ORDERS[key]
+        self.tile_order = table                            # the handle keeps only the pointer: the tensor must outlive it
+        E.check(lib.tnerf_set_tile_order(self.h.h, E.ptr(table), int(table.numel())), "tnerf_set_tile_order")
+        return summary
 
     # ---- GradScaler state ------------------------------------------------------------------------
     def _reset_beta_powers(self, steps_done: int):
