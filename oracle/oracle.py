@@ -168,7 +168,9 @@ def last_sample_sigma_pre(p: Params, rays_o: Tensor, rays_d: Tensor, near, far, 
 def composite(rgb: Tensor, sigma: Tensor, z: Tensor, rays_d: Tensor, white_bkgd: bool = True):
     """delta_i = (z_{i+1}-z_i)*|d|, delta_last = 1e10*|d| (:18-23); alpha = 1-exp(-sigma*delta)
     (:27); T = exclusive cumprod of (1-alpha+1e-10) (:30-32); w = alpha*T (:34); sums (:36-38);
-    white background adds 1-acc (:41-42).  Returns (rgb, depth, acc, weights) (:44)."""
+    white background adds 1-acc (:41-42).  Returns (rgb, depth, acc, weights) (:44).
+    Deliberate deviation at n_samples = 1: the reference takes delta_last from `deltas[..., :1]` of an EMPTY tensor (:19-21) and ends
+    up compositing no sample (weights (N, 0), background only); here the single sample is a last sample."""
     n, s = z.shape
     gap = torch.empty_like(z)
     gap[:, : s - 1] = z[:, 1:] - z[:, :-1]
