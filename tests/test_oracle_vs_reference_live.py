@@ -171,3 +171,47 @@ def test_one_training_step_loss_and_gradients(R):
     for k, v in ref.named_parameters():
         gr = v.grad
         assert float((grads[k] - gr).abs().max()) <= 1e-4 * float(gr.abs().max()) + 1e-9, k
+
+
+# ------------------------------------------------------------------------------------------ the drop-in's call surface
+def test_mirror_modules_have_the_reference_call_surface(R):
+    """the product's flat modules (tiny-nerf-pytorch_b200/*.py) expose the reference's public functions and
+    classes with the same parameter names, order and defaults -- checked against the staged reference modules by introspection
+    (nothing is launched; a CPU tensor would be refused)."""
+    import inspect
+
+    import camera as m_camera
+    import data as m_data
+    import encoding as m_encoding
+    import nerf as m_nerf
+    import rays as m_rays
+    import sampling as m_sampling
+    import utils as m_utils
+    import volume as m_volume
+    extra = {}
+    for n in ("camera", "data"):
+        spec = importlib.util.spec_from_file_location("live_reference_" + n, os.path.join(REF_DIR, n + ".py"))
+        extra[n] = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(extra[n])
+
+    def params(fn):
+        return [(p.name, p.default, p.kind) for p in inspect.signature(fn).parameters.values()]
+    pairs = [(m_rays, R.rays), (m_sampling, R.sampling), (m_encoding, R.encoding), (m_nerf, R.nerf), (m_volume, R.volume), (m_utils, R.utils),
+             (m_camera, extra["camera"]), (m_data, extra["data"])]
+    checked = []
+    for mine, ref in pairs:
+        for name, obj in vars(ref).items():
+            if name.startswith("_") or getattr(obj, "__module__", None) != ref.__name__:
+                continue                                    # imported names (torch, np, ...) are not the module's surface
+            assert hasattr(mine, name), f"{ref.__name__}.{name} has no counterpart"
+            got = getattr(mine, name)
+            if inspect.isclass(obj):
+                assert params(got.__init__) == params(obj.__init__), name
+                assert params(got.forward)[:len(params(obj.forward))] == params(obj.forward), name
+            elif inspect.isfunction(obj):
+                mine_p, ref_p = params(got), params(obj)
+                # the mirror may ADD trailing keyword parameters (e.g. an explicit jitter tensor for parity runs), never change the reference's
+                assert mine_p[:len(ref_p)] == ref_p, (name, mine_p, ref_p)
+                assert all(p[1] is not inspect.Parameter.empty for p in mine_p[len(ref_p):]), name
+            checked.append(name)
+    assert {"get_rays", "stratified_samples", "PositionalEncoding", "TinyNeRF", "volume_render"} <= set(checked), checked
