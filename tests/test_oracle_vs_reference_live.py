@@ -215,3 +215,22 @@ def test_mirror_modules_have_the_reference_call_surface(R):
                 assert all(p[1] is not inspect.Parameter.empty for p in mine_p[len(ref_p):]), name
             checked.append(name)
     assert {"get_rays", "stratified_samples", "PositionalEncoding", "TinyNeRF", "volume_render"} <= set(checked), checked
+
+
+def test_train_script_keeps_the_reference_cli(R):
+    """tiny-nerf-pytorch_b200/train.py keeps the reference's Config fields (names, types, defaults -> the same tyro command line,
+    src/train.py:21-34), in the same order; it may add fields behind them.  Compared by parsing both files (neither is imported)."""
+    import ast
+    ref_path = os.path.join(ROOT, "baseline", "_ref", "src", "train.py")
+    if not os.path.exists(ref_path):
+        pytest.skip("reference scripts not staged under baseline/_ref/src")
+
+    def fields(path):
+        for node in ast.walk(ast.parse(open(path).read())):
+            if isinstance(node, ast.ClassDef) and node.name == "Config":
+                return [(s.target.id, ast.unparse(s.annotation), ast.unparse(s.value) if s.value else None)
+                        for s in node.body if isinstance(s, ast.AnnAssign)]
+        raise AssertionError(f"no Config in {path}")
+    ref, mine = fields(ref_path), fields(os.path.join(ROOT, "tiny-nerf-pytorch_b200", "train.py"))
+    assert len(ref) >= 10 and mine[:len(ref)] == ref
+    assert all(default is not None for _, _, default in mine[len(ref):])
