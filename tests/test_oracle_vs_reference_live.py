@@ -234,3 +234,75 @@ def test_train_script_keeps_the_reference_cli(R):
     ref, mine = fields(ref_path), fields(os.path.join(ROOT, "tiny-nerf-pytorch_b200", "train.py"))
     assert len(ref) >= 10 and mine[:len(ref)] == ref
     assert all(default is not None for _, _, default in mine[len(ref):])
+
+
+# ------------------------------------------------------------------------------------------ BASELINE config 1 (tiny_nerf_min.py)
+@pytest.fixture(scope="module")
+def tiny_min(tmp_path_factory):
+    """src/tiny_nerf_min.py is a self-contained duplicate of the modules whose import has side effects (it prints,
+    creates outputs/ and checkpoints/ in the working directory and builds its global model): imported from the staged copy inside a
+    scratch directory, with the repo's imageio shim on the path."""
+    import sys
+    path = os.path.join(REF_DIR, "tiny_nerf_min.py")
+    if not os.path.exists(path):
+        pytest.skip("tiny_nerf_min.py not staged")
+    shim = os.path.join(ROOT, "tiny-nerf-pytorch_b200", "_shims")
+    cwd = os.getcwd()
+    scratch = tmp_path_factory.mktemp("tiny_min")
+    os.makedirs(scratch / "data")
+    np.savez(scratch / "data" / "tiny_nerf_data.npz", **O.synthetic_scene(n_views=3, H=8, W=8, focal=11.0))     # the script loads it at import
+    os.chdir(scratch)
+    added = shim not in sys.path
+    if added:
+        sys.path.append(shim)                  # behind everything else: a real imageio wins
+    try:
+        spec = importlib.util.spec_from_file_location("live_reference_tiny_nerf_min", path)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+    finally:
+        os.chdir(cwd)
+        if added:
+            sys.path.remove(shim)
+    return m
+
+
+def test_config1_script_computes_what_the_modules_compute(tiny_min):
+    """BASELINE config 1 is tiny_nerf_min.py's own train step (2048 rays x 64 samples): its private copies of the five stages against
+    the oracle -- the same math as the modules', so `bench.py --workload c1` measures it with the same kernels."""
+    M = tiny_min
+    assert (M.N_RAND, M.N_SAMPLES, M.NEAR, M.FAR, M.LR) == (2048, 64, 2.0, 6.0, 5e-4)
+    assert (M.enc.num_freqs, M.enc.include_input, M.enc.out_dim) == (10, True, 63)        # L = 10 as coded
+    pose = some_pose(80)
+    ro, rd = O.get_rays(21, 17, 30.5, pose)
+    mro, mrd = M.get_rays(21, 17, 30.5, pose, torch.device("cpu"))
+    close(ro, mro)
+    close(rd, mrd, rtol=1e-6, atol=1e-7)
+    g = torch.Generator().manual_seed(81)
+    idx = torch.randint(0, 21 * 17, (64,), generator=g)
+    ro, rd = ro[idx], rd[idx]
+    torch.manual_seed(82)
+    mz, mpts = M.stratified_samples(2.0, 6.0, 64, ro, rd, randomized=True)
+    torch.manual_seed(82)
+    u = torch.rand(64, 64)
+    z, pts = O.stratified(2.0, 6.0, 64, ro, rd, u)
+    assert torch.equal(z, mz) and torch.equal(pts, mpts)
+    enc = M.PositionalEncoding(10, True)
+    feat = O.posenc(pts.reshape(-1, 3), 10, True)
+    assert torch.equal(feat, enc(pts.reshape(-1, 3)))
+    torch.manual_seed(83)
+    model = M.TinyNeRF(63, 128, 4, 2)
+    p = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    assert [(k, tuple(v.shape)) for k, v in p.items()] == [(k, tuple(s)) for k, s in O.mlp_param_shapes(63, 128, 4, 2)]
+    target = torch.rand(64, 3, generator=g)
+    rgb, sigma = model(enc(mpts.reshape(-1, 3)))
+    comp, depth, acc, w = M.volume_render(rgb.reshape(64, 64, 3), sigma.reshape(64, 64, 1), mz, rd)
+    loss = torch.mean((comp - target) ** 2)
+    loss.backward()
+    l, grads, (oc, od, oa) = O.loss_and_grads(p, ro, rd, target, 2.0, 6.0, 64, u)
+    close(l, loss, rtol=1e-5)
+    close(oc, comp, rtol=1e-5, atol=1e-6)
+    close(od, depth, rtol=1e-5, atol=1e-6)
+    close(oa, acc, rtol=1e-5, atol=1e-6)
+    for k, v in model.named_parameters():
+        assert float((grads[k] - v.grad).abs().max()) <= 1e-4 * float(v.grad.abs().max()) + 1e-9, k
+    close(O.mse2psnr(loss.detach()), M.mse2psnr(loss.detach()), rtol=1e-6)
