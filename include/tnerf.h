@@ -109,7 +109,9 @@ int  tnerf_set_sum_buffer(tnerf_handle* h, float* buf);
  * alive by the caller) gives CTA b the dealing index order_dev[b]: a caller that has timed the CTAs (tnerf_set_debug_buffer: stamps
  * 1024 + 4 b = start, 1025 + 4 b = end of the tile loop of CTA b, globaltimer ns) hands the shorter allotments to the slowest SMs.
  * Used only when n equals the launch's CTA count and the schedule is not the reproducible one (train_sync = 0); any permutation
- * gives the same gradient up to fp32 summation order.  n = 0 restores the identity. */
+ * gives the same gradient up to fp32 summation order.  n = 0 restores the identity.  The table lives in device memory and is NOT
+ * validated: entries that are not a permutation of 0..n-1 make CTAs process the same tiles twice and others never (a wrong gradient,
+ * no fault) -- build it on the host from a sort, as engine.Trainer.calibrate_tile_order does. */
 int  tnerf_set_tile_order(tnerf_handle* h, const int* order_dev, int n);
 /* Developer hook: a device buffer of 2048 int64 that receives clock64() phase stamps of CTA 0 of the fused
  * forward kernel (tools/trace_fwd.py); NULL disables it. */
