@@ -306,3 +306,49 @@ def test_config1_script_computes_what_the_modules_compute(tiny_min):
     for k, v in model.named_parameters():
         assert float((grads[k] - v.grad).abs().max()) <= 1e-4 * float(v.grad.abs().max()) + 1e-9, k
     close(O.mse2psnr(loss.detach()), M.mse2psnr(loss.detach()), rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ edge cases the fixtures do not hold
+def test_edge_cases_agree_bit_for_bit(R):
+    """per-ray near / far tensors with jitter, a scaled (non-orthonormal) pose, L = 0, never-taken and early skips, unsorted depths, a
+    zero-length direction, both backgrounds, enormous and infinite densities: the oracle equals the reference exactly on all of them"""
+    g = torch.Generator().manual_seed(90)
+    ro, rd = torch.randn(9, 3, generator=g), torch.randn(9, 3, generator=g)
+    near = torch.rand(9, 1, generator=g) + 1.0
+    far = near + 1.0 + 4.0 * torch.rand(9, 1, generator=g)
+    torch.manual_seed(91)
+    rz, rpts = R.sampling.stratified_samples(near, far, 12, ro, rd, True)
+    torch.manual_seed(91)
+    z, pts = O.stratified(near, far, 12, ro, rd, torch.rand(9, 12))
+    assert torch.equal(z, rz) and torch.equal(pts, rpts)
+    pose = some_pose(92)
+    pose[:3, :3] *= 2.5
+    (o1, d1), (o2, d2) = O.get_rays(6, 5, 7.0, pose), R.rays.get_rays(6, 5, 7.0, pose)
+    assert torch.equal(o1, o2) and torch.allclose(d1, d2, rtol=1e-6, atol=1e-7)
+    x = torch.randn(4, 3, generator=g)
+    assert torch.equal(O.posenc(x, 0, True), R.encoding.PositionalEncoding(0, True)(x))
+    for cfg in [(27, 16, 3, 1), (27, 16, 3, 5)]:                 # skip after the first layer / never
+        torch.manual_seed(93)
+        ref = R.nerf.TinyNeRF(*cfg)
+        p = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+        xin = torch.randn(7, 27, generator=g)
+        with torch.no_grad():
+            rc, rs = ref(xin)
+        c, s = O.mlp_forward(p, xin, cfg[2], cfg[3])
+        close(c, rc, rtol=2e-6, atol=2e-7)
+        close(s, rs, rtol=2e-6, atol=2e-6)
+    with pytest.raises(RuntimeError):                            # skip_at == depth: the heads get hidden + in_dim features
+        R.nerf.TinyNeRF(27, 16, 1, 1)(torch.zeros(2, 27))
+    n, S = 5, 6
+    rgb, sig = torch.rand(n, S, 3, generator=g), 3.0 * torch.rand(n, S, 1, generator=g)
+    zz = 2.0 + 4.0 * torch.rand(n, S, generator=g)               # NOT sorted: negative deltas
+    dirs = torch.randn(n, 3, generator=g)
+    dirs[0] = 0.0                                                # zero-length direction: every delta is 0
+    for white in (True, False):
+        for a, b in zip(O.composite(rgb, sig, zz, dirs, white), R.volume.volume_render(rgb, sig, zz, dirs, white)):
+            assert torch.equal(a, b)
+    sig[1], sig[2] = 1e30, float("inf")
+    zs = torch.sort(zz, dim=1).values
+    for a, b in zip(O.composite(rgb, sig, zs, dirs, True), R.volume.volume_render(rgb, sig, zs, dirs, True)):
+        assert torch.allclose(a, b, rtol=0, atol=0, equal_nan=True)
+    close(O.mse2psnr(torch.tensor(-1.0)), R.utils.mse2psnr(torch.tensor(-1.0)))       # clamped at 1e-10: 100 dB
