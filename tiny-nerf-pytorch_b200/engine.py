@@ -265,7 +265,12 @@ class Trainer:
 
         self.tile_order = None
         if _TILE_ORDER and self.prec == E.PREC_F16_TC:
-            self.calibrate_tile_order()
+            try:
+                self.calibrate_tile_order()
+            except Exception as e:  # noqa: BLE001  (an optimisation only: the identity dealing is always correct)
+                print(f"[tnerf] tile-order calibration failed ({type(e).__name__}: {e}); keeping the identity dealing", flush=True)
+                E.lib().tnerf_set_tile_order(self.h.h, None, 0)
+                self.tile_order = None
 
     # ---- SM-speed-aware tile dealing ---------------------------------------------------------------
     def calibrate_tile_order(self, reps: int = 3, force: bool = False):
